@@ -1,0 +1,181 @@
+"""ctypes front-end of the CPU oracle (oracle/b2t_oracle.c).  TEST INFRASTRUCTURE ONLY -- see the C file's header.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+import ctypes, json, os, re, subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+_RANGES = os.path.join(_HERE, "..", "tokenizers_b200", "csrc", "unicode_ranges.inc")
+
+PT_GPT2, PT_LLAMA3, PT_WHITESPACE, PT_BYTELEVEL_NOREGEX = 0, 1, 2, 3
+MODEL_BPE, MODEL_WORDPIECE = 0, 1
+OFF_BYTE, OFF_CHAR = 0, 1
+
+LLAMA3_PATTERN = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*"
+                  r"|\s*[\r\n]+|\s+(?!\S)|\s+")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "b2t_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        L.orc_create.restype = ctypes.c_void_p
+        L.orc_create.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_uint32] + [ctypes.c_void_p] * 3 + \
+            [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p,
+             ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32]
+        L.orc_destroy.argtypes = [ctypes.c_void_p]
+        L.orc_encode_batch.restype = ctypes.c_int
+        L.orc_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int]
+        L.orc_n_tokens.restype = ctypes.c_uint64
+        L.orc_n_tokens.argtypes = [ctypes.c_void_p]
+        for f in ("orc_ids", "orc_offsets", "orc_word_ids", "orc_row_ptr"):
+            getattr(L, f).restype = ctypes.c_void_p
+            getattr(L, f).argtypes = [ctypes.c_void_p]
+        L.orc_pretokenize.restype = ctypes.c_uint32
+        L.orc_pretokenize.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32]
+        _lib = L
+    return _lib
+
+
+_tables = {}
+
+
+def class_table(scheme):
+    """0x110000-entry uint8 class table. scheme 'onig': 1=\\p{L} 2=\\p{N} 3=\\s 0=other; 'rust': 1=\\w 3=\\s 0=other."""
+    if scheme not in _tables:
+        txt = open(_RANGES).read()
+        def ranges(name):
+            body = re.search(r"%s\[\]\[2\] = \{(.*?)\};" % name, txt, re.S).group(1)
+            return [(int(a, 16), int(b, 16)) for a, b in re.findall(r"\{0x([0-9A-F]+),0x([0-9A-F]+)\}", body)]
+        t = np.zeros(0x110000, dtype=np.uint8)
+        if scheme == "onig":
+            for name, v in (("B2T_ONIG_L", 1), ("B2T_ONIG_N", 2), ("B2T_ONIG_S", 3)):
+                for a, b in ranges(name):
+                    t[a:b + 1] = v
+        else:
+            for name, v in (("B2T_RUST_W", 1), ("B2T_RUST_S", 3)):
+                for a, b in ranges(name):
+                    t[a:b + 1] = v
+        _tables[scheme] = t
+    return _tables[scheme]
+
+
+def _pack(strings):
+    bs = [s.encode("utf-8") for s in strings]
+    off = np.zeros(len(bs) + 1, dtype=np.uint32)
+    np.cumsum([len(b) for b in bs], out=off[1:])
+    return np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8).copy(), off
+
+
+def parse_config(js):
+    """tokenizer.json dict -> dict(model, pretok, add_prefix_space, ignore_merges, ...) or raise ValueError."""
+    m, pt = js["model"], js.get("pre_tokenizer")
+    cfg = dict(add_prefix_space=0, ignore_merges=0, unk=None, prefix="", max_chars=100, merges=[])
+    if js.get("normalizer") is not None:
+        raise ValueError("normalizers are host-side and out of scope")
+    if pt is None:
+        raise ValueError("no pre_tokenizer")
+    if pt["type"] == "ByteLevel":
+        cfg["pretok"] = PT_GPT2 if pt.get("use_regex", True) else PT_BYTELEVEL_NOREGEX
+        cfg["add_prefix_space"] = int(pt.get("add_prefix_space", True))
+    elif pt["type"] == "Whitespace":
+        cfg["pretok"] = PT_WHITESPACE
+    elif pt["type"] == "Sequence":
+        a, b = pt["pretokenizers"]
+        ok = (a["type"] == "Split" and a["pattern"].get("Regex") == LLAMA3_PATTERN and a["behavior"] == "Isolated"
+              and not a.get("invert", False) and b["type"] == "ByteLevel" and not b.get("use_regex", True)
+              and not b.get("add_prefix_space", True))
+        if not ok:
+            raise ValueError("unsupported Sequence pre_tokenizer")
+        cfg["pretok"] = PT_LLAMA3
+    else:
+        raise ValueError("unsupported pre_tokenizer " + pt["type"])
+    if m["type"] == "BPE":
+        cfg["model"] = MODEL_BPE
+        if m.get("dropout") or m.get("unk_token") or m.get("continuing_subword_prefix") or m.get("end_of_word_suffix") \
+                or m.get("byte_fallback") or cfg["pretok"] == PT_WHITESPACE:
+            raise ValueError("unsupported BPE options")
+        cfg["ignore_merges"] = int(m.get("ignore_merges", False))
+        cfg["merges"] = [tuple(x.split(" ")) if isinstance(x, str) else tuple(x) for x in m["merges"]]
+    elif m["type"] == "WordPiece":
+        cfg["model"] = MODEL_WORDPIECE
+        if cfg["pretok"] != PT_WHITESPACE:
+            raise ValueError("WordPiece is supported behind Whitespace only")
+        cfg["unk"] = m["unk_token"]; cfg["prefix"] = m["continuing_subword_prefix"]; cfg["max_chars"] = m["max_input_chars_per_word"]
+    else:
+        raise ValueError("unsupported model " + m["type"])
+    cfg["vocab"] = m["vocab"]
+    return cfg
+
+
+class Oracle:
+    def __init__(self, tokenizer_json):
+        js = json.loads(tokenizer_json) if isinstance(tokenizer_json, (str, bytes)) else tokenizer_json
+        c = parse_config(js)
+        self.cfg = c
+        toks = list(c["vocab"].keys())
+        self._vb, self._vo = _pack(toks)
+        self._vi = np.array([c["vocab"][t] for t in toks], dtype=np.uint32)
+        flat = [s for ab in c["merges"] for s in ab]
+        self._mb, self._mo = _pack(flat)
+        self._cls = class_table("rust" if c["pretok"] == PT_WHITESPACE else "onig")
+        err = ctypes.create_string_buffer(256)
+        unk = c["unk"].encode() if c["unk"] is not None else None
+        pre = c["prefix"].encode()
+        self._h = lib().orc_create(c["model"], c["pretok"], c["add_prefix_space"], c["ignore_merges"], self._cls.ctypes.data,
+                                   len(toks), self._vb.ctypes.data, self._vo.ctypes.data, self._vi.ctypes.data,
+                                   len(c["merges"]), self._mb.ctypes.data, self._mo.ctypes.data,
+                                   unk, len(unk) if unk else 0, pre, len(pre), c["max_chars"], err, 256)
+        if not self._h:
+            raise ValueError(err.value.decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_destroy(self._h); self._h = None
+
+    def encode_batch_csr(self, data, doc_off, offset_type=OFF_CHAR):
+        """data: np.uint8[N]; doc_off: np.uint64[n+1] -> (ids u32[T], offsets u32[T,2], word_ids u32[T], row_ptr u64[n+1])."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        n = len(doc_off) - 1
+        base = data.ctypes.data if data.size else 0
+        rc = lib().orc_encode_batch(self._h, base, doc_off.ctypes.data, n, offset_type)
+        if rc != 0:
+            raise RuntimeError("oracle: encode failed (missing [UNK] token)")
+        T = lib().orc_n_tokens(self._h)
+        def view(ptr, count, dt):
+            if count == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(count * np.dtype(dt).itemsize,)).view(dt).copy()
+        ids = view(lib().orc_ids(self._h), T, np.uint32)
+        offs = view(lib().orc_offsets(self._h), 2 * T, np.uint32).reshape(-1, 2)
+        wid = view(lib().orc_word_ids(self._h), T, np.uint32)
+        rp = view(lib().orc_row_ptr(self._h), n + 1, np.uint64)
+        return ids, offs, wid, rp
+
+    def encode_batch(self, docs, offset_type=OFF_CHAR):
+        bs = [d.encode("utf-8") for d in docs]
+        off = np.zeros(len(bs) + 1, dtype=np.uint64)
+        if bs:
+            np.cumsum([len(b) for b in bs], out=off[1:])
+        data = np.frombuffer(b"".join(bs), dtype=np.uint8)
+        return self.encode_batch_csr(data, off, offset_type)
+
+    def pre_tokenize(self, doc):
+        """[(start_byte, end_byte)] in original bytes, like pre_tokenize_str's offsets but in bytes."""
+        b = np.frombuffer(doc.encode("utf-8"), dtype=np.uint8)
+        out = np.zeros(2 * (len(b) + 2), dtype=np.uint32)
+        k = lib().orc_pretokenize(self._h, b.ctypes.data if b.size else 0, len(b), out.ctypes.data, len(b) + 2)
+        return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(k)]
