@@ -1,0 +1,140 @@
+/* b2t.h -- C ABI of the B200 batched tokenization engine (libb2t.so).
+ *
+ * Drop-in boundary for ONE path of huggingface/tokenizers: `Tokenizer::encode_batch` for ByteLevel-BPE
+ * (GPT-2 / Llama-3 style) and Whitespace + WordPiece.  Each entry point names the reference interface it
+ * replaces (paths relative to /root/reference/tokenizers/src unless noted).  A Rust host would bind this file
+ * with an `extern "C"` block; the Python shim in tokenizers_b200/ binds it with ctypes.
+ *
+ * Conventions: plain pointers and sizes only; every function returns a b2t_status value (0 = ok) unless noted; the
+ * message of the last error on the calling thread is available from b2t_last_error().  No CPU fallback exists:
+ * configurations outside the supported set fail with B2T_ERR_UNSUPPORTED, and every encode entry point needs a
+ * CUDA device (sm_100a).
+ */
+#ifndef B2T_H_
+#define B2T_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2t_engine b2t_engine;
+typedef struct b2t_result b2t_result;
+
+typedef enum {
+  B2T_OK = 0,
+  B2T_ERR_INVALID = 1,     /* bad argument */
+  B2T_ERR_UNSUPPORTED = 2, /* configuration outside the hot path (the reference would handle it on CPU) */
+  B2T_ERR_CUDA = 3,        /* CUDA runtime error, message has the details */
+  B2T_ERR_VOCAB = 4,       /* merge token out of vocabulary / missing [UNK] (models/bpe/mod.rs:12-36, wordpiece/mod.rs:17-22) */
+  B2T_ERR_TOO_LARGE = 5    /* batch exceeds the per-call device limits */
+} b2t_status;
+
+/* models::ModelWrapper variants on the path (models/mod.rs:60-68) */
+typedef enum { B2T_MODEL_BPE = 0, B2T_MODEL_WORDPIECE = 1 } b2t_model_kind;
+
+/* pre_tokenizers::PreTokenizerWrapper configurations on the path (pre_tokenizers/mod.rs:28-62) */
+typedef enum {
+  B2T_PRETOK_BYTELEVEL = 0,         /* ByteLevel{use_regex=true}: GPT-2 pattern, byte_level.rs:43-46,119-148 */
+  B2T_PRETOK_LLAMA3 = 1,            /* Sequence[Split(tiktoken pattern, Isolated), ByteLevel{use_regex=false}] */
+  B2T_PRETOK_WHITESPACE = 2,        /* Whitespace: whitespace.rs:20-29 */
+  B2T_PRETOK_BYTELEVEL_NOREGEX = 3  /* ByteLevel{use_regex=false}: the whole sequence is one pre-token */
+} b2t_pretok_kind;
+
+/* Engine configuration = what `TokenizerBuilder` (tokenizer/mod.rs:315-437) receives for this path:
+ * BPE::builder().vocab_and_merges(..).ignore_merges(..) (models/bpe/model.rs:36-210) or
+ * WordPiece::builder().vocab(..).unk_token(..).continuing_subword_prefix(..).max_input_chars_per_word(..)
+ * (models/wordpiece/mod.rs:40-120), plus the pre-tokenizer flags. Strings are UTF-8, exactly as in tokenizer.json. */
+typedef struct {
+  uint32_t struct_size; /* sizeof(b2t_config), for ABI evolution */
+  int32_t model;        /* b2t_model_kind */
+  int32_t pretok;       /* b2t_pretok_kind */
+  int32_t add_prefix_space; /* ByteLevel.add_prefix_space (byte_level.rs:57-68) */
+  int32_t ignore_merges;    /* BPE.ignore_merges (models/bpe/model.rs:558-567) */
+  /* vocabulary: n_vocab token strings, packed back to back; token i = vocab_bytes[vocab_off[i] .. vocab_off[i+1]) */
+  uint32_t n_vocab;
+  const uint8_t* vocab_bytes;
+  const uint32_t* vocab_off; /* n_vocab + 1 */
+  const uint32_t* vocab_ids; /* n_vocab */
+  /* BPE merges in rank order: merge i = (string 2i, string 2i+1) of the packed list (models/bpe/model.rs:252-275) */
+  uint32_t n_merges;
+  const uint8_t* merge_bytes;
+  const uint32_t* merge_off; /* 2 * n_merges + 1 */
+  /* WordPiece */
+  const char* unk_token;                 /* NUL-terminated, may be NULL for BPE */
+  const char* continuing_subword_prefix; /* NUL-terminated, e.g. "##" */
+  uint32_t max_input_chars_per_word;     /* 100 in bert */
+  int32_t device;                        /* CUDA device ordinal, -1 = current device */
+} b2t_config;
+
+/* encode flags */
+enum {
+  B2T_WANT_OFFSETS = 1u,   /* produce (start, end) per token */
+  B2T_WANT_WORD_IDS = 2u,  /* produce the pre-token ordinal per token (Encoding.words, tokenizer/pre_tokenizer.rs:252-256) */
+  B2T_OFFSETS_BYTES = 4u   /* OffsetType::Byte (Rust encode_batch) instead of OffsetType::Char (encode_batch_char_offsets,
+                              what the Python binding always uses: bindings/python/src/tokenizer.rs:1332) */
+};
+
+/* Replaces TokenizerBuilder::build for the path.  The tables are uploaded to the device once; the engine is
+ * immutable afterwards and may be used from several host threads (calls serialise on an internal mutex). */
+int b2t_engine_create(const b2t_config* cfg, b2t_engine** out);
+void b2t_engine_destroy(b2t_engine* e);
+
+/* Replaces TokenizerImpl::encode_batch / encode_batch_char_offsets / encode_batch_fast (tokenizer/mod.rs:1337-1401)
+ * for raw (not pre-tokenized) single sequences with add_special_tokens=false.  HOST buffers: `bytes` holds the
+ * documents back to back, document d = bytes[doc_off[d] .. doc_off[d+1]); doc_off[0] must be 0.  The call copies the
+ * input to the device in chunks, runs the kernels and copies the token CSR back into pinned host memory owned by
+ * the result.  flags = 0 is the encode_batch_fast analogue (ids only). */
+int b2t_encode_batch(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, uint32_t flags,
+                     b2t_result** out);
+
+/* Same, with the packed batch already in device memory (d_bytes 16-byte aligned, n_bytes = doc_off[n_docs] < 2^31) and the
+ * result left in device memory (owned by the engine, valid until the next call on this engine or b2t_result_free).
+ * `stream` is a cudaStream_t (NULL = the engine's own stream); the call is asynchronous with respect to the host
+ * except for one small device-to-host read of the token count.  This is the entry point the roofline numbers use. */
+int b2t_encode_batch_device(b2t_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint64_t* d_doc_off,
+                            uint32_t n_docs, uint32_t flags, void* stream, b2t_result** out);
+
+/* Replaces PreTokenizer::pre_tokenize (tokenizer/mod.rs:65-67) for a batch: the splits of every document as
+ * (start, end) BYTE offsets into the document (offsets[2k], offsets[2k+1]); row_ptr delimits documents.  ids and
+ * word_ids are absent.  Host buffers in, pinned host buffers out.  (With add_prefix_space the split that contains the
+ * inserted space starts at the first byte of the document.) */
+int b2t_pre_tokenize_batch(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs,
+                           b2t_result** out);
+
+/* Result accessors (Encoding fields of tokenizer/encoding.rs:11-31 as one CSR over the batch).  Pointers are host
+ * pointers for b2t_encode_batch / b2t_pre_tokenize_batch and device pointers for b2t_encode_batch_device. */
+uint64_t b2t_result_n_tokens(const b2t_result* r);
+uint32_t b2t_result_n_docs(const b2t_result* r);
+int b2t_result_on_device(const b2t_result* r);
+const uint32_t* b2t_result_ids(const b2t_result* r);      /* n_tokens */
+const uint32_t* b2t_result_offsets(const b2t_result* r);  /* 2 * n_tokens, or NULL */
+const uint32_t* b2t_result_word_ids(const b2t_result* r); /* n_tokens, or NULL */
+const uint64_t* b2t_result_row_ptr(const b2t_result* r);  /* n_docs + 1 */
+void b2t_result_free(b2t_result* r);
+
+/* Pinned host memory for callers that want b2t_encode_batch to copy straight from their buffer. */
+int b2t_host_alloc(size_t bytes, void** out);
+void b2t_host_free(void* p);
+
+/* Per-kernel device timings of the last b2t_encode_batch_device call when profiling is on (CUDA events on the
+ * launch stream).  names/ms arrays of capacity cap; returns the number of kernels launched by that call. */
+int b2t_engine_set_profiling(b2t_engine* e, int on);
+int b2t_engine_last_kernels(const b2t_engine* e, const char** names, float* ms, int cap);
+
+/* Unicode class tables the scan kernels use, one byte per code point (0x110000 entries):
+ * scheme 0 (Oniguruma: ByteLevel / Split): 1 = \p{L}, 2 = \p{N}, 3 = \s, 0 = other;
+ * scheme 1 (Rust regex: Whitespace):       1 = \w, 3 = \s, 0 = other.  Host only, no device needed. */
+int b2t_unicode_class_table(int scheme, uint8_t* out);
+
+/* Thread-local message of the last failing call. */
+const char* b2t_last_error(void);
+/* Library version string. */
+const char* b2t_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2T_H_ */

@@ -37,9 +37,26 @@ def rand_doc(rng, max_len=60):
     return "".join(out)
 
 
+def run_doc(rng):
+    """Long runs (newlines, spaces, digits, letters, punctuation) that cross chunk / window / page edges."""
+    out = []
+    for _ in range(rng.randint(1, 6)):
+        kind = rng.random()
+        n = rng.choice([1, 2, 3, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 100, 130, rng.randint(1, 300)])
+        if kind < 0.2: out.append(rng.choice(["\n", "\r\n", "\r", "\n\n"]) * n)
+        elif kind < 0.4: out.append(rng.choice([" ", "\t", "\xa0", "\u3000", " \t"]) * n)
+        elif kind < 0.55: out.append("".join(rng.choice(" \n\t\r\xa0") for _ in range(n)))
+        elif kind < 0.7: out.append("".join(rng.choice("0123456789٣５") for _ in range(n)))
+        elif kind < 0.8: out.append(rng.choice(["a", "é", "中", "ab"]) * n)
+        elif kind < 0.9: out.append(rng.choice(["!", "'", "-", "…", "!'"]) * n)
+        else: out.append(rng.choice(WORDS))
+        if rng.random() < 0.5: out.append(rng.choice(["x", "!", "1", "'s", " ", "", "\n", " x", "é"]))
+    return "".join(out)
+
+
 def rand_docs(seed, n, max_len=60):
     rng = random.Random(seed)
-    docs = [rand_doc(rng, max_len) for _ in range(n)]
+    docs = [run_doc(rng) if rng.random() < 0.15 else rand_doc(rng, max_len) for _ in range(n)]
     # always include the empty doc and a few fixed nasties
     docs[: min(n, 6)] = ["", " ", "\n", "'s", "a", "  "][: min(n, 6)]
     return docs

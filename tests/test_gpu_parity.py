@@ -1,0 +1,168 @@
+"""GPU (-m gpu): the CUDA path through the C ABI against the committed golden vectors, the oracle, and -- where it is
+importable -- the reference implementation itself.  Bit-exact: ids, (char_start, char_end) offsets, word ids, row_ptr."""
+import ctypes, json, os
+import numpy as np
+import pytest
+import helpers, fuzzgen, corpus
+
+pytestmark = pytest.mark.gpu
+
+from tokenizers_b200 import Tokenizer, UnsupportedConfig, _lib  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+ASSET_NAMES = ["gpt2_style", "llama3_style", "wordpiece"]
+_engines = {}
+
+
+def engine(name_or_json):
+    if name_or_json not in _engines:
+        js = helpers.asset_json(name_or_json) if name_or_json in ASSET_NAMES else name_or_json
+        _engines[name_or_json] = (Tokenizer.from_str(js), orc.Oracle(js), js)
+    return _engines[name_or_json]
+
+
+def gpu_csr(tok, docs, **kw):
+    data, off = helpers.pack_docs(docs)
+    be = tok.encode_batch_csr(data, off, **kw)
+    return be.ids, be.offsets, be.word_ids, be.row_ptr
+
+
+@pytest.mark.parametrize("name", [n for n in helpers.GOLDEN_NAMES if n != "gpt2_prefix"])
+def test_gpu_matches_reference_golden(name):
+    tj, cases = helpers.load_golden(name)
+    tok = Tokenizer.from_str(tj)
+    docs = [c["input"] for c in cases]
+    helpers.assert_csr_equal(gpu_csr(tok, docs), helpers.cases_to_csr(cases), docs, f"gpu vs golden_{name}")
+
+
+def test_prefix_space_is_refused_not_faked():
+    tj, _ = helpers.load_golden("gpt2_prefix")
+    with pytest.raises(UnsupportedConfig):
+        Tokenizer.from_str(tj)
+
+
+@pytest.mark.parametrize("name", ASSET_NAMES)
+def test_gpu_matches_oracle_fuzz(name):
+    tok, o, _ = engine(name)
+    for seed in range(6):
+        docs = fuzzgen.rand_docs(5000 + seed, 1500, max_len=60 if seed % 2 else 300)
+        helpers.assert_csr_equal(gpu_csr(tok, docs), o.encode_batch(docs), docs, f"{name} fuzz seed {seed}")
+
+
+@pytest.mark.parametrize("name", ASSET_NAMES)
+@pytest.mark.parametrize("kind", [1, 2, 4])
+def test_gpu_matches_oracle_corpus(name, kind):
+    tok, o, _ = engine(name)
+    data, off = corpus.generate(kind, 10 + kind, 0, 4000)
+    be = tok.encode_batch_csr(data, off)
+    exp = o.encode_batch_csr(data, off)
+    helpers.assert_csr_equal((be.ids, be.offsets, be.word_ids, be.row_ptr), exp, corpus.to_strings(data, off), f"{name} corpus {kind}")
+
+
+@pytest.mark.parametrize("name", ASSET_NAMES)
+def test_pre_tokenize_matches_oracle(name):
+    tok, o, _ = engine(name)
+    docs = fuzzgen.rand_docs(77, 800, max_len=80)
+    got = tok.pre_tokenize_batch(docs)
+    for d, g in zip(docs, got):
+        assert g == o.pre_tokenize(d), repr(d)
+
+
+@pytest.mark.parametrize("name", ASSET_NAMES)
+def test_flags_ids_only_and_byte_offsets(name):
+    tok, o, _ = engine(name)
+    docs = fuzzgen.rand_docs(91, 700, max_len=80)
+    exp_c = o.encode_batch(docs)
+    exp_b = o.encode_batch(docs, offset_type=orc.OFF_BYTE)
+    ids, offs, wid, rp = gpu_csr(tok, docs, offsets=False, word_ids=False)
+    assert offs is None and wid is None
+    assert np.array_equal(ids, exp_c[0]) and np.array_equal(rp, exp_c[3])
+    helpers.assert_csr_equal(gpu_csr(tok, docs, byte_offsets=True), exp_b, docs, f"{name} byte offsets")
+
+
+@pytest.mark.parametrize("name", ASSET_NAMES)
+def test_multi_chunk_host_pipeline(name):
+    """Tiny chunks force many in-flight chunks through the 3-slot pipeline; the result must not change."""
+    _, o, js = engine(name)
+    os.environ["B2T_CHUNK_BYTES"] = "3000"
+    try:
+        tok = Tokenizer.from_str(js)
+    finally:
+        del os.environ["B2T_CHUNK_BYTES"]
+    data, off = corpus.generate(2, 5, 0, 700)
+    docs = corpus.to_strings(data, off) + ["", "", "x"]
+    helpers.assert_csr_equal(gpu_csr(tok, docs), o.encode_batch(docs), docs, f"{name} multi-chunk")
+
+
+def test_edge_batches():
+    tok, o, _ = engine("gpt2_style")
+    for docs in ([], [""], ["", "", ""], ["a"], ["", "a", ""], ["é" * 700], [" " * 2047, "b"], ["a" * 2048, "b" * 2049, "c"],
+                 ["x" * 31 + "é", "\n" * 40], ["ab " * 1000]):
+        helpers.assert_csr_equal(gpu_csr(tok, docs), o.encode_batch(docs), docs, f"edge {[len(d) for d in docs]}")
+
+
+def test_device_resident_entry_point():
+    import torch
+    tok, o, _ = engine("gpt2_style")
+    data, off = corpus.generate(2, 21, 0, 3000)
+    d_bytes = torch.from_numpy(data.copy()).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    L = _lib.lib()
+    res = ctypes.c_void_p()
+    flags = _lib.WANT_OFFSETS | _lib.WANT_WORD_IDS
+    _lib.check(L.b2t_encode_batch_device(tok.handle, d_bytes.data_ptr(), int(off[-1]), d_off.data_ptr(), len(off) - 1, flags, None, ctypes.byref(res)))
+    assert L.b2t_result_on_device(res) == 1
+    T = L.b2t_result_n_tokens(res)
+
+    def dev(ptr, count, dtype):
+        out = torch.empty(count, dtype=dtype, device="cuda")
+        torch.cuda.synchronize()
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(count * out.element_size()), 3)
+        return out.cpu().numpy()
+    ids = dev(L.b2t_result_ids(res), T, torch.int32).view(np.uint32)
+    offs = dev(L.b2t_result_offsets(res), 2 * T, torch.int32).view(np.uint32).reshape(-1, 2)
+    wid = dev(L.b2t_result_word_ids(res), T, torch.int32).view(np.uint32)
+    rp = dev(L.b2t_result_row_ptr(res), len(off), torch.int64).view(np.uint64)
+    L.b2t_result_free(res)
+    helpers.assert_csr_equal((ids, offs, wid, rp), o.encode_batch_csr(data, off), None, "device entry point")
+
+
+@pytest.mark.parametrize("name", ASSET_NAMES)
+def test_gpu_matches_reference_wheel_large(name):
+    tk = helpers.wheel()
+    if tk is None:
+        pytest.skip("reference wheel not importable on this box")
+    tok, _, js = engine(name)
+    ref = tk.Tokenizer.from_str(js)
+    data, off = corpus.generate(4 if name == "wordpiece" else 2, 99, 0, 40000)
+    docs = corpus.to_strings(data, off)
+    be = tok.encode_batch_csr(data, off)
+    helpers.assert_csr_equal((be.ids, be.offsets, be.word_ids, be.row_ptr), helpers.wheel_csr(ref, docs), docs, f"{name} vs wheel")
+
+
+def test_full_size_properties():
+    """256 MB of the config-2 corpus: size-independent properties + oracle parity on a sampled slice."""
+    tok, o, _ = engine("gpt2_style")
+    data, off = corpus.generate(2, 2, 0, 1 << 19, max_bytes=256 << 20)
+    be = tok.encode_batch_csr(data, off)
+    rp = be.row_ptr
+    assert rp[0] == 0 and np.all(np.diff(rp.astype(np.int64)) >= 0) and int(rp[-1]) == len(be.ids)
+    assert be.ids.max() < tok.get_vocab_size()
+    # offsets: within a doc, starts are non-decreasing, end >= start, and the last token ends at the doc's char count
+    st, en = be.offsets[:, 0].astype(np.int64), be.offsets[:, 1].astype(np.int64)
+    assert np.all(en >= st)
+    lead = (data & 0xC0) != 0x80
+    cum = np.concatenate([[0], np.cumsum(lead)])
+    nchar = cum[off[1:].astype(np.int64)] - cum[off[:-1].astype(np.int64)]
+    last = rp[1:].astype(np.int64) - 1
+    nonempty = rp[1:] > rp[:-1]
+    assert np.array_equal(en[last[nonempty]], nchar[nonempty])
+    # sampled oracle parity: 3 slices of 2000 docs
+    n = len(off) - 1
+    for a in (0, n // 2, n - 2000):
+        sl_off = (off[a:a + 2001] - off[a]).astype(np.uint64)
+        sl = data[int(off[a]):int(off[a + 2000])]
+        exp = o.encode_batch_csr(sl, sl_off)
+        t0, t1 = int(rp[a]), int(rp[a + 2000])
+        got = (be.ids[t0:t1], be.offsets[t0:t1], be.word_ids[t0:t1], rp[a:a + 2001] - rp[a])
+        helpers.assert_csr_equal(got, exp, None, f"slice at doc {a}")

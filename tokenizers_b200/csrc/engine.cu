@@ -1,0 +1,569 @@
+// engine.cu -- the C ABI of include/b2t.h: engine construction, the device pipeline (K0 doc_mark -> K1 pretok_scan ->
+// K1b page_scan -> K2 model_tile) and the chunked host<->device pipeline of b2t_encode_batch.
+//
+// This is the batch-level seam of the reference (tokenizer/mod.rs:1337-1401 encode_batch*): one call = one batch,
+// results in input order, any failure fails the whole batch.  There is NO CPU implementation behind these entry
+// points; without a CUDA device they fail with B2T_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b2t.h"
+#include "host_tables.h"
+#include "model_kernels.cuh"
+#include "pretok_kernels.cuh"
+
+using namespace b2t;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t _e = (call);                                                                                  \
+    if (_e != cudaSuccess) return fail(B2T_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* b2t_last_error(void) { return g_err; }
+extern "C" const char* b2t_version(void) { return "tokenizers_b200 0.1 (sm_100a)"; }
+
+extern "C" int b2t_unicode_class_table(int scheme, uint8_t* out) {
+  if (!out || (scheme != 0 && scheme != 1)) return fail(B2T_ERR_INVALID, "b2t_unicode_class_table: bad arguments");
+  unicode_class_table(scheme, out);
+  return B2T_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ buffers
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return B2T_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CU(cudaMalloc(&p, want));
+    cap = want;
+    return B2T_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes, bool keep) {
+    if (bytes <= cap) return B2T_OK;
+    size_t want = bytes + bytes / 4 + 4096;
+    void* q = nullptr;
+    CU(cudaHostAlloc(&q, want, cudaHostAllocDefault));
+    if (p) { if (keep) memcpy(q, p, cap); cudaFreeHost(p); }
+    p = q; cap = want;
+    return B2T_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Device-side state of one in-flight batch (or chunk).
+struct Workspace {
+  DevBuf bytes, doc_off;              // only used by the host path (inputs staged on the device)
+  DevBuf doc_bits, start_bits, drop_bits, page_sum, page_carry, page_first_doc, tile_state, ctl;
+  DevBuf ids, offsets, word_ids, row_ptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  PinBuf h_ctl;                        // total tokens + error flag read back
+  void release() {
+    bytes.release(); doc_off.release(); doc_bits.release(); start_bits.release(); drop_bits.release(); page_sum.release();
+    page_carry.release(); page_first_doc.release(); tile_state.release(); ctl.release(); ids.release(); offsets.release();
+    word_ids.release(); row_ptr.release(); h_ctl.release();
+    if (stream) cudaStreamDestroy(stream);
+    if (done) cudaEventDestroy(done);
+    stream = nullptr; done = nullptr;
+  }
+};
+
+struct b2t_result {
+  b2t_engine* eng = nullptr;
+  int on_device = 0;
+  uint32_t n_docs = 0;
+  uint64_t n_tokens = 0;
+  const uint32_t* ids = nullptr; const uint32_t* offsets = nullptr; const uint32_t* word_ids = nullptr; const uint64_t* row_ptr = nullptr;
+  PinBuf h_ids, h_offsets, h_word_ids, h_row_ptr;  // host results own pinned memory (returned to the engine pool on free)
+};
+
+constexpr int NSLOT = 3;
+constexpr int MAX_KERNEL_RECORDS = 16;
+
+struct b2t_engine {
+  int device = 0;
+  int model = 0, pretok = 0, add_prefix_space = 0;
+  int sm_count = 148;
+  DeviceTables dt;
+  DevBuf d_cls, d_byte_to_id, d_merge, d_word, d_pool, d_edge;
+  std::mutex mu;
+  Workspace dev_ws;          // b2t_encode_batch_device
+  Workspace slot[NSLOT];     // b2t_encode_batch chunks
+  cudaStream_t own_stream = nullptr;
+  size_t chunk_bytes = 64u << 20;
+  // pinned result pool
+  std::vector<b2t_result*> pool;
+  // profiling
+  int profiling = 0;
+  int n_rec = 0;
+  const char* rec_name[MAX_KERNEL_RECORDS];
+  cudaEvent_t rec_ev[MAX_KERNEL_RECORDS + 1];
+  bool rec_ev_made = false;
+  int last_launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ create / destroy
+template <class T>
+static int upload(DevBuf& b, const std::vector<T>& v) {
+  size_t bytes = v.size() * sizeof(T);
+  int rc = b.ensure(bytes ? bytes : 16);
+  if (rc) return rc;
+  if (bytes) CU(cudaMemcpy(b.p, v.data(), bytes, cudaMemcpyHostToDevice));
+  return B2T_OK;
+}
+
+extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
+  if (!cfg || !out) return fail(B2T_ERR_INVALID, "b2t_engine_create: null argument");
+  if (cfg->struct_size != sizeof(b2t_config)) return fail(B2T_ERR_INVALID, "b2t_engine_create: struct_size mismatch (%u != %zu)", cfg->struct_size, sizeof(b2t_config));
+  *out = nullptr;
+  if (cfg->model != B2T_MODEL_BPE && cfg->model != B2T_MODEL_WORDPIECE) return fail(B2T_ERR_UNSUPPORTED, "unsupported model kind %d", cfg->model);
+  if (cfg->pretok < 0 || cfg->pretok > 3) return fail(B2T_ERR_UNSUPPORTED, "unsupported pre-tokenizer kind %d", cfg->pretok);
+  if (cfg->model == B2T_MODEL_BPE && cfg->pretok == B2T_PRETOK_WHITESPACE)
+    return fail(B2T_ERR_UNSUPPORTED, "BPE is supported behind the ByteLevel pre-tokenizers only");
+  if (cfg->model == B2T_MODEL_WORDPIECE && cfg->pretok != B2T_PRETOK_WHITESPACE)
+    return fail(B2T_ERR_UNSUPPORTED, "WordPiece is supported behind the Whitespace pre-tokenizer only");
+  if (cfg->add_prefix_space && cfg->pretok != B2T_PRETOK_BYTELEVEL && cfg->pretok != B2T_PRETOK_BYTELEVEL_NOREGEX)
+    return fail(B2T_ERR_UNSUPPORTED, "add_prefix_space is only meaningful for a top-level ByteLevel pre-tokenizer");
+  if (cfg->add_prefix_space) return fail(B2T_ERR_UNSUPPORTED, "ByteLevel add_prefix_space=true is not on the device path yet");
+  if (!cfg->vocab_bytes || !cfg->vocab_off || !cfg->vocab_ids || cfg->n_vocab == 0) return fail(B2T_ERR_INVALID, "empty vocabulary");
+
+  HostTables ht;
+  bool vocab_err = false;
+  std::string msg = build_host_tables(cfg->model, cfg->pretok, cfg->ignore_merges, cfg->n_vocab, cfg->vocab_bytes, cfg->vocab_off,
+                                      cfg->vocab_ids, cfg->n_merges, cfg->merge_bytes, cfg->merge_off, cfg->unk_token,
+                                      cfg->continuing_subword_prefix, cfg->max_input_chars_per_word, &ht, &vocab_err);
+  if (!msg.empty()) return fail(vocab_err ? B2T_ERR_VOCAB : B2T_ERR_UNSUPPORTED, "%s", msg.c_str());
+
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(B2T_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU path", cudaGetErrorString(ce));
+  int dev = cfg->device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(B2T_ERR_INVALID, "device %d out of range (%d devices)", dev, ndev);
+  CU(cudaSetDevice(dev));
+
+  b2t_engine* e = new b2t_engine();
+  e->device = dev; e->model = cfg->model; e->pretok = cfg->pretok; e->add_prefix_space = cfg->add_prefix_space;
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (const char* cb = getenv("B2T_CHUNK_BYTES")) {  // host-path chunk size (tests use tiny chunks to exercise the pipeline)
+    long long v = atoll(cb);
+    if (v >= 1024 && v < (1ll << 31)) e->chunk_bytes = (size_t)v;
+  }
+  int rc = B2T_OK;
+  if ((rc = upload(e->d_cls, ht.cls_packed)) || (rc = upload(e->d_byte_to_id, ht.byte_to_id)) || (rc = upload(e->d_merge, ht.merge_tbl)) ||
+      (rc = upload(e->d_word, ht.word_tbl)) || (rc = upload(e->d_pool, ht.word_pool)) || (rc = upload(e->d_edge, ht.edge_tbl))) {
+    b2t_engine_destroy(e);
+    return rc;
+  }
+  memset(&e->dt, 0, sizeof(e->dt));
+  e->dt.byte_to_id = e->d_byte_to_id.as<uint32_t>();
+  e->dt.merge_tbl = e->d_merge.as<uint4>();
+  e->dt.merge_mask = ht.merge_tbl.empty() ? 0 : (uint32_t)ht.merge_tbl.size() - 1;
+  e->dt.word_tbl = e->d_word.as<uint4>();
+  e->dt.word_mask = ht.word_tbl.empty() ? 0 : (uint32_t)ht.word_tbl.size() - 1;
+  e->dt.word_pool = e->d_pool.as<uint8_t>();
+  e->dt.ignore_merges = cfg->ignore_merges ? 1 : 0;
+  e->dt.edge_tbl = e->d_edge.as<uint4>();
+  e->dt.edge_mask = ht.edge_tbl.empty() ? 0 : (uint32_t)ht.edge_tbl.size() - 1;
+  e->dt.unk_id = ht.unk_id;
+  e->dt.max_chars = ht.max_chars;
+  cudaError_t se = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+  if (se != cudaSuccess) { b2t_engine_destroy(e); return fail(B2T_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(se)); }
+  *out = e;
+  return B2T_OK;
+}
+
+extern "C" void b2t_engine_destroy(b2t_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  e->dev_ws.release();
+  for (auto& s : e->slot) s.release();
+  e->d_cls.release(); e->d_byte_to_id.release(); e->d_merge.release(); e->d_word.release(); e->d_pool.release(); e->d_edge.release();
+  for (b2t_result* r : e->pool) { r->h_ids.release(); r->h_offsets.release(); r->h_word_ids.release(); r->h_row_ptr.release(); delete r; }
+  if (e->rec_ev_made) for (auto& ev : e->rec_ev) cudaEventDestroy(ev);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+// ------------------------------------------------------------------------------------------------ device pipeline
+struct ctl_block {  // lives in ws.ctl
+  uint32_t ticket;
+  uint32_t err;
+  unsigned long long total;
+};
+
+template <int KIND>
+static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Workspace& ws, cudaStream_t st) {
+  constexpr int TC = 256;
+  const int64_t n_chunks = n / CHUNK + 1;
+  const int64_t n_tiles = (n_chunks + TC - 1) / TC;
+  int64_t grid = std::min<int64_t>(n_tiles, (int64_t)e->sm_count * 8);
+  pretok_scan_kernel<KIND, TC><<<(unsigned)grid, TC, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
+                                                             ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
+                                                             ws.page_sum.as<uint64_t>(), n_tiles);
+}
+
+static void rec(b2t_engine* e, cudaStream_t st, const char* name) {
+  // records the event that ENDS kernel `name` (event 0 is recorded before the first kernel)
+  if (!e->profiling) return;
+  if (name == nullptr) { e->n_rec = 0; cudaEventRecord(e->rec_ev[0], st); return; }
+  if (e->n_rec >= MAX_KERNEL_RECORDS) return;
+  e->rec_name[e->n_rec] = name;
+  cudaEventRecord(e->rec_ev[e->n_rec + 1], st);
+  e->n_rec++;
+}
+
+// Runs K0..K2 for a batch resident on the device.  Does not synchronise.  model_pass=false stops after K1b.
+static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_bytes, int64_t n, const uint64_t* d_doc_off,
+                               uint32_t n_docs, uint32_t flags, cudaStream_t st, bool model_pass) {
+  if (n >= (1ll << 31)) return fail(B2T_ERR_TOO_LARGE, "batch of %lld bytes exceeds the per-call limit of 2^31-1; split it", (long long)n);
+  const int64_t n_words = n / 32 + 2, n_pages = n / PAGE + 1;
+  int rc;
+  if ((rc = ws.doc_bits.ensure(n_words * 4)) || (rc = ws.start_bits.ensure(n_words * 4)) || (rc = ws.page_sum.ensure(n_pages * 8)) ||
+      (rc = ws.page_carry.ensure(n_pages * 8)) || (rc = ws.page_first_doc.ensure(n_pages * 4)) || (rc = ws.tile_state.ensure(n_pages * 8)) ||
+      (rc = ws.ctl.ensure(sizeof(ctl_block))) || (rc = ws.h_ctl.ensure(sizeof(ctl_block), false)))
+    return rc;
+  if (e->pretok == PT_WHITESPACE && (rc = ws.drop_bits.ensure(n_words * 4))) return rc;
+  if (model_pass) {
+    if ((rc = ws.ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.row_ptr.ensure(((size_t)n_docs + 1) * 8))) return rc;
+    if ((flags & B2T_WANT_OFFSETS) && (rc = ws.offsets.ensure((size_t)(n + 1) * 8))) return rc;
+    if ((flags & B2T_WANT_WORD_IDS) && (rc = ws.word_ids.ensure((size_t)(n + 1) * 4))) return rc;
+  }
+  CU(cudaMemsetAsync(ws.doc_bits.p, 0, n_words * 4, st));
+  CU(cudaMemsetAsync(ws.tile_state.p, 0, n_pages * 8, st));
+  CU(cudaMemsetAsync(ws.ctl.p, 0, sizeof(ctl_block), st));
+  e->last_launches = 0;
+  rec(e, st, nullptr);
+  doc_mark_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.doc_bits.as<uint32_t>(), ws.page_first_doc.as<uint32_t>());
+  rec(e, st, "doc_mark"); e->last_launches++;
+  switch (e->pretok) {
+    case PT_GPT2: launch_pretok<PT_GPT2>(e, d_bytes, n, ws, st); break;
+    case PT_LLAMA3: launch_pretok<PT_LLAMA3>(e, d_bytes, n, ws, st); break;
+    case PT_WHITESPACE: launch_pretok<PT_WHITESPACE>(e, d_bytes, n, ws, st); break;
+    default: launch_pretok<PT_NOREGEX>(e, d_bytes, n, ws, st); break;
+  }
+  rec(e, st, "pretok_scan"); e->last_launches++;
+  page_scan_kernel<<<1, 1024, 0, st>>>(ws.page_sum.as<uint64_t>(), ws.page_carry.as<uint64_t>(), n_pages);
+  rec(e, st, "page_scan"); e->last_launches++;
+  if (model_pass) {
+    ModelParams P;
+    P.bytes = d_bytes; P.n = n;
+    P.start_bits = ws.start_bits.as<uint32_t>(); P.drop_bits = ws.drop_bits.as<uint32_t>(); P.doc_bits = ws.doc_bits.as<uint32_t>();
+    P.page_carry = ws.page_carry.as<uint64_t>(); P.page_first_doc = ws.page_first_doc.as<uint32_t>();
+    P.doc_off = d_doc_off; P.n_docs = n_docs;
+    P.flags = ((flags & B2T_WANT_OFFSETS) ? F_OFFSETS : 0u) | ((flags & B2T_WANT_WORD_IDS) ? F_WORD_IDS : 0u) |
+              ((flags & B2T_OFFSETS_BYTES) ? F_BYTE_OFFSETS : 0u);
+    P.ids = ws.ids.as<uint32_t>(); P.offsets = ws.offsets.as<uint32_t>(); P.word_ids = ws.word_ids.as<uint32_t>();
+    P.row_ptr = ws.row_ptr.as<uint64_t>();
+    P.tile_state = ws.tile_state.as<unsigned long long>();
+    ctl_block* ctl = ws.ctl.as<ctl_block>();
+    P.ticket = &ctl->ticket; P.err_flag = &ctl->err; P.total_out = &ctl->total;
+    P.n_tiles = n_pages;
+    P.t = e->dt;
+    if (e->model == B2T_MODEL_BPE) model_tile_kernel<MODEL_BPE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
+    else model_tile_kernel<MODEL_WORDPIECE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
+    rec(e, st, e->model == B2T_MODEL_BPE ? "bpe_tile" : "wordpiece_tile"); e->last_launches++;
+    CU(cudaMemcpyAsync(ws.h_ctl.p, ws.ctl.p, sizeof(ctl_block), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaGetLastError());
+  return B2T_OK;
+}
+
+static int check_ctl(const Workspace& ws) {
+  const ctl_block* c = ws.h_ctl.as<ctl_block>();
+  if (c->err & ERR_LONG_PRETOKEN)
+    return fail(B2T_ERR_TOO_LARGE, "a BPE pre-token longer than %d bytes is not supported on the device path yet", TILE + 256);
+  return B2T_OK;
+}
+
+static int ensure_events(b2t_engine* e) {
+  if (e->rec_ev_made) return B2T_OK;
+  for (auto& ev : e->rec_ev) CU(cudaEventCreate(&ev));
+  e->rec_ev_made = true;
+  return B2T_OK;
+}
+
+extern "C" int b2t_engine_set_profiling(b2t_engine* e, int on) {
+  if (!e) return fail(B2T_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  if (on) { int rc = ensure_events(e); if (rc) return rc; }
+  e->profiling = on ? 1 : 0;
+  e->n_rec = 0;
+  return B2T_OK;
+}
+
+extern "C" int b2t_engine_last_kernels(const b2t_engine* e, const char** names, float* ms, int cap) {
+  if (!e) return 0;
+  if (e->profiling && e->n_rec > 0) {
+    cudaEventSynchronize(e->rec_ev[e->n_rec]);
+    for (int i = 0; i < e->n_rec && i < cap; ++i) {
+      if (names) names[i] = e->rec_name[i];
+      if (ms) { ms[i] = 0.f; cudaEventElapsedTime(&ms[i], e->rec_ev[i], e->rec_ev[i + 1]); }
+    }
+  }
+  return e->last_launches;
+}
+
+extern "C" int b2t_encode_batch_device(b2t_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint64_t* d_doc_off,
+                                       uint32_t n_docs, uint32_t flags, void* stream, b2t_result** out) {
+  if (!e || !out || !d_doc_off || (!d_bytes && n_bytes)) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device: null argument");
+  if (((uintptr_t)d_bytes & 15u) != 0) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device: d_bytes must be 16-byte aligned");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->own_stream;
+  Workspace& ws = e->dev_ws;
+  int rc = run_device_pipeline(e, ws, d_bytes, (int64_t)n_bytes, d_doc_off, n_docs, flags, st, true);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(st));
+  if ((rc = check_ctl(ws))) return rc;
+  b2t_result* r = new b2t_result();
+  r->eng = e; r->on_device = 1; r->n_docs = n_docs;
+  r->n_tokens = ws.h_ctl.as<ctl_block>()->total;
+  r->ids = ws.ids.as<uint32_t>();
+  r->offsets = (flags & B2T_WANT_OFFSETS) ? ws.offsets.as<uint32_t>() : nullptr;
+  r->word_ids = (flags & B2T_WANT_WORD_IDS) ? ws.word_ids.as<uint32_t>() : nullptr;
+  r->row_ptr = ws.row_ptr.as<uint64_t>();
+  *out = r;
+  return B2T_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host pipeline
+static b2t_result* pool_get(b2t_engine* e) {
+  if (!e->pool.empty()) { b2t_result* r = e->pool.back(); e->pool.pop_back(); return r; }
+  return new b2t_result();
+}
+
+static int slot_init(Workspace& ws) {
+  if (!ws.stream) CU(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+  if (!ws.done) CU(cudaEventCreateWithFlags(&ws.done, cudaEventDisableTiming));
+  return B2T_OK;
+}
+
+// rebases doc offsets of a chunk to the chunk start (runs on the slot's stream before K0)
+__global__ void rebase_kernel(uint64_t* doc_off, uint32_t count, uint64_t base) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) doc_off[i] -= base;
+}
+
+struct Chunk { uint32_t d0, d1; uint64_t b0, b1; uint64_t tok_base; };
+
+static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, uint32_t flags, bool pretok_only,
+                       b2t_result** out) {
+  if (doc_off[0] != 0) return fail(B2T_ERR_INVALID, "doc_off[0] must be 0");
+  const uint64_t total_bytes = doc_off[n_docs];
+  // ---- split into chunks of whole documents
+  std::vector<Chunk> chunks;
+  uint64_t max_chunk = 0;
+  {
+    uint32_t d = 0;
+    while (d < n_docs) {
+      uint64_t limit = doc_off[d] + e->chunk_bytes;
+      uint32_t d1 = (uint32_t)(std::upper_bound(doc_off + d + 1, doc_off + n_docs + 1, limit) - doc_off) - 1;
+      if (d1 <= d) d1 = d + 1;  // a single document larger than the chunk size
+      if (doc_off[d1] - doc_off[d] >= (1ull << 31)) return fail(B2T_ERR_TOO_LARGE, "document %u is larger than 2 GiB", d);
+      chunks.push_back({d, d1, doc_off[d], doc_off[d1], 0});
+      max_chunk = std::max(max_chunk, doc_off[d1] - doc_off[d]);
+      d = d1;
+    }
+    if (chunks.empty()) chunks.push_back({0, 0, 0, 0, 0});
+  }
+  b2t_result* r = pool_get(e);
+  r->eng = e; r->on_device = 0; r->n_docs = n_docs; r->n_tokens = 0;
+  int rc;
+  const bool want_off = (flags & B2T_WANT_OFFSETS) || pretok_only, want_wid = (flags & B2T_WANT_WORD_IDS) && !pretok_only;
+  // initial capacity guess: 0.30 tokens per byte, grown on demand (pinned pool => steady state allocates nothing)
+  uint64_t cap_tok = std::max<uint64_t>(total_bytes * 3 / 10 + 1024, 4096);
+  if ((rc = r->h_row_ptr.ensure(((size_t)n_docs + 1) * 8, false))) { e->pool.push_back(r); return rc; }
+  auto grow = [&](uint64_t need_tok) -> int {
+    int rc2;
+    if (!pretok_only && (rc2 = r->h_ids.ensure(need_tok * 4, true))) return rc2;
+    if (want_off && (rc2 = r->h_offsets.ensure(need_tok * 8, true))) return rc2;
+    if (want_wid && (rc2 = r->h_word_ids.ensure(need_tok * 4, true))) return rc2;
+    return B2T_OK;
+  };
+  if ((rc = grow(cap_tok))) { e->pool.push_back(r); return rc; }
+
+  uint64_t tok_base = 0;
+  const size_t nc = chunks.size();
+  // Pipeline over NSLOT device slots: chunk i is issued (H2D + kernels + count read-back) while older chunks compute;
+  // drain(i) waits for chunk i's kernels and queues the D2H of its results on the same slot stream.
+  auto drain = [&](size_t ci) -> int {
+    Chunk& c = chunks[ci];
+    Workspace& ws = e->slot[ci % NSLOT];
+    CU(cudaEventSynchronize(ws.done));
+    if (pretok_only) return B2T_OK;
+    int rc2 = check_ctl(ws);
+    if (rc2) return rc2;
+    const uint64_t nt = ws.h_ctl.as<ctl_block>()->total;
+    c.tok_base = tok_base;
+    if (tok_base + nt > cap_tok) {
+      // earlier chunks may still be copying into the old buffers: let them land, then grow (contents are kept)
+      for (auto& s : e->slot) if (s.stream) CU(cudaStreamSynchronize(s.stream));
+      cap_tok = (tok_base + nt) * 2;
+      if ((rc2 = grow(cap_tok))) return rc2;
+    }
+    const uint32_t nd = c.d1 - c.d0;
+    if (nt) {
+      CU(cudaMemcpyAsync(r->h_ids.as<uint32_t>() + tok_base, ws.ids.p, nt * 4, cudaMemcpyDeviceToHost, ws.stream));
+      if (want_off) CU(cudaMemcpyAsync(r->h_offsets.as<uint32_t>() + 2 * tok_base, ws.offsets.p, nt * 8, cudaMemcpyDeviceToHost, ws.stream));
+      if (want_wid) CU(cudaMemcpyAsync(r->h_word_ids.as<uint32_t>() + tok_base, ws.word_ids.p, nt * 4, cudaMemcpyDeviceToHost, ws.stream));
+    }
+    // chunk-relative row_ptr: entries d0..d1-1 (the last chunk also owns entry d1 = n_docs)
+    const size_t nrp = (size_t)nd + (ci + 1 == nc ? 1 : 0);
+    if (nrp) CU(cudaMemcpyAsync(r->h_row_ptr.as<uint64_t>() + c.d0, ws.row_ptr.p, nrp * 8, cudaMemcpyDeviceToHost, ws.stream));
+    tok_base += nt;
+    return B2T_OK;
+  };
+  size_t drained = 0;
+  rc = B2T_OK;
+  for (size_t ci = 0; ci < nc && rc == B2T_OK; ++ci) {
+    Workspace& ws = e->slot[ci % NSLOT];
+    if ((rc = slot_init(ws))) break;
+    if (ci >= NSLOT) {
+      // slot reuse: the chunk that used it must be drained and its copies must have landed
+      while (rc == B2T_OK && drained + NSLOT <= ci) rc = drain(drained++);
+      if (rc) break;
+      CU(cudaStreamSynchronize(ws.stream));
+    }
+    Chunk& c = chunks[ci];
+    const uint64_t nb = c.b1 - c.b0;
+    const uint32_t nd = c.d1 - c.d0;
+    if ((rc = ws.bytes.ensure(nb + 64)) || (rc = ws.doc_off.ensure(((size_t)nd + 1) * 8))) break;
+    if (nb) CU(cudaMemcpyAsync(ws.bytes.p, bytes + c.b0, nb, cudaMemcpyHostToDevice, ws.stream));
+    CU(cudaMemcpyAsync(ws.doc_off.p, doc_off + c.d0, ((size_t)nd + 1) * 8, cudaMemcpyHostToDevice, ws.stream));
+    if (c.b0) rebase_kernel<<<(nd + 1 + 255) / 256, 256, 0, ws.stream>>>(ws.doc_off.as<uint64_t>(), nd + 1, c.b0);
+    rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)nb, ws.doc_off.as<uint64_t>(), nd, flags, ws.stream, !pretok_only);
+    if (rc) break;
+    CU(cudaEventRecord(ws.done, ws.stream));
+    // keep at most NSLOT - 1 chunks un-drained so that result copies overlap the next chunks' kernels
+    while (rc == B2T_OK && drained + (NSLOT - 1) <= ci) rc = drain(drained++);
+  }
+  while (rc == B2T_OK && drained < nc) rc = drain(drained++);
+  for (auto& s : e->slot) if (s.stream) cudaStreamSynchronize(s.stream);
+  if (rc) { e->pool.push_back(r); return rc; }
+
+  if (!pretok_only) {
+    // chunk-relative row_ptr -> batch-relative (host fix-up: one addition per document)
+    uint64_t* rp = r->h_row_ptr.as<uint64_t>();
+    for (size_t ci = 1; ci < nc; ++ci) {
+      const Chunk& c = chunks[ci];
+      const uint32_t hi = (ci + 1 == nc) ? c.d1 : c.d1 - 1;
+      for (uint32_t d = c.d0; d <= hi; ++d) rp[d] += c.tok_base;
+    }
+    r->n_tokens = tok_base;
+    r->ids = r->h_ids.as<uint32_t>();
+    r->offsets = want_off ? r->h_offsets.as<uint32_t>() : nullptr;
+    r->word_ids = want_wid ? r->h_word_ids.as<uint32_t>() : nullptr;
+    r->row_ptr = rp;
+  }
+  *out = r;
+  return B2T_OK;
+}
+
+extern "C" int b2t_encode_batch(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, uint32_t flags,
+                                b2t_result** out) {
+  if (!e || !out || !doc_off || (!bytes && doc_off[n_docs])) return fail(B2T_ERR_INVALID, "b2t_encode_batch: null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  return host_encode(e, bytes, doc_off, n_docs, flags, false, out);
+}
+
+// PreTokenizer seam: runs K0/K1 and expands the split bitmaps into (start, end) pairs.  The expansion of the bitmap
+// into the pair list is output formatting and happens on the host (this is an inspection API, not the hot path).
+extern "C" int b2t_pre_tokenize_batch(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, b2t_result** out) {
+  if (!e || !out || !doc_off || (!bytes && doc_off[n_docs])) return fail(B2T_ERR_INVALID, "b2t_pre_tokenize_batch: null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  if (doc_off[0] != 0) return fail(B2T_ERR_INVALID, "doc_off[0] must be 0");
+  const uint64_t n = doc_off[n_docs];
+  Workspace& ws = e->slot[0];
+  int rc;
+  if ((rc = slot_init(ws)) || (rc = ws.bytes.ensure(n + 64)) || (rc = ws.doc_off.ensure(((size_t)n_docs + 1) * 8))) return rc;
+  if (n) CU(cudaMemcpyAsync(ws.bytes.p, bytes, n, cudaMemcpyHostToDevice, ws.stream));
+  CU(cudaMemcpyAsync(ws.doc_off.p, doc_off, ((size_t)n_docs + 1) * 8, cudaMemcpyHostToDevice, ws.stream));
+  if ((rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)n, ws.doc_off.as<uint64_t>(), n_docs, 0, ws.stream, false))) return rc;
+  const size_t n_words = n / 32 + 2;
+  std::vector<uint32_t> sb(n_words), db(n_words, 0u);
+  CU(cudaMemcpyAsync(sb.data(), ws.start_bits.p, n_words * 4, cudaMemcpyDeviceToHost, ws.stream));
+  if (e->pretok == PT_WHITESPACE) CU(cudaMemcpyAsync(db.data(), ws.drop_bits.p, n_words * 4, cudaMemcpyDeviceToHost, ws.stream));
+  CU(cudaStreamSynchronize(ws.stream));
+  b2t_result* r = pool_get(e);
+  r->eng = e; r->on_device = 0; r->n_docs = n_docs;
+  auto bit = [](const std::vector<uint32_t>& v, uint64_t p) { return (v[p >> 5] >> (p & 31)) & 1u; };
+  uint64_t count = 0;
+  for (uint64_t p = 0; p < n; ++p) count += bit(sb, p) && !bit(db, p);
+  if ((rc = r->h_offsets.ensure((count + 1) * 8, false)) || (rc = r->h_row_ptr.ensure(((size_t)n_docs + 1) * 8, false))) { e->pool.push_back(r); return rc; }
+  uint32_t* off = r->h_offsets.as<uint32_t>();
+  uint64_t* rp = r->h_row_ptr.as<uint64_t>();
+  uint64_t k = 0;
+  for (uint32_t d = 0; d < n_docs; ++d) {
+    rp[d] = k;
+    uint64_t p = doc_off[d];
+    const uint64_t end = doc_off[d + 1];
+    while (p < end) {
+      uint64_t q = p + 1;
+      while (q < end && !bit(sb, q)) ++q;
+      if (!bit(db, p)) { off[2 * k] = (uint32_t)(p - doc_off[d]); off[2 * k + 1] = (uint32_t)(q - doc_off[d]); ++k; }
+      p = q;
+    }
+  }
+  rp[n_docs] = k;
+  r->n_tokens = k; r->ids = nullptr; r->word_ids = nullptr; r->offsets = off; r->row_ptr = rp;
+  *out = r;
+  return B2T_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ results
+extern "C" uint64_t b2t_result_n_tokens(const b2t_result* r) { return r ? r->n_tokens : 0; }
+extern "C" uint32_t b2t_result_n_docs(const b2t_result* r) { return r ? r->n_docs : 0; }
+extern "C" int b2t_result_on_device(const b2t_result* r) { return r ? r->on_device : 0; }
+extern "C" const uint32_t* b2t_result_ids(const b2t_result* r) { return r ? r->ids : nullptr; }
+extern "C" const uint32_t* b2t_result_offsets(const b2t_result* r) { return r ? r->offsets : nullptr; }
+extern "C" const uint32_t* b2t_result_word_ids(const b2t_result* r) { return r ? r->word_ids : nullptr; }
+extern "C" const uint64_t* b2t_result_row_ptr(const b2t_result* r) { return r ? r->row_ptr : nullptr; }
+extern "C" void b2t_result_free(b2t_result* r) {
+  if (!r) return;
+  if (r->on_device || !r->eng) { delete r; return; }
+  b2t_engine* e = r->eng;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->pool.size() < 4) e->pool.push_back(r);
+  else { cudaSetDevice(e->device); r->h_ids.release(); r->h_offsets.release(); r->h_word_ids.release(); r->h_row_ptr.release(); delete r; }
+}
+
+extern "C" int b2t_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(B2T_ERR_INVALID, "null argument");
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return B2T_OK;
+}
+extern "C" void b2t_host_free(void* p) { if (p) cudaFreeHost(p); }

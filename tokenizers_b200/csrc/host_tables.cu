@@ -1,0 +1,183 @@
+// host_tables.cu -- see host_tables.h
+#include "host_tables.h"
+
+#include <string.h>
+#include <vector_types.h>
+
+#include "pretok_logic.cuh"
+#include "unicode_ranges.inc"
+
+namespace b2t {
+
+void unicode_class_table(int scheme, uint8_t* out) {
+  memset(out, 0, 0x110000);
+  auto fill = [&](const uint32_t (*r)[2], uint32_t cnt, uint8_t v) {
+    for (uint32_t i = 0; i < cnt; ++i)
+      for (uint32_t c = r[i][0]; c <= r[i][1]; ++c) out[c] = v;
+  };
+  if (scheme == 0) {
+    fill(B2T_ONIG_L, B2T_ONIG_L_COUNT, CLS_L);
+    fill(B2T_ONIG_N, B2T_ONIG_N_COUNT, CLS_N);
+    fill(B2T_ONIG_S, B2T_ONIG_S_COUNT, CLS_S);
+  } else {
+    fill(B2T_RUST_W, B2T_RUST_W_COUNT, CLS_L);
+    fill(B2T_RUST_S, B2T_RUST_S_COUNT, CLS_S);
+  }
+}
+
+static void utf8_append(std::string& s, uint32_t cp) {
+  if (cp < 0x80) s.push_back((char)cp);
+  else if (cp < 0x800) { s.push_back((char)(0xC0 | (cp >> 6))); s.push_back((char)(0x80 | (cp & 63))); }
+  else if (cp < 0x10000) { s.push_back((char)(0xE0 | (cp >> 12))); s.push_back((char)(0x80 | ((cp >> 6) & 63))); s.push_back((char)(0x80 | (cp & 63))); }
+  else { s.push_back((char)(0xF0 | (cp >> 18))); s.push_back((char)(0x80 | ((cp >> 12) & 63))); s.push_back((char)(0x80 | ((cp >> 6) & 63))); s.push_back((char)(0x80 | (cp & 63))); }
+}
+
+// byte_level.rs:15-39: printable bytes keep their code point, the other 68 map to U+0100 + k in byte order
+static void bytes_char_table(uint32_t cp_of_byte[256]) {
+  uint32_t k = 0;
+  for (int b = 0; b < 256; ++b) {
+    bool printable = (b >= '!' && b <= '~') || (b >= 0xA1 && b <= 0xAC) || (b >= 0xAE && b <= 0xFF);
+    cp_of_byte[b] = printable ? (uint32_t)b : 256u + k++;
+  }
+}
+
+static uint32_t pow2_at_least(uint64_t x) {
+  uint32_t c = 16;
+  while (c < x) c <<= 1;
+  return c;
+}
+
+std::string build_host_tables(int model, int pretok, int ignore_merges, uint32_t n_vocab, const uint8_t* vocab_bytes,
+                              const uint32_t* vocab_off, const uint32_t* vocab_ids, uint32_t n_merges,
+                              const uint8_t* merge_bytes, const uint32_t* merge_off, const char* unk_token,
+                              const char* cont_prefix, uint32_t max_chars, HostTables* out, bool* vocab_err) {
+  *vocab_err = false;
+  // ---- class table
+  {
+    std::vector<uint8_t> cls(0x110000);
+    unicode_class_table(pretok == PT_WHITESPACE ? 1 : 0, cls.data());
+    out->cls_packed.assign(0x110000 / 16, 0u);
+    for (uint32_t c = 0; c < 0x110000; ++c) out->cls_packed[c >> 4] |= (uint32_t)cls[c] << ((c & 15) * 2);
+  }
+  std::unordered_map<std::string, uint32_t> vocab;
+  vocab.reserve((size_t)n_vocab * 2);
+  for (uint32_t i = 0; i < n_vocab; ++i)
+    vocab[std::string((const char*)vocab_bytes + vocab_off[i], vocab_off[i + 1] - vocab_off[i])] = vocab_ids[i];
+  out->max_chars = max_chars;
+
+  if (model == 0) {
+    // ---- ByteLevel alphabet -> ids
+    uint32_t cp_of_byte[256];
+    bytes_char_table(cp_of_byte);
+    std::unordered_map<uint32_t, uint8_t> byte_of_cp;
+    out->byte_to_id.assign(256, 0);
+    for (int b = 0; b < 256; ++b) {
+      std::string ch;
+      utf8_append(ch, cp_of_byte[b]);
+      auto it = vocab.find(ch);
+      if (it == vocab.end())
+        return "BPE vocab lacks the ByteLevel character of byte " + std::to_string(b) +
+               " (the reference would silently drop such bytes; unsupported on device)";
+      out->byte_to_id[b] = it->second;
+      byte_of_cp[cp_of_byte[b]] = (uint8_t)b;
+    }
+    // ---- merges (models/bpe/model.rs:252-275)
+    uint32_t cap = pow2_at_least((uint64_t)n_merges * 5 / 2 + 16);
+    out->merge_tbl.assign(cap, make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, EMPTY_KEY));
+    for (uint32_t i = 0; i < n_merges; ++i) {
+      std::string a((const char*)merge_bytes + merge_off[2 * i], merge_off[2 * i + 1] - merge_off[2 * i]);
+      std::string b((const char*)merge_bytes + merge_off[2 * i + 1], merge_off[2 * i + 2] - merge_off[2 * i + 1]);
+      auto ia = vocab.find(a), ib = vocab.find(b), in = vocab.find(a + b);
+      if (ia == vocab.end() || ib == vocab.end() || in == vocab.end()) {
+        *vocab_err = true;
+        return "merge " + std::to_string(i) + ": token out of vocabulary";  // Error::MergeTokenOutOfVocabulary
+      }
+      uint32_t h = pair_hash(ia->second, ib->second) & (cap - 1);
+      while (true) {
+        uint4& e = out->merge_tbl[h];
+        if (e.x == EMPTY_KEY || (e.x == ia->second && e.y == ib->second)) {  // a later duplicate overwrites (HashMap collect)
+          e = make_uint4(ia->second, ib->second, i, in->second);
+          break;
+        }
+        h = (h + 1) & (cap - 1);
+      }
+    }
+    // ---- whole-word table for ignore_merges (models/bpe/model.rs:558-567)
+    if (ignore_merges) {
+      uint32_t wcap = pow2_at_least((uint64_t)n_vocab * 5 / 2 + 16);
+      out->word_tbl.assign(wcap, make_uint4(0, 0, EMPTY_KEY, 0));
+      for (uint32_t i = 0; i < n_vocab; ++i) {
+        const uint8_t* s = vocab_bytes + vocab_off[i];
+        uint32_t len = vocab_off[i + 1] - vocab_off[i];
+        std::string raw;
+        bool ok = len > 0;
+        for (uint32_t p = 0; p < len && ok;) {  // byte-level chars back to bytes
+          uint32_t b0 = s[p], cp, l;
+          if (b0 < 0x80) { cp = b0; l = 1; }
+          else if (b0 < 0xE0 && p + 1 < len) { cp = ((b0 & 31u) << 6) | (s[p + 1] & 63u); l = 2; }
+          else { ok = false; break; }
+          auto it = byte_of_cp.find(cp);
+          if (it == byte_of_cp.end()) { ok = false; break; }
+          raw.push_back((char)it->second);
+          p += l;
+        }
+        if (!ok) continue;  // contains a char outside the byte alphabet: can never equal a pre-token
+        StrHash h;
+        strhash_init(h);
+        for (unsigned char c : raw) strhash_byte(h, c);
+        strhash_fin(h);
+        uint32_t slot = h.h1 & (wcap - 1);
+        while (out->word_tbl[slot].z != EMPTY_KEY) slot = (slot + 1) & (wcap - 1);
+        out->word_tbl[slot] = make_uint4(h.h2, (uint32_t)raw.size(), vocab_ids[i], (uint32_t)out->word_pool.size());
+        out->word_pool.insert(out->word_pool.end(), raw.begin(), raw.end());
+      }
+      out->word_pool.resize(out->word_pool.size() + 16, 0);
+    }
+  } else {
+    // ---- WordPiece: byte trie with two roots
+    if (!unk_token) return "WordPiece needs unk_token";
+    auto iu = vocab.find(unk_token);
+    if (iu == vocab.end()) {
+      *vocab_err = true;
+      return "WordPiece error: Missing [UNK] token from the vocabulary";  // wordpiece/mod.rs:17-22
+    }
+    out->unk_id = iu->second;
+    std::string prefix = cont_prefix ? cont_prefix : "";
+    std::unordered_map<uint64_t, uint32_t> edges;  // node << 8 | byte -> child
+    std::vector<uint32_t> node_tok(2, EMPTY_KEY);
+    auto insert = [&](uint32_t root, const uint8_t* s, uint32_t len, uint32_t id) {
+      uint32_t node = root;
+      for (uint32_t p = 0; p < len; ++p) {
+        uint64_t key = ((uint64_t)node << 8) | s[p];
+        auto it = edges.find(key);
+        if (it == edges.end()) {
+          uint32_t child = (uint32_t)node_tok.size();
+          node_tok.push_back(EMPTY_KEY);
+          edges.emplace(key, child);
+          node = child;
+        } else node = it->second;
+      }
+      node_tok[node] = id;
+    };
+    for (uint32_t i = 0; i < n_vocab; ++i) {
+      const uint8_t* s = vocab_bytes + vocab_off[i];
+      uint32_t len = vocab_off[i + 1] - vocab_off[i];
+      if (len == 0) continue;
+      insert(0, s, len, vocab_ids[i]);
+      if (len > prefix.size() && memcmp(s, prefix.data(), prefix.size()) == 0)
+        insert(1, s + prefix.size(), len - (uint32_t)prefix.size(), vocab_ids[i]);
+    }
+    if (node_tok.size() >= (1u << 24)) return "WordPiece vocabulary too large for the device trie";
+    uint32_t ecap = pow2_at_least((uint64_t)edges.size() * 5 / 2 + 16);
+    out->edge_tbl.assign(ecap, make_uint4(EMPTY_KEY, 0, EMPTY_KEY, 0));
+    for (auto& kv : edges) {
+      uint32_t node = (uint32_t)(kv.first >> 8), byte = (uint32_t)(kv.first & 255);
+      uint32_t slot = edge_hash(node, byte) & (ecap - 1);
+      while (out->edge_tbl[slot].x != EMPTY_KEY) slot = (slot + 1) & (ecap - 1);
+      out->edge_tbl[slot] = make_uint4((uint32_t)kv.first, kv.second, node_tok[kv.second], 0);
+    }
+  }
+  return "";
+}
+
+}  // namespace b2t

@@ -1,0 +1,36 @@
+// host_tables.h -- host-side construction of the device tables from the engine configuration.
+//
+// Restates the one-time table building of the reference (paths relative to /root/reference/tokenizers/src):
+//   pre_tokenizers/byte_level.rs:15-39   bytes_char(): the byte <-> unicode char map of ByteLevel
+//   models/bpe/model.rs:252-275          merges (a, b) -> ids through the vocab, new token = a + b
+//   models/wordpiece/mod.rs:143-153      vocab, unk token, continuing subword prefix
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "b2t_tables.h"
+
+namespace b2t {
+
+struct HostTables {
+  std::vector<uint32_t> cls_packed;   // 2 bits per code point
+  std::vector<uint32_t> byte_to_id;   // 256
+  std::vector<uint4> merge_tbl;
+  std::vector<uint4> word_tbl;
+  std::vector<uint8_t> word_pool;
+  std::vector<uint4> edge_tbl;
+  uint32_t unk_id = EMPTY_KEY;
+  uint32_t max_chars = 100;
+};
+
+// Fills out[0x110000] with the class of every code point (scheme 0 = Oniguruma L/N/S, 1 = Rust regex \w,\s).
+void unicode_class_table(int scheme, uint8_t* out);
+
+// Returns "" on success, else an error message; *vocab_err distinguishes B2T_ERR_VOCAB from B2T_ERR_UNSUPPORTED.
+std::string build_host_tables(int model, int pretok, int ignore_merges, uint32_t n_vocab, const uint8_t* vocab_bytes,
+                              const uint32_t* vocab_off, const uint32_t* vocab_ids, uint32_t n_merges,
+                              const uint8_t* merge_bytes, const uint32_t* merge_off, const char* unk_token,
+                              const char* cont_prefix, uint32_t max_chars, HostTables* out, bool* vocab_err);
+
+}  // namespace b2t

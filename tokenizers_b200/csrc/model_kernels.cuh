@@ -1,0 +1,494 @@
+// model_kernels.cuh -- K2: one tile kernel that turns (bytes, pre-token bitmap) into the token CSR.
+//
+// Replaces, per 2 KB page of the packed batch (paths relative to /root/reference/tokenizers/src):
+//   models/bpe/model.rs:465-612 (merge_word, tokenize_with_cache incl. ignore_merges) + models/bpe/word.rs:162-268
+//   models/wordpiece/mod.rs:224-283 (greedy longest match, max_input_chars_per_word, [UNK])
+//   tokenizer/pre_tokenizer.rs:198-263,329-364 (into_encoding: offsets -> original -> char, word ids)
+//   tokenizer/encoding.rs:541-565 (collecting tokens of all splits in order)
+//
+// Work decomposition: the block owns the pre-tokens that START inside its page (they may run into the halo).
+//   * every symbol lives at its byte position in shared memory (id, length, rank of the pair it forms with its right
+//     neighbour), so symbols never move: a merge extends the left symbol and zeroes the length of the right one;
+//   * short pre-tokens (<= 32 bytes) are merged by one thread each (dynamic queue, "leftmost pair of minimal rank"
+//     per round == the reference's heap order (rank, pos) with its stale-entry check);
+//   * longer ones are merged by one warp each (lanes stride over the positions, __reduce_min_sync picks the pair);
+//   * surviving symbol starts are exactly the token starts: a ballot per 32 positions gives the token bitmap, a
+//     decoupled look-back over the pages gives the global token index, and ids / offsets / word ids are written in
+//     order straight into the CSR.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b2t_tables.h"
+#include "pretok_logic.cuh"
+
+namespace b2t {
+
+constexpr int TILE = PAGE;
+constexpr int MODEL_THREADS = 256;
+constexpr int THREAD_PATH_MAX = 32;  // pre-tokens up to this many bytes are merged by a single thread
+enum { MODEL_BPE = 0, MODEL_WORDPIECE = 1 };
+enum { F_OFFSETS = 1u, F_WORD_IDS = 2u, F_BYTE_OFFSETS = 4u };
+enum { ERR_LONG_PRETOKEN = 1u };
+
+struct ModelParams {
+  const uint8_t* bytes; int64_t n;
+  const uint32_t* start_bits; const uint32_t* drop_bits; const uint32_t* doc_bits;
+  const uint64_t* page_carry; const uint32_t* page_first_doc;
+  const uint64_t* doc_off; uint32_t n_docs;
+  uint32_t flags;
+  uint32_t* ids; uint32_t* offsets; uint32_t* word_ids; uint64_t* row_ptr;
+  unsigned long long* tile_state; uint32_t* ticket; unsigned long long* total_out; uint32_t* err_flag;
+  int64_t n_tiles;
+  DeviceTables t;
+};
+
+__device__ __forceinline__ uint64_t merge_lookup(const DeviceTables& t, uint32_t a, uint32_t b) {
+  uint32_t h = pair_hash(a, b) & t.merge_mask;
+  while (true) {
+    uint4 e = __ldg(t.merge_tbl + h);
+    if (e.x == a && e.y == b) return ((uint64_t)e.z << 32) | e.w;
+    if (e.x == EMPTY_KEY) return NO_MERGE;
+    h = (h + 1) & t.merge_mask;
+  }
+}
+
+// exclusive prefix of popcounts over nw (<= 96) words, by one full warp; returns the total
+__device__ __forceinline__ int warp_prefix_words(const uint32_t* bits, uint16_t* pref, int nw, int lane) {
+  int c0 = 0, c1 = 0, c2 = 0;
+  int i = lane * 3;
+  if (i < nw) c0 = __popc(bits[i]);
+  if (i + 1 < nw) c1 = __popc(bits[i + 1]);
+  if (i + 2 < nw) c2 = __popc(bits[i + 2]);
+  int tot = c0 + c1 + c2, inc = tot;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    int o = __shfl_up_sync(0xFFFFFFFFu, inc, s);
+    if (lane >= s) inc += o;
+  }
+  int ex = inc - tot;
+  if (i < nw) pref[i] = (uint16_t)ex;
+  if (i + 1 < nw) pref[i + 1] = (uint16_t)(ex + c0);
+  if (i + 2 < nw) pref[i + 2] = (uint16_t)(ex + c0 + c1);
+  return __shfl_sync(0xFFFFFFFFu, inc, 31);
+}
+
+__device__ __forceinline__ uint32_t mask_le(int b) { return b >= 31 ? 0xFFFFFFFFu : ((2u << b) - 1u); }
+
+#define B2T_ST_AGG (1ull << 62)
+#define B2T_ST_INCL (2ull << 62)
+#define B2T_ST_VAL ((1ull << 62) - 1ull)
+
+template <int MODEL>
+__global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelParams P) {
+  constexpr int HALO = MODEL == MODEL_BPE ? 256 : 416;
+  constexpr int SPAN = TILE + HALO;
+  constexpr int NW = SPAN / 32;
+  constexpr int TW = TILE / 32;
+  static_assert(NW <= 96, "warp_prefix_words handles <= 96 words");
+  __shared__ __align__(16) uint8_t s_byte[SPAN];
+  __shared__ uint16_t s_len[SPAN];
+  __shared__ uint32_t s_id[SPAN];
+  __shared__ uint64_t s_val[MODEL == MODEL_BPE ? SPAN : 1];
+  __shared__ uint32_t s_startb[NW + 1], s_keptb[NW + 1], s_leadb[NW + 1], s_tokb[NW + 1], s_dsb[TW + 1];
+  __shared__ uint16_t s_apref[NW + 1], s_spref[NW + 1], s_lpref[NW + 1], s_tpref[NW + 1];
+  __shared__ int16_t s_dlast[TW + 1];
+  __shared__ uint16_t s_pt[TILE + 2];
+  __shared__ uint16_t s_mq[TILE / THREAD_PATH_MAX + 2];
+  __shared__ int s_tile, s_next, s_nmq, s_P, s_Elast, s_long, s_ntok;
+  __shared__ unsigned long long s_excl;
+  __shared__ long long s_long_end, s_span_doc_start;
+  __shared__ int s_long_chars;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARPS = MODEL_THREADS / 32;
+  if (tid == 0) {
+    s_tile = (int)atomicAdd(P.ticket, 1u);
+    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0;
+  }
+  __syncthreads();
+  const int64_t t = s_tile;
+  if (t >= P.n_tiles) return;
+  const int64_t base = t * TILE;
+  const int64_t n = P.n;
+  const int64_t n_chunks = n / CHUNK + 1;
+
+  // ---------------------------------------------------------------- P0: stage bytes and bitmaps
+  for (int i = tid; i < SPAN / 16; i += MODEL_THREADS) {
+    int64_t g = base + (int64_t)i * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g + 16 <= n) v = __ldg(reinterpret_cast<const uint4*>(P.bytes + g));
+    else if (g < n) {
+      uint32_t w[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 16 && g + k < n; ++k) w[k >> 2] |= (uint32_t)__ldg(P.bytes + g + k) << (8 * (k & 3));
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    reinterpret_cast<uint4*>(s_byte)[i] = v;
+  }
+  for (int w = tid; w <= NW; w += MODEL_THREADS) {
+    int64_t gw = base / 32 + w;
+    uint32_t sb = (w < NW && gw < n_chunks) ? __ldg(P.start_bits + gw) : 0u;
+    uint32_t db = (MODEL == MODEL_WORDPIECE && w < NW && gw < n_chunks) ? __ldg(P.drop_bits + gw) : 0u;
+    s_startb[w] = sb;
+    s_keptb[w] = sb & ~db;
+    if (w <= TW) s_dsb[w] = (w < TW && gw < n_chunks) ? __ldg(P.doc_bits + gw) : 0u;
+  }
+  __syncthreads();
+  // lead bits + symbol init, one 32-byte row per warp iteration
+  for (int row = warp; row < NW; row += NWARPS) {
+    int pos = row * 32 + lane;
+    uint32_t b = s_byte[pos];
+    bool lead = ((b & 0xC0u) != 0x80u) && (base + pos < n);
+    uint32_t lb = __ballot_sync(0xFFFFFFFFu, lead);
+    if (lane == 0) s_leadb[row] = lb;
+    if (MODEL == MODEL_BPE) { s_id[pos] = __ldg(P.t.byte_to_id + b); s_len[pos] = 1; }
+    else s_len[pos] = 0;
+  }
+  if (tid == 0) s_leadb[NW] = 0u;
+  __syncthreads();
+
+  // ---------------------------------------------------------------- P1/P2: prefixes, end of the last pre-token
+  if (warp == 0) {
+    int tot = warp_prefix_words(s_startb, s_apref, TW, lane);  // all starts inside the page
+    if (lane == 0) s_P = tot;
+  } else if (warp == 1) {
+    warp_prefix_words(s_keptb, s_spref, NW, lane);
+  } else if (warp == 2) {
+    warp_prefix_words(s_leadb, s_lpref, NW, lane);
+  } else if (warp == 3) {
+    // first start bit at a position >= TILE (the end of the page's last pre-token)
+    int found = SPAN;
+    for (int w = TW + lane; w < NW; w += 32) {
+      uint32_t b = s_startb[w];
+      if (b) { found = w * 32 + (__ffs((int)b) - 1); break; }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) found = min(found, __shfl_xor_sync(0xFFFFFFFFu, found, s));
+    int64_t lim = n - base;  // bytes available from the page start
+    int is_long = 0;
+    long long long_end = 0;
+    if (found >= SPAN) {
+      if (lim <= SPAN) found = (int)lim;
+      else {
+        // no start inside the halo: the last pre-token is LONG.  Find its true end in the global bitmap.
+        is_long = 1;
+        int64_t gw = (base + SPAN) / 32;
+        long long e = -1;
+        while (e < 0) {
+          int64_t w = gw + lane;
+          uint32_t b = (w < n_chunks) ? __ldg(P.start_bits + w) : 0u;
+          uint32_t any = __ballot_sync(0xFFFFFFFFu, b != 0u);
+          if (any) {
+            int l = __ffs((int)any) - 1;
+            uint32_t bb = __shfl_sync(0xFFFFFFFFu, b, l);
+            e = (gw + l) * 32 + (__ffs((int)bb) - 1);
+          } else if (gw + 32 >= n_chunks) e = n;
+          gw += 32;
+        }
+        long_end = e < n ? e : n;
+        found = SPAN;
+      }
+    } else if (found > lim) found = (int)lim;
+    if (lane == 0) { s_Elast = found; s_long = is_long; s_long_end = long_end; }
+  } else if (warp == 4) {
+    // last doc start strictly before each word of the page
+    int mine0 = -1, mine1 = -1;  // lane handles words 2*lane, 2*lane+1
+    uint32_t b0 = s_dsb[2 * lane], b1 = s_dsb[2 * lane + 1];
+    int last0 = b0 ? (2 * lane) * 32 + 31 - __clz((int)b0) : -1;
+    int last1 = b1 ? (2 * lane + 1) * 32 + 31 - __clz((int)b1) : -1;
+    int mx = max(last0, last1), inc = mx;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      int o = __shfl_up_sync(0xFFFFFFFFu, inc, s);
+      if (lane >= s) inc = max(inc, o);
+    }
+    int before = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    if (lane == 0) before = -1;
+    mine0 = before; mine1 = max(before, last0);
+    s_dlast[2 * lane] = (int16_t)mine0; s_dlast[2 * lane + 1] = (int16_t)mine1;
+    if (lane == 31) s_dlast[TW] = (int16_t)inc;
+  } else if (warp == 5 && lane == 0) {
+    // byte position of the start of the document that spans into this page (for byte offsets)
+    uint32_t fd = __ldg(P.page_first_doc + t);
+    s_span_doc_start = fd > 0 ? (long long)__ldg(P.doc_off + fd - 1) : 0;
+  }
+  __syncthreads();
+  const int Pn = s_P;
+  const int Elast = s_Elast;
+  const int is_long = s_long;
+  if (tid < TW) {
+    uint32_t bits = s_startb[tid];
+    int idx = s_apref[tid];
+    while (bits) { s_pt[idx++] = (uint16_t)(tid * 32 + __ffs((int)bits) - 1); bits &= bits - 1u; }
+  }
+  if (tid == 0) s_pt[Pn] = (uint16_t)Elast;
+  __syncthreads();
+  const int first = Pn ? (int)s_pt[0] : Elast;
+  // the region whose symbols this block resolves in shared memory (a LONG last pre-token is excluded)
+  const int Eproc = Pn ? (is_long ? (int)s_pt[Pn - 1] : Elast) : 0;
+  const int Pproc = is_long ? Pn - 1 : Pn;
+
+  if (MODEL == MODEL_BPE) {
+    if (is_long && tid == 0) atomicOr(P.err_flag, ERR_LONG_PRETOKEN);
+    // -------------------------------------------------------------- P3: ranks of all adjacent byte pairs
+    if (!P.t.ignore_merges) {
+      for (int pos = tid; pos < SPAN; pos += MODEL_THREADS) {
+        uint64_t v = NO_MERGE;
+        if (pos >= first && pos + 1 < Eproc && !((s_startb[(pos + 1) >> 5] >> ((pos + 1) & 31)) & 1u))
+          v = merge_lookup(P.t, s_id[pos], s_id[pos + 1]);
+        s_val[pos] = v;
+      }
+    }
+    __syncthreads();
+    // -------------------------------------------------------------- P4a: one thread per short pre-token
+    while (true) {
+      int k = atomicAdd(&s_next, 1);
+      if (k >= Pproc) break;
+      const int s = s_pt[k], e = s_pt[k + 1], len = e - s;
+      if (P.t.ignore_merges) {
+        // models/bpe/model.rs:558-567: the whole pre-token is a vocab entry -> one token
+        StrHash h; strhash_init(h);
+        for (int p = s; p < e; ++p) strhash_byte(h, s_byte[p]);
+        strhash_fin(h);
+        uint32_t slot = h.h1 & P.t.word_mask;
+        bool hit = false;
+        while (true) {
+          uint4 en = __ldg(P.t.word_tbl + slot);
+          if (en.z == EMPTY_KEY) break;
+          if (en.x == h.h2 && en.y == (uint32_t)len) {
+            const uint8_t* q = P.t.word_pool + en.w;
+            bool same = true;
+            for (int i = 0; i < len; ++i) if (__ldg(q + i) != s_byte[s + i]) { same = false; break; }
+            if (same) { s_id[s] = en.z; hit = true; break; }
+          }
+          slot = (slot + 1) & P.t.word_mask;
+        }
+        if (hit) {
+          s_len[s] = (uint16_t)len;
+          for (int p = s + 1; p < e; ++p) s_len[p] = 0;
+          continue;
+        }
+        if (len <= THREAD_PATH_MAX) {
+          for (int p = s; p + 1 < e; ++p) s_val[p] = merge_lookup(P.t, s_id[p], s_id[p + 1]);
+          s_val[e - 1] = NO_MERGE;
+        }
+      }
+      if (len == 1) continue;
+      if (len > THREAD_PATH_MAX) { s_mq[atomicAdd(&s_nmq, 1)] = (uint16_t)k; continue; }
+      while (true) {
+        uint64_t best = NO_MERGE;
+        int bp = -1, bprev = -1, prev = -1, p = s;
+        while (p < e) {
+          uint64_t v = s_val[p];
+          if (v < best) { best = v; bp = p; bprev = prev; }
+          prev = p; p += s_len[p];
+        }
+        if (bp < 0) break;
+        const int q = bp + s_len[bp];
+        const uint32_t nid = (uint32_t)best;
+        const int nl = s_len[bp] + s_len[q];
+        s_id[bp] = nid; s_len[bp] = (uint16_t)nl; s_len[q] = 0;
+        const int nx = bp + nl;
+        s_val[bp] = nx < e ? merge_lookup(P.t, nid, s_id[nx]) : NO_MERGE;
+        if (bprev >= 0) s_val[bprev] = merge_lookup(P.t, s_id[bprev], nid);
+      }
+    }
+    __syncthreads();
+    // -------------------------------------------------------------- P4b: one warp per longer pre-token
+    const int nmq = s_nmq;
+    for (int qi = warp; qi < nmq; qi += NWARPS) {
+      const int k = s_mq[qi], s = s_pt[k], e = s_pt[k + 1];
+      if (P.t.ignore_merges) {
+        for (int p = s + lane; p < e; p += 32) s_val[p] = (p + 1 < e) ? merge_lookup(P.t, s_id[p], s_id[p + 1]) : NO_MERGE;
+        __syncwarp();
+      }
+      while (true) {
+        uint32_t brank = 0xFFFFFFFFu;
+        int bpos = 0x7FFFFFFF;
+        for (int p = s + lane; p < e; p += 32) {
+          if (s_len[p]) {
+            uint32_t r = (uint32_t)(s_val[p] >> 32);
+            if (r < brank) { brank = r; bpos = p; }  // positions grow, so the first hit is the leftmost of this lane
+          }
+        }
+        uint32_t mr = __reduce_min_sync(0xFFFFFFFFu, brank);
+        if (mr == 0xFFFFFFFFu) break;
+        int bp = (int)__reduce_min_sync(0xFFFFFFFFu, brank == mr ? (uint32_t)bpos : 0x7FFFFFFFu);
+        if (lane == 0) {
+          const int q = bp + s_len[bp];
+          const uint32_t nid = (uint32_t)s_val[bp];
+          const int nl = s_len[bp] + s_len[q];
+          s_id[bp] = nid; s_len[bp] = (uint16_t)nl; s_len[q] = 0;
+          const int nx = bp + nl;
+          s_val[bp] = nx < e ? merge_lookup(P.t, nid, s_id[nx]) : NO_MERGE;
+          if (bp > s) {
+            int pv = bp - 1;
+            while (s_len[pv] == 0) --pv;
+            s_val[pv] = merge_lookup(P.t, s_id[pv], nid);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- WordPiece: one thread per kept split
+    while (true) {
+      int k = atomicAdd(&s_next, 1);
+      if (k >= Pproc) break;
+      const int s = s_pt[k], e = s_pt[k + 1], len = e - s;
+      if (!((s_keptb[s >> 5] >> (s & 31)) & 1u)) continue;  // removed whitespace
+      // chars = lead bytes in [s, e)
+      int chars = (int)s_lpref[(e - 1) >> 5] + __popc(s_leadb[(e - 1) >> 5] & mask_le((e - 1) & 31)) -
+                  ((int)s_lpref[s >> 5] + __popc(s_leadb[s >> 5] & (mask_le(s & 31) >> 1)));
+      bool bad = chars > (int)P.t.max_chars;
+      if (!bad) {
+        int start = s;
+        while (start < e) {
+          uint32_t node = (start == s) ? 0u : 1u, best_id = 0;
+          int best_end = -1;
+          for (int p = start; p < e; ++p) {
+            const uint32_t key = (node << 8) | s_byte[p];
+            uint32_t slot = edge_hash(node, s_byte[p]) & P.t.edge_mask;
+            uint4 en;
+            while (true) {
+              en = __ldg(P.t.edge_tbl + slot);
+              if (en.x == key || en.x == EMPTY_KEY) break;
+              slot = (slot + 1) & P.t.edge_mask;
+            }
+            if (en.x == EMPTY_KEY) break;
+            node = en.y;
+            if (en.z != EMPTY_KEY) { best_id = en.z; best_end = p + 1; }
+          }
+          if (best_end < 0) { bad = true; break; }
+          s_id[start] = best_id; s_len[start] = (uint16_t)(best_end - start);
+          start = best_end;
+        }
+      }
+      if (bad) {
+        for (int p = s; p < e; ++p) s_len[p] = 0;
+        s_id[s] = P.t.unk_id; s_len[s] = (uint16_t)len;
+      }
+    }
+    // a LONG split (> 416 bytes) has more than max_input_chars_per_word (<= 100 * 4 bytes) characters: it is [UNK];
+    // count its characters for the end offset
+    if (is_long) {
+      const int64_t ls = base + s_pt[Pn - 1], le = s_long_end;
+      int cnt = 0;
+      for (int64_t p = ls + tid; p < le; p += MODEL_THREADS) cnt += ((__ldg(P.bytes + p) & 0xC0u) != 0x80u);
+#pragma unroll
+      for (int sft = 16; sft >= 1; sft >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, sft);
+      if (lane == 0) atomicAdd(&s_long_chars, cnt);
+    }
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- P5: token bitmap and count
+  for (int row = warp; row < NW; row += NWARPS) {
+    int pos = row * 32 + lane;
+    bool tok = pos >= first && pos < Eproc && s_len[pos] != 0;
+    uint32_t tb = __ballot_sync(0xFFFFFFFFu, tok);
+    if (lane == 0) s_tokb[row] = tb;
+  }
+  __syncthreads();
+  const bool long_kept = is_long && ((s_keptb[s_pt[Pn - 1] >> 5] >> (s_pt[Pn - 1] & 31)) & 1u);
+  if (warp == 0) {
+    int tot = warp_prefix_words(s_tokb, s_tpref, NW, lane);
+    const int A = tot + ((MODEL == MODEL_WORDPIECE && long_kept) ? 1 : 0);
+    // ---------------------------------------------------------------- P6: decoupled look-back over the pages
+    unsigned long long excl = 0;
+    volatile unsigned long long* st = P.tile_state;
+    if (t == 0) {
+      if (lane == 0) st[0] = B2T_ST_INCL | (unsigned long long)A;
+    } else {
+      if (lane == 0) st[t] = B2T_ST_AGG | (unsigned long long)A;
+      int64_t look = t - 1;
+      while (true) {
+        int64_t idx = look - lane;
+        unsigned long long v = idx >= 0 ? st[idx] : B2T_ST_INCL;
+        unsigned fl = (unsigned)(v >> 62);
+        unsigned pend = __ballot_sync(0xFFFFFFFFu, fl == 0u);
+        unsigned incl = __ballot_sync(0xFFFFFFFFu, fl == 2u);
+        unsigned need = incl ? ((1u << (__ffs((int)incl) - 1)) - 1u) | (1u << (__ffs((int)incl) - 1)) : 0xFFFFFFFFu;
+        if (pend & need) continue;  // a needed predecessor has not published yet
+        unsigned long long c = ((1u << lane) & need) ? (v & B2T_ST_VAL) : 0ull;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, s);
+        excl += c;
+        if (incl) break;
+        look -= 32;
+      }
+      if (lane == 0) st[t] = B2T_ST_INCL | (excl + (unsigned long long)A);
+    }
+    if (lane == 0) {
+      s_excl = excl; s_ntok = A;
+      if (t == P.n_tiles - 1) *P.total_out = excl + (unsigned long long)A;
+    }
+  }
+  __syncthreads();
+  const unsigned long long excl = s_excl;
+  const uint64_t carry = __ldg(P.page_carry + t);
+  const int carry_chars = (int)(uint32_t)carry, carry_starts = (int)(uint32_t)(carry >> 32);
+  const bool want_off = P.flags & F_OFFSETS, want_wid = P.flags & F_WORD_IDS, byte_off = P.flags & F_BYTE_OFFSETS;
+
+  // ---------------------------------------------------------------- P7: emit tokens in order
+  auto lc_incl = [&](int x) -> int { return (int)s_lpref[x >> 5] + __popc(s_leadb[x >> 5] & mask_le(x & 31)); };
+  auto kept_incl = [&](int x) -> int { return (int)s_spref[x >> 5] + __popc(s_keptb[x >> 5] & mask_le(x & 31)); };
+  auto doc_base = [&](int x) -> int {  // last doc start at or before x inside the page, or -1
+    int xx = x < TILE ? x : TILE - 1;
+    uint32_t m = s_dsb[xx >> 5] & mask_le(xx & 31);
+    return m ? (xx & ~31) + 31 - __clz((int)m) : (int)s_dlast[xx >> 5];
+  };
+  auto emit = [&](unsigned long long out, uint32_t id, int ts, int64_t tend_abs, int end_chars_in_page, bool end_known) {
+    // ts: token start (page-relative); tend_abs: absolute end byte; end_chars_in_page: lc_incl(e-1) if end_known
+    P.ids[out] = id;
+    const int D = doc_base(ts);
+    if (want_off) {
+      uint32_t o0, o1;
+      if (!byte_off) {
+        const int cb = D >= 0 ? lc_incl(D) - 1 : -carry_chars;  // chars before the doc start, page-relative
+        o0 = (uint32_t)(lc_incl(ts) - 1 - cb);
+        o1 = (uint32_t)(end_chars_in_page - cb);
+      } else {
+        int64_t ds = D >= 0 ? base + D : s_span_doc_start;
+        int64_t gs = base + ts, ge = tend_abs;
+        while (gs > 0 && (__ldg(P.bytes + gs) & 0xC0u) == 0x80u) --gs;
+        while (ge < n && (__ldg(P.bytes + ge) & 0xC0u) == 0x80u) ++ge;
+        o0 = (uint32_t)(gs - ds); o1 = (uint32_t)(ge - ds);
+      }
+      (void)end_known;
+      reinterpret_cast<uint2*>(P.offsets)[out] = make_uint2(o0, o1);
+    }
+    if (want_wid) {
+      const int wb = D >= 0 ? kept_incl(D) - 1 : -carry_starts;
+      P.word_ids[out] = (uint32_t)(kept_incl(ts) - 1 - wb);
+    }
+  };
+  for (int row = warp; row < NW; row += NWARPS) {
+    const uint32_t tb = s_tokb[row];
+    if (!((tb >> lane) & 1u)) continue;
+    const int pos = row * 32 + lane;
+    const unsigned long long out = excl + s_tpref[row] + __popc(tb & ((1u << lane) - 1u));
+    const int e = pos + s_len[pos];
+    emit(out, s_id[pos], pos, base + e, lc_incl(e - 1), true);
+  }
+  if (MODEL == MODEL_WORDPIECE && long_kept && tid == 0) {
+    const int ls = s_pt[Pn - 1];
+    const unsigned long long out = excl + (unsigned long long)(s_ntok - 1);
+    // chars up to the end of the long split = chars before it in the page + its own
+    const int end_chars = lc_incl(ls) - 1 + s_long_chars;
+    emit(out, P.t.unk_id, ls, s_long_end, end_chars, true);
+  }
+
+  // ---------------------------------------------------------------- P8: row_ptr of the documents starting in this page
+  {
+    const uint32_t fd = __ldg(P.page_first_doc + t);
+    for (uint64_t d = (uint64_t)fd + tid; d <= P.n_docs; d += MODEL_THREADS) {
+      const int64_t pos = (int64_t)__ldg(P.doc_off + d) - base;
+      if (pos >= TILE) break;
+      // tokens that start before `pos` (a doc start is a pre-token start, so no token straddles it)
+      const int before = pos == 0 ? 0 : (int)s_tpref[(pos - 1) >> 5] + __popc(s_tokb[(pos - 1) >> 5] & mask_le((int)((pos - 1) & 31)));
+      P.row_ptr[d] = excl + (unsigned long long)before;
+    }
+  }
+}
+
+}  // namespace b2t

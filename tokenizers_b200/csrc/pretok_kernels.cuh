@@ -1,0 +1,238 @@
+// pretok_kernels.cuh -- K0 doc_mark, K1 pretok_scan (the HBM-roofline-graded kernel), K1b page_scan.
+//
+// Data layout in HBM (one batch = `n` packed UTF-8 bytes, documents back to back):
+//   bytes      u8 [n]                input, read once by K1 with 16-byte loads
+//   doc_bits   u32[n/32 + 2]         bit p set <=> some document starts at byte p (K0; bit n is the end sentinel)
+//   start_bits u32[n/32 + 2]         bit p set <=> a pre-token (split) starts at byte p            (K1 output)
+//   drop_bits  u32[n/32 + 2]         Whitespace only: the split starting at p is removed whitespace (K1 output)
+//   page_sum   u64[n/2048 + 1]       per 2 KB page: #chars, #kept splits, and the same counted from the last doc start
+//   page_carry u64[n/2048 + 1]       K1b: #chars (low 32) / #kept splits (high 32) of the document that spans into the
+//                                    page, counted from that document's start to the page start
+//   page_first_doc u32[n/2048 + 1]   K0: first document d with doc_off[d] >= page start
+// K1 algorithmic traffic: n bytes in + n/8 (doc_bits) in + n/8 (start_bits) out = 1.25 B per input byte.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pretok_logic.cuh"
+
+namespace b2t {
+
+struct ByteAtGlobal {
+  const uint8_t* __restrict__ p;
+  int64_t n;
+  __device__ __forceinline__ uint32_t operator()(int64_t i) const { return (i >= 0 && i < n) ? (uint32_t)__ldg(p + i) : 0u; }
+};
+
+// ------------------------------------------------------------------------------------------------ K0
+// One thread per document boundary d in [0, n_docs]: marks the doc start bit and fills page_first_doc.
+__global__ void doc_mark_kernel(const uint64_t* __restrict__ doc_off, uint32_t n_docs, uint32_t* __restrict__ doc_bits,
+                                uint32_t* __restrict__ page_first_doc) {
+  uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d > n_docs) return;
+  uint64_t pos = doc_off[d];
+  atomicOr(&doc_bits[pos >> 5], 1u << (pos & 31));
+  uint64_t p_hi = pos / PAGE;
+  uint64_t p_lo = (d == 0) ? 0 : doc_off[d - 1] / PAGE + 1;
+  for (uint64_t p = p_lo; p <= p_hi; ++p) page_first_doc[p] = d;
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+__device__ __forceinline__ void load_chunk_words(const uint8_t* __restrict__ bytes, int64_t base, int64_t n, uint32_t w[8]) {
+  if (base + CHUNK <= n) {
+    const uint4* q = reinterpret_cast<const uint4*>(bytes + base);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t x = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int64_t p = base + j * 4 + k;
+        if (p < n) x |= (uint32_t)__ldg(bytes + p) << (8 * k);
+      }
+      w[j] = x;
+    }
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ ChunkMasks classify_global(const uint8_t* __restrict__ bytes, int64_t n, int64_t chunk,
+                                                      const uint32_t* __restrict__ cls_tbl) {
+  ChunkMasks m;
+  int64_t base = chunk * CHUNK;
+  if (chunk < 0 || base >= n) {
+    m.lead = m.L = m.N = m.S = m.SP = m.NL = m.AP = 0u;
+    return m;
+  }
+  uint32_t w[8];
+  load_chunk_words(bytes, base, n, w);
+  ByteAtGlobal at{bytes, n};
+  return classify_chunk(w, base, n, at, cls_tbl, KIND == PT_WHITESPACE);
+}
+
+// masks of any chunk: from shared memory when it belongs to the tile (+-1 chunk), else re-classified from global
+template <int KIND, int TC>
+struct TileMaskAt {
+  const ChunkMasks* sm;  // TC + 2 entries, entry 0 = chunk tile_c0 - 1
+  int64_t tile_c0;
+  const uint8_t* __restrict__ bytes;
+  int64_t n;
+  const uint32_t* __restrict__ cls_tbl;
+  __device__ __forceinline__ ChunkMasks operator()(int64_t k) const {
+    int64_t r = k - tile_c0 + 1;
+    if (r >= 0 && r < TC + 2) return sm[r];
+    return classify_global<KIND>(bytes, n, k, cls_tbl);
+  }
+};
+struct DsAtGlobal {
+  const uint32_t* __restrict__ doc_bits;
+  int64_t n_chunks;
+  __device__ __forceinline__ uint32_t operator()(int64_t k) const { return (k >= 0 && k < n_chunks) ? __ldg(doc_bits + k) : 0u; }
+};
+
+// page summary packing: [11:0] chars, [23:12] kept splits, [35:24] chars since last doc start, [47:36] splits since, [48] has doc start
+__device__ __forceinline__ uint64_t pack_sum(uint32_t tot, uint32_t aft, uint32_t flag) {
+  // tot / aft carry two 16-bit fields each (chars | splits << 16)
+  return (uint64_t)(tot & 0xFFFu) | ((uint64_t)((tot >> 16) & 0xFFFu) << 12) | ((uint64_t)(aft & 0xFFFu) << 24) |
+         ((uint64_t)((aft >> 16) & 0xFFFu) << 36) | ((uint64_t)(flag & 1u) << 48);
+}
+
+template <int KIND, int TC>
+__global__ void __launch_bounds__(TC) pretok_scan_kernel(const uint8_t* __restrict__ bytes, int64_t n,
+                                                         const uint32_t* __restrict__ doc_bits,
+                                                         const uint32_t* __restrict__ cls_tbl,
+                                                         uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
+                                                         uint64_t* __restrict__ page_sum, int64_t n_tiles) {
+  __shared__ ChunkMasks sm[TC + 2];
+  __shared__ uint32_t sds[TC + 2];
+  __shared__ uint32_t s_wsum[(TC / 32) * 3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n_chunks = n / CHUNK + 1;
+  ByteAtGlobal at{bytes, n};
+  DsAtGlobal dsat{doc_bits, n_chunks};
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t c0 = tile * TC, c = c0 + tid;
+    // ---- phase A: class masks of my chunk (+ the two halo chunks) into shared memory
+    sm[tid + 1] = classify_global<KIND>(bytes, n, c, cls_tbl);
+    sds[tid + 1] = dsat(c);
+    if (tid < 2) {
+      int64_t hc = tid == 0 ? c0 - 1 : c0 + TC;
+      sm[tid == 0 ? 0 : TC + 1] = classify_global<KIND>(bytes, n, hc, cls_tbl);
+      sds[tid == 0 ? 0 : TC + 1] = dsat(hc);
+    }
+    __syncthreads();
+    // ---- phase B: boundaries of my 32 positions from the 64-byte window
+    BoundaryOut r;
+    uint32_t own_lead, own_ds;
+    {
+      const ChunkMasks p = sm[tid], o = sm[tid + 1], x = sm[tid + 2];
+      Window w;
+      w.lead = win(p.lead, o.lead, x.lead); w.L = win(p.L, o.L, x.L); w.N = win(p.N, o.N, x.N); w.S = win(p.S, o.S, x.S);
+      w.SP = win(p.SP, o.SP, x.SP); w.NL = win(p.NL, o.NL, x.NL); w.AP = win(p.AP, o.AP, x.AP);
+      w.DS = win(sds[tid], sds[tid + 1], sds[tid + 2]);
+      own_lead = o.lead; own_ds = sds[tid + 1];
+      const int64_t wb = c * CHUNK - 16;
+      if (KIND == PT_GPT2) {
+        r = boundaries_gpt2(w, wb, at);
+      } else if (KIND == PT_LLAMA3) {
+        LlamaCarry cy; cy.n_count_before_window = 0; cy.zone_before_window = false; cy.tail_after_window = false;
+        r = boundaries_llama3(w, wb, at, cy);
+        if (r.slow) {
+          TileMaskAt<KIND, TC> masks{sm, c0, bytes, n, cls_tbl};
+          cy = llama_carry(c, n_chunks, masks, dsat);
+          r = boundaries_llama3(w, wb, at, cy);
+        }
+      } else if (KIND == PT_WHITESPACE) {
+        r = boundaries_whitespace(w);
+      } else {
+        r.start = (uint32_t)((w.DS & w.lead) >> 16); r.drop = 0; r.slow = 0;
+      }
+    }
+    if (c < n_chunks) {
+      start_bits[c] = r.start;
+      if (KIND == PT_WHITESPACE) drop_bits[c] = r.drop;
+    }
+    // ---- page summaries (segmented: counts restart at the last doc start of the page)
+    {
+      uint32_t kept = r.start & ~r.drop;
+      uint32_t tot = (uint32_t)__popc(own_lead) | ((uint32_t)__popc(kept) << 16);
+      uint32_t flag = own_ds != 0u, aft = 0u;
+      if (flag) {
+        uint32_t from = ~bits_below(31 - __clz((int)own_ds));
+        aft = (uint32_t)__popc(own_lead & from) | ((uint32_t)__popc(kept & from) << 16);
+      }
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {  // combine(mine = earlier, other = later)
+        uint32_t o_tot = __shfl_down_sync(0xFFFFFFFFu, tot, s), o_aft = __shfl_down_sync(0xFFFFFFFFu, aft, s),
+                 o_flag = __shfl_down_sync(0xFFFFFFFFu, flag, s);
+        if (lane + s < 32) {
+          aft = o_flag ? o_aft : aft + o_tot;
+          tot += o_tot;
+          flag |= o_flag;
+        }
+      }
+      if (lane == 0) { s_wsum[warp * 3] = tot; s_wsum[warp * 3 + 1] = aft; s_wsum[warp * 3 + 2] = flag; }
+      __syncthreads();
+      constexpr int WPP = PAGE_CHUNKS / 32;  // warps per page (2)
+      if (tid < TC / 32 / WPP) {
+        uint32_t t0 = s_wsum[(tid * WPP) * 3], a0 = s_wsum[(tid * WPP) * 3 + 1], f0 = s_wsum[(tid * WPP) * 3 + 2];
+#pragma unroll
+        for (int k = 1; k < WPP; ++k) {
+          uint32_t t1 = s_wsum[(tid * WPP + k) * 3], a1 = s_wsum[(tid * WPP + k) * 3 + 1], f1 = s_wsum[(tid * WPP + k) * 3 + 2];
+          a0 = f1 ? a1 : a0 + t1; t0 += t1; f0 |= f1;
+        }
+        int64_t page = tile * (TC / PAGE_CHUNKS) + tid;
+        if (page * PAGE <= n) page_sum[page] = pack_sum(t0, a0, f0);
+      }
+    }
+    __syncthreads();  // shared memory is reused by the next tile
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1b
+// Exclusive segmented scan over the page summaries -> page_carry (single block; n_pages ~ n/2048 entries).
+__device__ __forceinline__ void sum_unpack(uint64_t s, uint32_t& tc, uint32_t& ts, uint32_t& ac, uint32_t& as, uint32_t& f) {
+  tc = (uint32_t)(s & 0xFFFu); ts = (uint32_t)((s >> 12) & 0xFFFu); ac = (uint32_t)((s >> 24) & 0xFFFu);
+  as = (uint32_t)((s >> 36) & 0xFFFu); f = (uint32_t)((s >> 48) & 1u);
+}
+
+__global__ void __launch_bounds__(1024) page_scan_kernel(const uint64_t* __restrict__ page_sum, uint64_t* __restrict__ page_carry,
+                                                         int64_t n_pages) {
+  __shared__ uint32_t s_c[1024], s_s[1024], s_f[1024];
+  const int tid = threadIdx.x;
+  const int64_t per = (n_pages + 1023) / 1024;
+  const int64_t lo = (int64_t)tid * per, hi = (lo + per < n_pages) ? lo + per : n_pages;
+  // pass 1: summary of my segment as a function of the incoming carry: out = flag ? after : in + total
+  uint32_t totc = 0, tots = 0, aftc = 0, afts = 0, flag = 0;
+  for (int64_t p = lo; p < hi; ++p) {
+    uint32_t tc, ts, ac, as, f;
+    sum_unpack(page_sum[p], tc, ts, ac, as, f);
+    if (f) { aftc = ac; afts = as; flag = 1; } else { aftc += tc; afts += ts; }
+    totc += tc; tots += ts;
+  }
+  // "aft*" now = chars/splits since the last doc start in the segment (or since segment start if none)
+  s_c[tid] = aftc; s_s[tid] = afts; s_f[tid] = flag;
+  __syncthreads();
+  // exclusive segmented scan over the 1024 segment summaries (Hillis-Steele on (value, flag))
+  uint32_t vc = aftc, vs = afts, vf = flag;
+  for (int s = 1; s < 1024; s <<= 1) {
+    uint32_t oc = 0, os = 0, of = 0;
+    if (tid >= s) { oc = s_c[tid - s]; os = s_s[tid - s]; of = s_f[tid - s]; }
+    __syncthreads();
+    if (tid >= s && !vf) { vc += oc; vs += os; vf = of; }
+    s_c[tid] = vc; s_s[tid] = vs; s_f[tid] = vf;
+    __syncthreads();
+  }
+  uint32_t cc = tid ? s_c[tid - 1] : 0u, cs = tid ? s_s[tid - 1] : 0u;  // carry into my segment
+  // pass 2
+  for (int64_t p = lo; p < hi; ++p) {
+    page_carry[p] = (uint64_t)cc | ((uint64_t)cs << 32);
+    uint32_t tc, ts, ac, as, f;
+    sum_unpack(page_sum[p], tc, ts, ac, as, f);
+    if (f) { cc = ac; cs = as; } else { cc += tc; cs += ts; }
+  }
+}
+
+}  // namespace b2t
