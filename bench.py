@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- encode_batch throughput of the B200 engine on BASELINE.json's headline config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mb 1024] [--config gpt2|llama3|wordpiece]
+
+One step = one pass of the whole hot path (doc_mark -> pretok_scan -> page_scan -> bpe_tile) over one batch of the
+synthetic corpus of SURVEY.md §8(d) config 2 ("GPT-2 ByteLevel BPE, 1 GB synthetic UTF-8 docs avg 512 B").  Prints ONE
+JSON line (rank 0).  `value` is device-resident (input already in HBM, CUDA events); `e2e` goes through the C-ABI call
+b2t_encode_batch with pinned HOST buffers, copies inside the timed region; `roofline` is the pre-tokenization scan
+kernel (the HBM-bound one) from CUDA events recorded on its launch stream; `cpu_baseline` is the reference's own Rust
+implementation (the `tokenizers` wheel) on this box's host cores over a bounded sample.
+
+With N > 1 (torchrun) every rank encodes its own shard of N x the corpus (weak scaling) and the token CSR is
+all-gathered over NCCL at the end of each step, as BASELINE.json's north_star describes the path.
+"""
+import argparse, ctypes, gzip, json, os, subprocess, sys, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import numpy as np  # noqa: E402
+
+ASSET = {"gpt2": "gpt2_style", "llama3": "llama3_style", "wordpiece": "wordpiece"}
+KIND = {"gpt2": 2, "llama3": 2, "wordpiece": 4}
+SEED = {"gpt2": 2, "llama3": 3, "wordpiece": 4}
+
+
+def tokenizer_json(cfg):
+    return gzip.open(os.path.join(ROOT, "assets", ASSET[cfg] + ".json.gz")).read().decode("utf-8")
+
+
+def gen_corpus(kind, seed, first_doc, n_docs, max_bytes, out):
+    """Generate docs [first_doc, ...) into `out` (np.uint8 view of pinned memory) with 8 host threads."""
+    import corpus
+    corpus.build()
+    nthr = 8
+    per = (n_docs + nthr - 1) // nthr
+    parts = [None] * nthr
+    cap_each = max_bytes // nthr
+
+    def work(i):
+        buf = np.empty(cap_each + 200000, dtype=np.uint8)
+        d, o = corpus.generate(kind, seed, first_doc + i * per, per, max_bytes=cap_each, out=buf)
+        parts[i] = (d, o)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(nthr)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    pos, offs = 0, [np.zeros(1, dtype=np.uint64)]
+    for d, o in parts:
+        out[pos:pos + len(d)] = d
+        offs.append(o[1:] + np.uint64(pos))
+        pos += len(d)
+    return pos, np.concatenate(offs)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.p, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(cfg, data, off, budget_s=15.0):
+    """The reference's own Rust/rayon encode_batch (tokenizers wheel) on all host cores over a bounded sample."""
+    cores = len(os.sched_getaffinity(0))
+    os.environ.setdefault("TOKENIZERS_PARALLELISM", "true")
+    os.environ.setdefault("RAYON_NUM_THREADS", str(cores))
+    import tokenizers
+    tok = tokenizers.Tokenizer.from_str(tokenizer_json(cfg))
+    raw = data.tobytes() if len(data) < (1 << 28) else data[: 1 << 28].tobytes()
+    n_avail = int(np.searchsorted(off, len(raw), side="right")) - 1
+
+    def docs(n):
+        return [raw[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(n)]
+    probe_n = min(n_avail, 16384)
+    d = docs(probe_n)
+    tok.encode_batch(d[:2048], add_special_tokens=False)  # warm-up (rayon pool, caches)
+    t0 = time.perf_counter(); enc = tok.encode_batch(d, add_special_tokens=False); t1 = time.perf_counter()
+    rate = int(off[probe_n]) / (t1 - t0)
+    n = int(min(n_avail, max(probe_n, np.searchsorted(off, rate * budget_s))))
+    d = docs(n)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter(); enc = tok.encode_batch(d, add_special_tokens=False); dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    nbytes = int(off[n]); ntok = sum(len(e.ids) for e in enc)
+    return {"value": nbytes / best / 1e9, "unit": "GB/s", "tokens_per_s": ntok / best, "cores": cores, "kind": "reference",
+            "sample": f"tokenizers wheel {tokenizers.__version__} Tokenizer.encode_batch (char offsets) on the first {n} docs / {nbytes / 1e6:.1f} MB of the same corpus, best of 2",
+            "seconds": best}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mb", type=int, default=1024, help="corpus size per GPU in MiB")
+    ap.add_argument("--config", default="gpt2", choices=list(ASSET))
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = a.config
+    workload = {"gpt2": "GPT-2 ByteLevel BPE (50257 vocab trained offline by the reference trainer), synthetic UTF-8 docs avg ~480 B",
+                "llama3": "Llama-3-style BPE (tiktoken regex, 128k vocab, ignore_merges)", "wordpiece": "Whitespace + WordPiece 30522"}[cfg]
+    max_bytes = a.mb << 20
+    n_docs_target = max_bytes // 300
+
+    if a.impl == "reference":
+        # the reference's CPU implementation, all host threads, bounded sample per step; rank 0 only
+        if rank != 0:
+            return
+        buf = np.empty(min(max_bytes, 256 << 20) + (1 << 20), dtype=np.uint8)
+        n, off = gen_corpus(KIND[cfg], SEED[cfg], 0, min(n_docs_target, (256 << 20) // 300), min(max_bytes, 256 << 20), buf)
+        per_step = []
+        for s in range(a.warmup + a.steps):
+            r = cpu_reference(cfg, buf[:n], off, budget_s=max(2.0, 60.0 / (a.warmup + a.steps)))
+            if s >= a.warmup:
+                per_step.append(r)
+        r = max(per_step, key=lambda x: x["value"])
+        out = {"impl": "reference", "metric": "encode_batch input throughput", "value": r["value"], "unit": "GB/s", "tokens_per_s": r["tokens_per_s"],
+               "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": workload, "bytes_per_step": None, "sample": r["sample"]},
+               "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+               "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(out))
+        return
+
+    import torch
+    from tokenizers_b200 import Tokenizer, _lib
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.lib()
+    tok = Tokenizer.from_str(tokenizer_json(cfg), device=local)
+
+    # ---- corpus: this rank's shard, generated straight into pinned host memory
+    hptr = ctypes.c_void_p()
+    _lib.check(L.b2t_host_alloc(max_bytes + (1 << 20), ctypes.byref(hptr)))
+    hbuf = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint8)), shape=(max_bytes + (1 << 20),))
+    n, off = gen_corpus(KIND[cfg], SEED[cfg], rank * n_docs_target, n_docs_target, max_bytes, hbuf)
+    n_docs = len(off) - 1
+    hoff_ptr = ctypes.c_void_p()
+    _lib.check(L.b2t_host_alloc((n_docs + 1) * 8, ctypes.byref(hoff_ptr)))
+    hoff = np.ctypeslib.as_array(ctypes.cast(hoff_ptr, ctypes.POINTER(ctypes.c_uint64)), shape=(n_docs + 1,))
+    hoff[:] = off
+    d_bytes = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+    d_bytes[:n].copy_(torch.from_numpy(hbuf[:n]))
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    torch.cuda.synchronize()
+    flags = _lib.WANT_OFFSETS
+    stream = torch.cuda.current_stream()
+    _lib.check(L.b2t_engine_set_profiling(tok.handle, 1))
+
+    class DevArr:  # zero-copy torch view of an engine-owned device buffer
+        def __init__(self, ptr, count, typestr):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+    gbuf = {}
+
+    def step_device():
+        res = ctypes.c_void_p()
+        _lib.check(L.b2t_encode_batch_device(tok.handle, d_bytes.data_ptr(), n, d_off.data_ptr(), n_docs, flags, ctypes.c_void_p(stream.cuda_stream), ctypes.byref(res)))
+        T = L.b2t_result_n_tokens(res)
+        if world > 1:  # one all-gather-v of the token CSR (counts, then padded payloads)
+            cnt = torch.tensor([T], dtype=torch.int64, device="cuda")
+            cnts = torch.empty(world, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(cnts, cnt)
+            mx = int(cnts.max().item())
+            ids = torch.as_tensor(DevArr(L.b2t_result_ids(res), mx, "<i4"), device="cuda")
+            offs = torch.as_tensor(DevArr(L.b2t_result_offsets(res), 2 * mx, "<i4"), device="cuda")
+            if gbuf.get("ids") is None or gbuf["ids"].numel() < world * mx:
+                gbuf["ids"] = torch.empty(world * mx, dtype=torch.int32, device="cuda")
+                gbuf["off"] = torch.empty(2 * world * mx, dtype=torch.int32, device="cuda")
+            dist.all_gather_into_tensor(gbuf["ids"][: world * mx], ids)
+            dist.all_gather_into_tensor(gbuf["off"][: 2 * world * mx], offs)
+        L.b2t_result_free(res)
+        return T
+
+    names = (ctypes.c_char_p * 16)(); ms = (ctypes.c_float * 16)()
+    for _ in range(a.warmup):
+        T = step_device()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kern_ms = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    launches = 0
+    for _ in range(a.steps):
+        T = step_device()
+        launches += L.b2t_engine_last_kernels(tok.handle, names, ms, 16)
+        for i in range(16):
+            if names[i] is None:
+                break
+            kern_ms.setdefault(names[i].decode(), []).append(ms[i])
+        for i in range(16):
+            names[i] = None
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the C ABI with pinned host buffers (H2D + kernels + D2H inside the call)
+    _lib.check(L.b2t_engine_set_profiling(tok.handle, 0))
+
+    def step_e2e():
+        res = ctypes.c_void_p()
+        _lib.check(L.b2t_encode_batch(tok.handle, hptr, hoff_ptr, n_docs, flags, ctypes.byref(res)))
+        T = L.b2t_result_n_tokens(res)
+        L.b2t_result_free(res)
+        return T
+    for _ in range(a.warmup):
+        step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        Te = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert Te == T
+
+    # ---- reduce over ranks: time = max, work = sum
+    if world > 1:
+        v = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        w = torch.tensor([float(n), float(T)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms = v.tolist(); tot_bytes, tot_tok = w.tolist()
+    else:
+        e2e_ms, tot_bytes, tot_tok = e2e_s * 1e3, float(n), float(T)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = dev_ms / a.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    k1 = float(np.mean(kern_ms.get("pretok_scan", [float("nan")])))
+    k1_bytes = n * 1.25 + (n / 2048) * 8  # bytes + doc_bits in, start_bits + page summaries out
+    roof = {"kernel": "pretok_scan_kernel", "bound": "hbm", "achieved": k1_bytes / (k1 * 1e-3) / 1e9, "peak": peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback (of fallback)",
+            "unit": "GB/s", "frac": k1_bytes / (k1 * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1,
+            "input_GBps": n / (k1 * 1e-3) / 1e9}
+    out = {"metric": "encode_batch input throughput", "value": tot_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
+           "tokens_per_s": tot_tok / (ms_per_step * 1e-3), "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+           "config": {"workload": workload + f", {n / 1e6:.0f} MB / {n_docs} docs per GPU, ids + char offsets", "bytes_per_gpu": n, "docs_per_gpu": n_docs,
+                      "tokens_per_gpu": int(T), "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"docs sharded over {world} rank(s)" + (", NCCL all-gather-v of ids/offsets per step" if world > 1 else "")},
+           "kernels_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()},
+           "roofline": roof,
+           "e2e": {"value": tot_bytes / (e2e_ms / a.steps * 1e-3) / 1e9, "unit": "GB/s", "tokens_per_s": tot_tok / (e2e_ms / a.steps * 1e-3), "ms_per_step": e2e_ms / a.steps,
+                   "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(T * 12 + (n_docs + 1) * 8 + 16 * ((n >> 26) + 1))},
+           "gpu_launches": int(launches), "clocks": clocks}
+    if not a.no_cpu and world == 1:
+        try:
+            out["cpu_baseline"] = {k: v for k, v in cpu_reference(cfg, hbuf[:n], off).items() if k != "seconds"}
+        except Exception as ex:  # the wheel is part of the image; if it is missing say so instead of inventing a number
+            out["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": len(os.sched_getaffinity(0)), "kind": "reference", "sample": f"unavailable: {ex}"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

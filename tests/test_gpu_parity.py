@@ -50,10 +50,10 @@ def test_gpu_matches_oracle_fuzz(name):
 
 
 @pytest.mark.parametrize("name", ASSET_NAMES)
-@pytest.mark.parametrize("kind", [1, 2, 4])
+@pytest.mark.parametrize("kind", [1, 2, 4, 5])
 def test_gpu_matches_oracle_corpus(name, kind):
     tok, o, _ = engine(name)
-    data, off = corpus.generate(kind, 10 + kind, 0, 4000)
+    data, off = corpus.generate(kind, 10 + kind, 0, 4000 if kind != 5 else 6000)
     be = tok.encode_batch_csr(data, off)
     exp = o.encode_batch_csr(data, off)
     helpers.assert_csr_equal((be.ids, be.offsets, be.word_ids, be.row_ptr), exp, corpus.to_strings(data, off), f"{name} corpus {kind}")
@@ -92,6 +92,25 @@ def test_multi_chunk_host_pipeline(name):
     data, off = corpus.generate(2, 5, 0, 700)
     docs = corpus.to_strings(data, off) + ["", "", "x"]
     helpers.assert_csr_equal(gpu_csr(tok, docs), o.encode_batch(docs), docs, f"{name} multi-chunk")
+
+
+def test_long_pretokens_monotone_and_not():
+    """Pre-tokens longer than 256 bytes take the long path (pre-pass); hand-written NON-monotone merges force its
+    one-merge-per-round mode, trained vocabularies the all-occurrences mode."""
+    import random
+    tj, _ = helpers.load_golden("nonmonotone")
+    tok, o = Tokenizer.from_str(tj), orc.Oracle(tj)
+    rng = random.Random(5)
+    docs = ["ab" * 400, "a" * 1000, "aab" * 300 + " " + "ba" * 200, "x" + "ab" * 129, "ab" * 128, "ab" * 128 + "a",
+            "".join(rng.choice("ab") for _ in range(5000)), "".join(rng.choice("ab ") for _ in range(3000)), "b" * 257 + " " + "a" * 2500]
+    helpers.assert_csr_equal(gpu_csr(tok, docs), o.encode_batch(docs), docs, "nonmonotone long")
+    helpers.assert_csr_equal(gpu_csr(tok, docs, byte_offsets=True), o.encode_batch(docs, offset_type=orc.OFF_BYTE), docs, "nonmonotone long bytes")
+    for name in ("gpt2_style", "llama3_style"):
+        tok, o, _ = engine(name)
+        docs = ["a" * 70000, " " * 66000 + "x", "é" * 5000, "".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(40000)),
+                "the" * 1000 + " and " + "1" * 3000, "\n" * 3000 + "x" * 300, "z" * 257, "z" * 256, "hello " + "q" * 2047 + " world",
+                "".join(rng.choice("etaoinshr") for _ in range(300)) + " end", "中" * 2000, "😀" * 700]
+        helpers.assert_csr_equal(gpu_csr(tok, docs), o.encode_batch(docs), docs, f"{name} long")
 
 
 def test_edge_batches():

@@ -52,6 +52,7 @@ struct DeviceTables {
   uint32_t word_mask;
   const uint8_t* word_pool;    // token strings as raw bytes (ByteLevel chars mapped back to bytes)
   int ignore_merges;
+  int monotone;                // every merge ranks after all merges creating its parts (long_kernels.cuh)
   // WordPiece: byte trie, two roots (0 = word start, 1 = after the continuing-subword prefix)
   const uint4* edge_tbl;       // {node << 8 | byte, child node, token id of child or EMPTY_KEY, 0}; x == EMPTY_KEY free
   uint32_t edge_mask;

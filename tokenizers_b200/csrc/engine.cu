@@ -17,6 +17,7 @@
 
 #include "../../include/b2t.h"
 #include "host_tables.h"
+#include "long_kernels.cuh"
 #include "model_kernels.cuh"
 #include "pretok_kernels.cuh"
 
@@ -83,6 +84,8 @@ struct Workspace {
   DevBuf bytes, doc_off;              // only used by the host path (inputs staged on the device)
   DevBuf doc_bits, start_bits, drop_bits, page_sum, page_carry, page_first_doc, tile_state, ctl;
   DevBuf ids, offsets, word_ids, row_ptr;
+  DevBuf page_long, long_desc, lp_id, lp_val, lp_len, lp_plen, lp_aux, lp_out;  // long BPE pre-tokens (long_kernels.cuh)
+  unsigned long long pool_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   PinBuf h_ctl;                        // total tokens + error flag read back
@@ -90,6 +93,7 @@ struct Workspace {
     bytes.release(); doc_off.release(); doc_bits.release(); start_bits.release(); drop_bits.release(); page_sum.release();
     page_carry.release(); page_first_doc.release(); tile_state.release(); ctl.release(); ids.release(); offsets.release();
     word_ids.release(); row_ptr.release(); h_ctl.release();
+    page_long.release(); long_desc.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
     stream = nullptr; done = nullptr;
@@ -113,6 +117,7 @@ struct b2t_engine {
   int model = 0, pretok = 0, add_prefix_space = 0;
   int sm_count = 148;
   DeviceTables dt;
+  int monotone = 0;
   DevBuf d_cls, d_byte_to_id, d_merge, d_word, d_pool, d_edge;
   std::mutex mu;
   Workspace dev_ws;          // b2t_encode_batch_device
@@ -192,6 +197,8 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
   e->dt.word_mask = ht.word_tbl.empty() ? 0 : (uint32_t)ht.word_tbl.size() - 1;
   e->dt.word_pool = e->d_pool.as<uint8_t>();
   e->dt.ignore_merges = cfg->ignore_merges ? 1 : 0;
+  e->dt.monotone = ht.monotone ? 1 : 0;
+  e->monotone = e->dt.monotone;
   e->dt.edge_tbl = e->d_edge.as<uint4>();
   e->dt.edge_mask = ht.edge_tbl.empty() ? 0 : (uint32_t)ht.edge_tbl.size() - 1;
   e->dt.unk_id = ht.unk_id;
@@ -220,7 +227,19 @@ struct ctl_block {  // lives in ws.ctl
   uint32_t ticket;
   uint32_t err;
   unsigned long long total;
+  LongCtl lc;
 };
+
+static int ensure_long_pool(Workspace& ws, unsigned long long bytes) {
+  if (bytes <= ws.pool_cap) return B2T_OK;
+  unsigned long long cap = bytes + bytes / 4 + 4096;
+  int rc;
+  if ((rc = ws.lp_id.ensure(cap * 4)) || (rc = ws.lp_val.ensure(cap * 8)) || (rc = ws.lp_len.ensure(cap * 4)) || (rc = ws.lp_plen.ensure(cap * 4)) ||
+      (rc = ws.lp_aux.ensure(cap * 4)) || (rc = ws.lp_out.ensure(cap * 16)))
+    return rc;
+  ws.pool_cap = cap;
+  return B2T_OK;
+}
 
 template <int KIND>
 static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Workspace& ws, cudaStream_t st) {
@@ -254,6 +273,12 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
       (rc = ws.ctl.ensure(sizeof(ctl_block))) || (rc = ws.h_ctl.ensure(sizeof(ctl_block), false)))
     return rc;
   if (e->pretok == PT_WHITESPACE && (rc = ws.drop_bits.ensure(n_words * 4))) return rc;
+  const bool bpe = e->model == B2T_MODEL_BPE;
+  if (model_pass && bpe) {
+    if ((rc = ws.page_long.ensure(n_pages * 4)) || (rc = ws.long_desc.ensure((size_t)(n / (LONG_PRETOK_MIN + 1) + 2) * sizeof(LongDesc))) ||
+        (rc = ensure_long_pool(ws, 1u << 20)))
+      return rc;
+  }
   if (model_pass) {
     if ((rc = ws.ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.row_ptr.ensure(((size_t)n_docs + 1) * 8))) return rc;
     if ((flags & B2T_WANT_OFFSETS) && (rc = ws.offsets.ensure((size_t)(n + 1) * 8))) return rc;
@@ -275,6 +300,17 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   rec(e, st, "pretok_scan"); e->last_launches++;
   page_scan_kernel<<<1, 1024, 0, st>>>(ws.page_sum.as<uint64_t>(), ws.page_carry.as<uint64_t>(), n_pages);
   rec(e, st, "page_scan"); e->last_launches++;
+  if (model_pass && bpe) {
+    ctl_block* ctl = ws.ctl.as<ctl_block>();
+    LongPool pool;
+    pool.id = ws.lp_id.as<uint32_t>(); pool.val = ws.lp_val.as<uint64_t>(); pool.len = ws.lp_len.as<uint32_t>(); pool.plen = ws.lp_plen.as<uint32_t>();
+    pool.aux = ws.lp_aux.as<uint32_t>(); pool.out = ws.lp_out.as<uint4>(); pool.cap = ws.pool_cap;
+    long_find_kernel<<<(unsigned)((n_pages + 7) / 8), 256, 0, st>>>(ws.start_bits.as<uint32_t>(), n, n_pages, &ctl->lc, ws.long_desc.as<LongDesc>(),
+                                                                   ws.page_long.as<int32_t>(), ws.pool_cap);
+    rec(e, st, "long_find"); e->last_launches++;
+    bpe_long_kernel<<<(unsigned)(e->sm_count * 2), LONG_THREADS, 0, st>>>(d_bytes, &ctl->lc, ws.long_desc.as<LongDesc>(), pool, e->dt, e->monotone);
+    rec(e, st, "bpe_long"); e->last_launches++;
+  }
   if (model_pass) {
     ModelParams P;
     P.bytes = d_bytes; P.n = n;
@@ -289,6 +325,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     ctl_block* ctl = ws.ctl.as<ctl_block>();
     P.ticket = &ctl->ticket; P.err_flag = &ctl->err; P.total_out = &ctl->total;
     P.n_tiles = n_pages;
+    P.page_long = ws.page_long.as<int32_t>(); P.long_desc = ws.long_desc.as<LongDesc>(); P.long_out = ws.lp_out.as<uint4>();
     P.t = e->dt;
     if (e->model == B2T_MODEL_BPE) model_tile_kernel<MODEL_BPE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
     else model_tile_kernel<MODEL_WORDPIECE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
@@ -299,10 +336,11 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   return B2T_OK;
 }
 
-static int check_ctl(const Workspace& ws) {
+// 0 = ok, -1 = the long pool was too small (grow to *want and rerun), else an error status
+static int check_ctl(const Workspace& ws, unsigned long long* want) {
   const ctl_block* c = ws.h_ctl.as<ctl_block>();
-  if (c->err & ERR_LONG_PRETOKEN)
-    return fail(B2T_ERR_TOO_LARGE, "a BPE pre-token longer than %d bytes is not supported on the device path yet", TILE + 256);
+  if ((c->err | c->lc.err) & ERR_INTERNAL) return fail(B2T_ERR_CUDA, "internal error: long pre-token bookkeeping mismatch");
+  if (c->lc.err & ERR_POOL_OVERFLOW) { *want = c->lc.pool_used; return -1; }
   return B2T_OK;
 }
 
@@ -343,10 +381,16 @@ extern "C" int b2t_encode_batch_device(b2t_engine* e, const uint8_t* d_bytes, ui
   CU(cudaSetDevice(e->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->own_stream;
   Workspace& ws = e->dev_ws;
-  int rc = run_device_pipeline(e, ws, d_bytes, (int64_t)n_bytes, d_doc_off, n_docs, flags, st, true);
-  if (rc) return rc;
-  CU(cudaStreamSynchronize(st));
-  if ((rc = check_ctl(ws))) return rc;
+  int rc;
+  for (int attempt = 0;; ++attempt) {
+    if ((rc = run_device_pipeline(e, ws, d_bytes, (int64_t)n_bytes, d_doc_off, n_docs, flags, st, true))) return rc;
+    CU(cudaStreamSynchronize(st));
+    unsigned long long want = 0;
+    rc = check_ctl(ws, &want);
+    if (rc == B2T_OK) break;
+    if (rc != -1 || attempt >= 2) return rc == -1 ? fail(B2T_ERR_CUDA, "long pool did not converge") : rc;
+    if ((rc = ensure_long_pool(ws, want))) return rc;  // rare: the batch has more long pre-token bytes than the pool held
+  }
   b2t_result* r = new b2t_result();
   r->eng = e; r->on_device = 1; r->n_docs = n_docs;
   r->n_tokens = ws.h_ctl.as<ctl_block>()->total;
@@ -423,8 +467,17 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
     Workspace& ws = e->slot[ci % NSLOT];
     CU(cudaEventSynchronize(ws.done));
     if (pretok_only) return B2T_OK;
-    int rc2 = check_ctl(ws);
-    if (rc2) return rc2;
+    int rc2;
+    for (int attempt = 0;; ++attempt) {
+      unsigned long long want = 0;
+      rc2 = check_ctl(ws, &want);
+      if (rc2 == B2T_OK) break;
+      if (rc2 != -1 || attempt >= 2) return rc2 == -1 ? fail(B2T_ERR_CUDA, "long pool did not converge") : rc2;
+      // rerun this chunk with a larger pool (its input is still resident in the slot)
+      if ((rc2 = ensure_long_pool(ws, want))) return rc2;
+      if ((rc2 = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)(c.b1 - c.b0), ws.doc_off.as<uint64_t>(), c.d1 - c.d0, flags, ws.stream, true))) return rc2;
+      CU(cudaStreamSynchronize(ws.stream));
+    }
     const uint64_t nt = ws.h_ctl.as<ctl_block>()->total;
     c.tok_base = tok_base;
     if (tok_base + nt > cap_tok) {

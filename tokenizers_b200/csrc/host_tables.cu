@@ -102,6 +102,25 @@ std::string build_host_tables(int model, int pretok, int ignore_merges, uint32_t
         h = (h + 1) & (cap - 1);
       }
     }
+    // ---- monotonicity: rank of every merge > rank of every merge that creates one of its parts
+    {
+      std::unordered_map<uint32_t, uint32_t> created;  // token id -> highest rank of a merge producing it
+      bool mono = true;
+      uint32_t live = 0;
+      for (const uint4& e : out->merge_tbl) {
+        if (e.x == EMPTY_KEY) continue;
+        ++live;
+        auto it = created.find(e.w);
+        if (it == created.end() || it->second < e.z) created[e.w] = e.z;
+      }
+      if (live != n_merges) mono = false;  // duplicate pairs were overwritten: be conservative
+      for (const uint4& e : out->merge_tbl) {
+        if (e.x == EMPTY_KEY) continue;
+        auto ia = created.find(e.x), ib = created.find(e.y);
+        if ((ia != created.end() && ia->second >= e.z) || (ib != created.end() && ib->second >= e.z)) { mono = false; break; }
+      }
+      out->monotone = mono;
+    }
     // ---- whole-word table for ignore_merges (models/bpe/model.rs:558-567)
     if (ignore_merges) {
       uint32_t wcap = pow2_at_least((uint64_t)n_vocab * 5 / 2 + 16);

@@ -22,6 +22,7 @@ struct HostTables {
   std::vector<uint4> edge_tbl;
   uint32_t unk_id = EMPTY_KEY;
   uint32_t max_chars = 100;
+  bool monotone = false;
 };
 
 // Fills out[0x110000] with the class of every code point (scheme 0 = Oniguruma L/N/S, 1 = Rust regex \w,\s).

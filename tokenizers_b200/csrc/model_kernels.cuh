@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "b2t_tables.h"
+#include "long_kernels.cuh"
 #include "pretok_logic.cuh"
 
 namespace b2t {
@@ -28,7 +29,7 @@ constexpr int MODEL_THREADS = 256;
 constexpr int THREAD_PATH_MAX = 32;  // pre-tokens up to this many bytes are merged by a single thread
 enum { MODEL_BPE = 0, MODEL_WORDPIECE = 1 };
 enum { F_OFFSETS = 1u, F_WORD_IDS = 2u, F_BYTE_OFFSETS = 4u };
-enum { ERR_LONG_PRETOKEN = 1u };
+constexpr int MAX_LONG_PER_PAGE = TILE / (LONG_PRETOK_MIN + 1) + 1;  // 8
 
 struct ModelParams {
   const uint8_t* bytes; int64_t n;
@@ -39,6 +40,8 @@ struct ModelParams {
   uint32_t* ids; uint32_t* offsets; uint32_t* word_ids; uint64_t* row_ptr;
   unsigned long long* tile_state; uint32_t* ticket; unsigned long long* total_out; uint32_t* err_flag;
   int64_t n_tiles;
+  // long BPE pre-tokens resolved by the pre-pass (long_kernels.cuh)
+  const int32_t* page_long; const LongDesc* long_desc; const uint4* long_out;
   DeviceTables t;
 };
 
@@ -98,12 +101,16 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
   __shared__ unsigned long long s_excl;
   __shared__ long long s_long_end, s_span_doc_start;
   __shared__ int s_long_chars;
+  __shared__ int s_nl;                                   // long BPE pre-tokens that start in this page
+  __shared__ uint16_t s_lk[MAX_LONG_PER_PAGE + 1];       // their pre-token indices, in position order
+  __shared__ int s_lcum[MAX_LONG_PER_PAGE + 2];          // exclusive prefix of their token counts
+  __shared__ unsigned long long s_loff[MAX_LONG_PER_PAGE + 1];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARPS = MODEL_THREADS / 32;
   if (tid == 0) {
     s_tile = (int)atomicAdd(P.ticket, 1u);
-    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0;
+    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0;
   }
   __syncthreads();
   const int64_t t = s_tile;
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
         // no start inside the halo: the last pre-token is LONG.  Find its true end in the global bitmap.
         is_long = 1;
         int64_t gw = (base + SPAN) / 32;
-        long long e = -1;
+        long long e = (MODEL == MODEL_BPE) ? n : -1;  // BPE: the pre-pass already knows the end
         while (e < 0) {
           int64_t w = gw + lane;
           uint32_t b = (w < n_chunks) ? __ldg(P.start_bits + w) : 0u;
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
   __syncthreads();
   const int Pn = s_P;
   const int Elast = s_Elast;
-  const int is_long = s_long;
+  const int is_long = s_long && Pn > 0;  // without a start in the page the long pre-token belongs to an earlier page
   if (tid < TW) {
     uint32_t bits = s_startb[tid];
     int idx = s_apref[tid];
@@ -223,17 +230,51 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
   if (tid == 0) s_pt[Pn] = (uint16_t)Elast;
   __syncthreads();
   const int first = Pn ? (int)s_pt[0] : Elast;
-  // the region whose symbols this block resolves in shared memory (a LONG last pre-token is excluded)
-  const int Eproc = Pn ? (is_long ? (int)s_pt[Pn - 1] : Elast) : 0;
-  const int Pproc = is_long ? Pn - 1 : Pn;
+  // WordPiece: a split that does not fit the halo is [UNK] (handled below).  BPE: pre-tokens longer than LONG_PRETOK_MIN were
+  // resolved by the pre-pass; collect them (position order) and blank their bytes so the page logic skips them.
+  const int Eproc = Pn ? ((MODEL == MODEL_WORDPIECE && is_long) ? (int)s_pt[Pn - 1] : Elast) : 0;
+  const int Pproc = (MODEL == MODEL_WORDPIECE && is_long) ? Pn - 1 : Pn;
+  if (MODEL == MODEL_BPE) {
+    for (int k = tid; k < Pn; k += MODEL_THREADS)
+      if ((int)s_pt[k + 1] - (int)s_pt[k] > LONG_PRETOK_MIN) { int i = atomicAdd(&s_nl, 1); if (i < MAX_LONG_PER_PAGE) s_lk[i] = (uint16_t)k; }
+    __syncthreads();
+    if (tid == 0) {
+      int nl = s_nl;
+      if (nl > MAX_LONG_PER_PAGE) { nl = MAX_LONG_PER_PAGE; atomicOr(P.err_flag, ERR_INTERNAL); }
+      for (int a = 1; a < nl; ++a) { uint16_t v = s_lk[a]; int b = a - 1; while (b >= 0 && s_lk[b] > v) { s_lk[b + 1] = s_lk[b]; --b; } s_lk[b + 1] = v; }
+      const int32_t slot0 = nl ? __ldg(P.page_long + t) : 0;
+      if (nl && slot0 < 0) { atomicOr(P.err_flag, ERR_INTERNAL); nl = 0; }
+      int cum = 0;
+      for (int a = 0; a < nl; ++a) {
+        const LongDesc d = P.long_desc[slot0 + a];
+        if (d.start != base + s_pt[s_lk[a]]) atomicOr(P.err_flag, ERR_INTERNAL);
+        s_lcum[a] = cum; s_loff[a] = d.pool_off;
+        cum += (d.pool_off == ~0ull) ? 0 : (int)d.ntok;
+      }
+      s_lcum[nl] = cum;
+      s_nl = nl;
+    }
+    __syncthreads();
+    for (int a = 0; a < s_nl; ++a) {
+      const int ls = s_pt[s_lk[a]], le = min((int)s_pt[s_lk[a] + 1], SPAN);
+      for (int pos = ls + tid; pos < le; pos += MODEL_THREADS) s_len[pos] = 0;
+    }
+    __syncthreads();
+  }
+  const int n_longs = MODEL == MODEL_BPE ? s_nl : 0;
+  // number of long-path tokens that precede page position x
+  auto long_tokens_before = [&](int x) -> int {
+    int c = 0;
+    for (int a = 0; a < n_longs; ++a) if ((int)s_pt[s_lk[a]] < x) c = s_lcum[a + 1];
+    return c;
+  };
 
   if (MODEL == MODEL_BPE) {
-    if (is_long && tid == 0) atomicOr(P.err_flag, ERR_LONG_PRETOKEN);
     // -------------------------------------------------------------- P3: ranks of all adjacent byte pairs
     if (!P.t.ignore_merges) {
       for (int pos = tid; pos < SPAN; pos += MODEL_THREADS) {
         uint64_t v = NO_MERGE;
-        if (pos >= first && pos + 1 < Eproc && !((s_startb[(pos + 1) >> 5] >> ((pos + 1) & 31)) & 1u))
+        if (pos >= first && pos + 1 < Eproc && s_len[pos] && !((s_startb[(pos + 1) >> 5] >> ((pos + 1) & 31)) & 1u))
           v = merge_lookup(P.t, s_id[pos], s_id[pos + 1]);
         s_val[pos] = v;
       }
@@ -244,6 +285,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
       int k = atomicAdd(&s_next, 1);
       if (k >= Pproc) break;
       const int s = s_pt[k], e = s_pt[k + 1], len = e - s;
+      if (len > LONG_PRETOK_MIN) continue;  // resolved by the pre-pass
       if (P.t.ignore_merges) {
         // models/bpe/model.rs:558-567: the whole pre-token is a vocab entry -> one token
         StrHash h; strhash_init(h);
@@ -389,10 +431,10 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
     if (lane == 0) s_tokb[row] = tb;
   }
   __syncthreads();
-  const bool long_kept = is_long && ((s_keptb[s_pt[Pn - 1] >> 5] >> (s_pt[Pn - 1] & 31)) & 1u);
+  const bool long_kept = MODEL == MODEL_WORDPIECE && is_long && ((s_keptb[s_pt[Pn - 1] >> 5] >> (s_pt[Pn - 1] & 31)) & 1u);
   if (warp == 0) {
     int tot = warp_prefix_words(s_tokb, s_tpref, NW, lane);
-    const int A = tot + ((MODEL == MODEL_WORDPIECE && long_kept) ? 1 : 0);
+    const int A = tot + ((MODEL == MODEL_WORDPIECE && long_kept) ? 1 : 0) + (MODEL == MODEL_BPE ? s_lcum[n_longs] : 0);
     // ---------------------------------------------------------------- P6: decoupled look-back over the pages
     unsigned long long excl = 0;
     volatile unsigned long long* st = P.tile_state;
@@ -458,7 +500,8 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
       reinterpret_cast<uint2*>(P.offsets)[out] = make_uint2(o0, o1);
     }
     if (want_wid) {
-      const int wb = D >= 0 ? kept_incl(D) - 1 : -carry_starts;
+      // kept splits before the doc start (the split AT the doc start may itself be removed whitespace)
+      const int wb = D >= 0 ? kept_incl(D) - (int)((s_keptb[D >> 5] >> (D & 31)) & 1u) : -carry_starts;
       P.word_ids[out] = (uint32_t)(kept_incl(ts) - 1 - wb);
     }
   };
@@ -466,9 +509,42 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
     const uint32_t tb = s_tokb[row];
     if (!((tb >> lane) & 1u)) continue;
     const int pos = row * 32 + lane;
-    const unsigned long long out = excl + s_tpref[row] + __popc(tb & ((1u << lane) - 1u));
+    const unsigned long long out = excl + s_tpref[row] + __popc(tb & ((1u << lane) - 1u)) + long_tokens_before(pos);
     const int e = pos + s_len[pos];
     emit(out, s_id[pos], pos, base + e, lc_incl(e - 1), true);
+  }
+  if (MODEL == MODEL_BPE) {
+    // tokens of the long pre-tokens, produced by the pre-pass (relative to the pre-token start)
+    for (int a = 0; a < n_longs; ++a) {
+      const int ls = s_pt[s_lk[a]];
+      const int ntl = s_lcum[a + 1] - s_lcum[a];
+      if (ntl == 0) continue;
+      const uint4* __restrict__ lo = P.long_out + s_loff[a];
+      const int nb = ls == 0 ? 0 : (int)s_tpref[(ls - 1) >> 5] + __popc(s_tokb[(ls - 1) >> 5] & mask_le((ls - 1) & 31));
+      const unsigned long long obase = excl + (unsigned long long)(nb + s_lcum[a]);
+      const int D = doc_base(ls);
+      const int cb = D >= 0 ? lc_incl(D) - 1 : -carry_chars;
+      const int X = lc_incl(ls) - 1 - cb;  // char index of the pre-token's first char inside its document
+      const int wb = D >= 0 ? kept_incl(D) - (int)((s_keptb[D >> 5] >> (D & 31)) & 1u) : -carry_starts;
+      const uint32_t wid = (uint32_t)(kept_incl(ls) - 1 - wb);
+      const int64_t ds = D >= 0 ? base + D : s_span_doc_start;
+      for (int k = tid; k < ntl; k += MODEL_THREADS) {
+        const uint4 r = lo[k];
+        P.ids[obase + k] = r.x;
+        if (want_off) {
+          uint32_t o0, o1;
+          if (!byte_off) { o0 = (uint32_t)X + r.z; o1 = (uint32_t)X + r.w; }
+          else {
+            int64_t gs = base + ls + (k ? (int64_t)lo[k - 1].y : 0), ge = base + ls + (int64_t)r.y;
+            while (gs > 0 && (__ldg(P.bytes + gs) & 0xC0u) == 0x80u) --gs;
+            while (ge < n && (__ldg(P.bytes + ge) & 0xC0u) == 0x80u) ++ge;
+            o0 = (uint32_t)(gs - ds); o1 = (uint32_t)(ge - ds);
+          }
+          reinterpret_cast<uint2*>(P.offsets)[obase + k] = make_uint2(o0, o1);
+        }
+        if (want_wid) P.word_ids[obase + k] = wid;
+      }
+    }
   }
   if (MODEL == MODEL_WORDPIECE && long_kept && tid == 0) {
     const int ls = s_pt[Pn - 1];
@@ -486,7 +562,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
       if (pos >= TILE) break;
       // tokens that start before `pos` (a doc start is a pre-token start, so no token straddles it)
       const int before = pos == 0 ? 0 : (int)s_tpref[(pos - 1) >> 5] + __popc(s_tokb[(pos - 1) >> 5] & mask_le((int)((pos - 1) & 31)));
-      P.row_ptr[d] = excl + (unsigned long long)before;
+      P.row_ptr[d] = excl + (unsigned long long)(before + long_tokens_before((int)pos));
     }
   }
 }
