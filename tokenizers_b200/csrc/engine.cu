@@ -82,18 +82,19 @@ struct PinBuf {
 // Device-side state of one in-flight batch (or chunk).
 struct Workspace {
   DevBuf bytes, doc_off;              // only used by the host path (inputs staged on the device)
-  DevBuf doc_bits, start_bits, drop_bits, page_sum, page_carry, page_first_doc, tile_state, ctl;
+  DevBuf doc_bits, start_bits, drop_bits, page_sum, page_carry, block_sum, block_carry, page_first_doc, tile_state, ctl;
   DevBuf ids, offsets, word_ids, row_ptr;
   DevBuf page_long, long_desc, lp_id, lp_val, lp_len, lp_plen, lp_aux, lp_out;  // long BPE pre-tokens (long_kernels.cuh)
   unsigned long long pool_cap = 0;
+  DevBuf wcache;                      // per-batch word cache (model_kernels.cuh)
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   PinBuf h_ctl;                        // total tokens + error flag read back
   void release() {
     bytes.release(); doc_off.release(); doc_bits.release(); start_bits.release(); drop_bits.release(); page_sum.release();
-    page_carry.release(); page_first_doc.release(); tile_state.release(); ctl.release(); ids.release(); offsets.release();
+    page_carry.release(); block_sum.release(); block_carry.release(); page_first_doc.release(); tile_state.release(); ctl.release(); ids.release(); offsets.release();
     word_ids.release(); row_ptr.release(); h_ctl.release();
-    page_long.release(); long_desc.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
+    wcache.release(); page_long.release(); long_desc.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
     stream = nullptr; done = nullptr;
@@ -269,12 +270,15 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   const int64_t n_words = n / 32 + 2, n_pages = n / PAGE + 1;
   int rc;
   if ((rc = ws.doc_bits.ensure(n_words * 4)) || (rc = ws.start_bits.ensure(n_words * 4)) || (rc = ws.page_sum.ensure(n_pages * 8)) ||
-      (rc = ws.page_carry.ensure(n_pages * 8)) || (rc = ws.page_first_doc.ensure(n_pages * 4)) || (rc = ws.tile_state.ensure(n_pages * 8)) ||
+      (rc = ws.page_carry.ensure(n_pages * 8)) || (rc = ws.block_sum.ensure((n_pages / SCAN_BLOCK + 2) * 8)) ||
+      (rc = ws.block_carry.ensure((n_pages / SCAN_BLOCK + 2) * 8)) || (rc = ws.page_first_doc.ensure(n_pages * 4)) || (rc = ws.tile_state.ensure(n_pages * 8)) ||
       (rc = ws.ctl.ensure(sizeof(ctl_block))) || (rc = ws.h_ctl.ensure(sizeof(ctl_block), false)))
     return rc;
   if (e->pretok == PT_WHITESPACE && (rc = ws.drop_bits.ensure(n_words * 4))) return rc;
   const bool bpe = e->model == B2T_MODEL_BPE;
+  constexpr uint32_t WCACHE_SLOTS = 1u << 19;  // x 64 B = 32 MiB, L2 resident
   if (model_pass && bpe) {
+    if ((rc = ws.wcache.ensure((size_t)WCACHE_SLOTS * 64))) return rc;
     if ((rc = ws.page_long.ensure(n_pages * 4)) || (rc = ws.long_desc.ensure((size_t)(n / (LONG_PRETOK_MIN + 1) + 2) * sizeof(LongDesc))) ||
         (rc = ensure_long_pool(ws, 1u << 20)))
       return rc;
@@ -287,6 +291,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   CU(cudaMemsetAsync(ws.doc_bits.p, 0, n_words * 4, st));
   CU(cudaMemsetAsync(ws.tile_state.p, 0, n_pages * 8, st));
   CU(cudaMemsetAsync(ws.ctl.p, 0, sizeof(ctl_block), st));
+  if (model_pass && bpe) CU(cudaMemsetAsync(ws.wcache.p, 0, (size_t)WCACHE_SLOTS * 64, st));
   e->last_launches = 0;
   rec(e, st, nullptr);
   doc_mark_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.doc_bits.as<uint32_t>(), ws.page_first_doc.as<uint32_t>());
@@ -298,8 +303,11 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     default: launch_pretok<PT_NOREGEX>(e, d_bytes, n, ws, st); break;
   }
   rec(e, st, "pretok_scan"); e->last_launches++;
-  page_scan_kernel<<<1, 1024, 0, st>>>(ws.page_sum.as<uint64_t>(), ws.page_carry.as<uint64_t>(), n_pages);
-  rec(e, st, "page_scan"); e->last_launches++;
+  const int64_t n_scan_blocks = (n_pages + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  page_scan_block_kernel<<<(unsigned)n_scan_blocks, SCAN_BLOCK, 0, st>>>(ws.page_sum.as<uint64_t>(), ws.page_carry.as<uint64_t>(),
+                                                                      ws.block_sum.as<uint64_t>(), n_pages);
+  page_scan_top_kernel<<<1, SCAN_BLOCK, 0, st>>>(ws.block_sum.as<uint64_t>(), ws.block_carry.as<uint64_t>(), n_scan_blocks);
+  rec(e, st, "page_scan"); e->last_launches += 2;
   if (model_pass && bpe) {
     ctl_block* ctl = ws.ctl.as<ctl_block>();
     LongPool pool;
@@ -315,7 +323,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     ModelParams P;
     P.bytes = d_bytes; P.n = n;
     P.start_bits = ws.start_bits.as<uint32_t>(); P.drop_bits = ws.drop_bits.as<uint32_t>(); P.doc_bits = ws.doc_bits.as<uint32_t>();
-    P.page_carry = ws.page_carry.as<uint64_t>(); P.page_first_doc = ws.page_first_doc.as<uint32_t>();
+    P.page_carry = ws.page_carry.as<uint64_t>(); P.block_carry = ws.block_carry.as<uint64_t>(); P.page_first_doc = ws.page_first_doc.as<uint32_t>();
     P.doc_off = d_doc_off; P.n_docs = n_docs;
     P.flags = ((flags & B2T_WANT_OFFSETS) ? F_OFFSETS : 0u) | ((flags & B2T_WANT_WORD_IDS) ? F_WORD_IDS : 0u) |
               ((flags & B2T_OFFSETS_BYTES) ? F_BYTE_OFFSETS : 0u);
@@ -326,6 +334,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     P.ticket = &ctl->ticket; P.err_flag = &ctl->err; P.total_out = &ctl->total;
     P.n_tiles = n_pages;
     P.page_long = ws.page_long.as<int32_t>(); P.long_desc = ws.long_desc.as<LongDesc>(); P.long_out = ws.lp_out.as<uint4>();
+    P.wcache = ws.wcache.as<uint4>(); P.wcache_mask = WCACHE_SLOTS - 1;
     P.t = e->dt;
     if (e->model == B2T_MODEL_BPE) model_tile_kernel<MODEL_BPE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
     else model_tile_kernel<MODEL_WORDPIECE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);

@@ -26,7 +26,7 @@ namespace b2t {
 
 constexpr int TILE = PAGE;
 constexpr int MODEL_THREADS = 256;
-constexpr int THREAD_PATH_MAX = 32;  // pre-tokens up to this many bytes are merged by a single thread
+constexpr int THREAD_PATH_MAX = 32;  // pre-tokens up to this many bytes are merged by an 8-lane group, longer ones by a warp
 enum { MODEL_BPE = 0, MODEL_WORDPIECE = 1 };
 enum { F_OFFSETS = 1u, F_WORD_IDS = 2u, F_BYTE_OFFSETS = 4u };
 constexpr int MAX_LONG_PER_PAGE = TILE / (LONG_PRETOK_MIN + 1) + 1;  // 8
@@ -34,7 +34,7 @@ constexpr int MAX_LONG_PER_PAGE = TILE / (LONG_PRETOK_MIN + 1) + 1;  // 8
 struct ModelParams {
   const uint8_t* bytes; int64_t n;
   const uint32_t* start_bits; const uint32_t* drop_bits; const uint32_t* doc_bits;
-  const uint64_t* page_carry; const uint32_t* page_first_doc;
+  const uint64_t* page_carry; const uint64_t* block_carry; const uint32_t* page_first_doc;
   const uint64_t* doc_off; uint32_t n_docs;
   uint32_t flags;
   uint32_t* ids; uint32_t* offsets; uint32_t* word_ids; uint64_t* row_ptr;
@@ -42,6 +42,8 @@ struct ModelParams {
   int64_t n_tiles;
   // long BPE pre-tokens resolved by the pre-pass (long_kernels.cuh)
   const int32_t* page_long; const LongDesc* long_desc; const uint4* long_out;
+  // per-batch word cache (cleared at the start of every batch): pre-token bytes -> its token list
+  uint4* wcache; uint32_t wcache_mask;
   DeviceTables t;
 };
 
@@ -77,6 +79,202 @@ __device__ __forceinline__ int warp_prefix_words(const uint32_t* bits, uint16_t*
 
 __device__ __forceinline__ uint32_t mask_le(int b) { return b >= 31 ? 0xFFFFFFFFu : ((2u << b) - 1u); }
 
+
+// ------------------------------------------------------------------------------------------------ word cache
+// The reference keeps a per-thread word cache in front of merge_word (models/bpe/model.rs:24-90, 568-586) because
+// natural text repeats its words; it has no semantic effect.  Same idea here, per batch and shared by all blocks: a
+// pre-token of up to 24 bytes whose result has up to 6 tokens is published once and reused by every later occurrence
+// in the batch (full key comparison, so a hit is exact).  Slot = 64 bytes:
+//   q0 = {tag lo, tag hi, key[0], key[1]}   q1 = {key[2..5]}   q2 = {ntok | len0..2, len3..5 | -, id0, id1}   q3 = {id2..id5}
+// tag: 0 = free, BUSY | fp = being written, READY | fp = valid.  Writers publish with payload -> fence -> tag.
+constexpr int WC_MAX_BYTES = 24, WC_MAX_TOK = 6, WC_PROBES = 4;
+#define B2T_WC_READY (1ull << 63)
+#define B2T_WC_BUSY (1ull << 62)
+#define B2T_WC_FP ((1ull << 62) - 1ull)
+
+struct WordKey {
+  uint32_t k[6];
+  uint32_t slot;
+  unsigned long long fp;
+};
+
+// 24 zero-padded bytes of the pre-token [s, s + len) from shared memory + their hash
+__device__ __forceinline__ void wc_make_key(const uint8_t* s_byte, int s, int len, WordKey& key) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(s_byte) + (s >> 2);
+  const uint32_t sh = (uint32_t)(s & 3) * 8u;
+  uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4], a5 = w[5], a6 = w[6];
+  uint32_t k[6] = {__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh),
+                   __funnelshift_r(a3, a4, sh), __funnelshift_r(a4, a5, sh), __funnelshift_r(a5, a6, sh)};
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int valid = len - 4 * i;  // bytes of word i that belong to the pre-token
+    const uint32_t m = valid >= 4 ? 0xFFFFFFFFu : (valid <= 0 ? 0u : ((1u << (8 * valid)) - 1u));
+    key.k[i] = k[i] & m;
+  }
+  uint32_t a = key.k[0] ^ (key.k[2] * 0x9E3779B1u) ^ (key.k[4] * 0x85EBCA77u);
+  uint32_t b = key.k[1] ^ (key.k[3] * 0xC2B2AE3Du) ^ (key.k[5] * 0x27D4EB2Fu);
+  a = (a ^ (uint32_t)len) * 0x2C1B3C6Du; b = (b + a) * 0x297A2D39u;
+  a ^= b >> 15; a *= 0x85EBCA6Bu; b ^= a >> 13; b *= 0xC2B2AE35u; a ^= b >> 16;
+  key.slot = a;
+  key.fp = ((((unsigned long long)b << 32) | a) ^ ((unsigned long long)len << 56)) & B2T_WC_FP;
+  if (key.fp == 0) key.fp = 1;
+}
+
+// Returns true on a hit (tokens written to s_id / s_len).
+__device__ __forceinline__ bool wc_lookup(uint4* cache, uint32_t mask, const WordKey& key, int s, uint32_t* s_id, uint16_t* s_len) {
+  uint32_t slot = key.slot & mask;
+#pragma unroll 1
+  for (int pr = 0; pr < WC_PROBES; ++pr, slot = (slot + 1) & mask) {
+    const uint4* q = cache + (size_t)slot * 4;
+    const uint4 q0 = __ldcg(q);
+    const unsigned long long tag = ((unsigned long long)q0.y << 32) | q0.x;
+    if (tag == 0ull) return false;
+    if (tag != (B2T_WC_READY | key.fp)) {
+      if (tag == (B2T_WC_BUSY | key.fp)) return false;  // someone is publishing this very word: just compute it
+      continue;
+    }
+    if (q0.z != key.k[0] || q0.w != key.k[1]) continue;
+    const uint4 q1 = __ldcg(q + 1);
+    if (q1.x != key.k[2] || q1.y != key.k[3] || q1.z != key.k[4] || q1.w != key.k[5]) continue;
+    const uint4 q2 = __ldcg(q + 2), q3 = __ldcg(q + 3);
+    const int ntok = (int)(q2.x & 0xFFu);
+    const uint32_t ids[6] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+    const uint32_t lens[6] = {(q2.x >> 8) & 0xFFu, (q2.x >> 16) & 0xFFu, q2.x >> 24, q2.y & 0xFFu, (q2.y >> 8) & 0xFFu, (q2.y >> 16) & 0xFFu};
+    int pos = s;
+#pragma unroll
+    for (int t = 0; t < WC_MAX_TOK; ++t)
+      if (t < ntok) { s_id[pos] = ids[t]; s_len[pos] = (uint16_t)lens[t]; pos += (int)lens[t]; }
+    return true;
+  }
+  return false;
+}
+
+// Publish the merged pre-token [s, e) (symbols chained by s_len) into the first free slot of its probe sequence.
+__device__ __forceinline__ void wc_publish(uint4* cache, uint32_t mask, const WordKey& key, int s, int e, const uint32_t* s_id,
+                                           const uint16_t* s_len) {
+  uint32_t ids[6] = {0, 0, 0, 0, 0, 0}, lens[6] = {0, 0, 0, 0, 0, 0};
+  int nt = 0, p = s;
+  while (p < e) {
+    if (nt == WC_MAX_TOK) return;  // too many tokens for a slot
+    const int l = s_len[p];
+#pragma unroll
+    for (int t = 0; t < WC_MAX_TOK; ++t) if (t == nt) { ids[t] = s_id[p]; lens[t] = (uint32_t)l; }
+    ++nt; p += l;
+  }
+  uint32_t slot = key.slot & mask;
+#pragma unroll 1
+  for (int pr = 0; pr < WC_PROBES; ++pr, slot = (slot + 1) & mask) {
+    uint4* q = cache + (size_t)slot * 4;
+    unsigned long long* tagp = reinterpret_cast<unsigned long long*>(q);
+    unsigned long long tag = *reinterpret_cast<volatile unsigned long long*>(tagp);
+    if (tag == 0ull) tag = atomicCAS(tagp, 0ull, B2T_WC_BUSY | key.fp);
+    if (tag == 0ull) {  // the slot is ours
+      reinterpret_cast<uint2*>(q)[1] = make_uint2(key.k[0], key.k[1]);
+      q[1] = make_uint4(key.k[2], key.k[3], key.k[4], key.k[5]);
+      q[2] = make_uint4((uint32_t)nt | (lens[0] << 8) | (lens[1] << 16) | (lens[2] << 24), lens[3] | (lens[4] << 8) | (lens[5] << 16), ids[0], ids[1]);
+      q[3] = make_uint4(ids[2], ids[3], ids[4], ids[5]);
+      __threadfence();
+      atomicExch(tagp, B2T_WC_READY | key.fp);
+      return;
+    }
+    if ((tag & B2T_WC_FP) == key.fp) return;  // (probably) the same word, already there or on its way
+  }
+}
+
+// models/bpe/model.rs:558-567 (ignore_merges): is the whole pre-token a vocabulary entry?  Writes its id to s_id[s].
+__device__ __forceinline__ bool vocab_whole_word(const DeviceTables& t, const uint8_t* s_byte, int s, int len, uint32_t* s_id) {
+  StrHash h; strhash_init(h);
+  for (int p = s; p < s + len; ++p) strhash_byte(h, s_byte[p]);
+  strhash_fin(h);
+  uint32_t slot = h.h1 & t.word_mask;
+  while (true) {
+    const uint4 en = __ldg(t.word_tbl + slot);
+    if (en.z == EMPTY_KEY) return false;
+    if (en.x == h.h2 && en.y == (uint32_t)len) {
+      const uint8_t* q = t.word_pool + en.w;
+      bool same = true;
+      for (int i = 0; i < len; ++i) if (__ldg(q + i) != s_byte[s + i]) { same = false; break; }
+      if (same) { s_id[s] = en.z; return true; }
+    }
+    slot = (slot + 1) & t.word_mask;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cooperative merge
+// G lanes resolve one pre-token [s, e) of up to G * J bytes: lane g owns the positions s + g + G * j (j < J) and
+// keeps the rank / new id of the pair that starts at each of them in registers.  Every round the group agrees on
+// the leftmost pair of minimal rank (== the reference's heap order (rank, pos), models/bpe/word.rs:28-35), its owner
+// merges, and the (at most two) pairs that changed are looked up again.  All groups of a warp step together; the
+// control flow is warp-uniform, so nothing diverges -- idle groups are predicated off.
+template <int G, int J>
+__device__ __forceinline__ void coop_bpe(const DeviceTables& t, const uint8_t* s_byte, uint32_t* s_id, uint16_t* s_len, int s, int e,
+                                         bool active, int gl) {
+  uint32_t rk[J], ni[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = s + gl + G * j;
+    rk[j] = 0xFFFFFFFFu; ni[j] = 0u;
+    if (active && p < e) { s_id[p] = __ldg(t.byte_to_id + s_byte[p]); s_len[p] = 1; }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = s + gl + G * j;
+    if (active && p + 1 < e) { const uint64_t v = merge_lookup(t, s_id[p], s_id[p + 1]); rk[j] = (uint32_t)(v >> 32); ni[j] = (uint32_t)v; }
+  }
+  while (true) {
+    // leftmost minimum over my positions (they grow with j), then over the group
+    uint32_t br = 0xFFFFFFFFu, bpos = 0x7FFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < J; ++j) if (rk[j] < br) { br = rk[j]; bpos = (uint32_t)(s + gl + G * j); }
+#pragma unroll
+    for (int st = G / 2; st >= 1; st >>= 1) {
+      const uint32_t orr = __shfl_xor_sync(0xFFFFFFFFu, br, st), op = __shfl_xor_sync(0xFFFFFFFFu, bpos, st);
+      if (orr < br || (orr == br && op < bpos)) { br = orr; bpos = op; }
+    }
+    const bool have = active && br != 0xFFFFFFFFu;
+    if (!__any_sync(0xFFFFFFFFu, have)) break;
+    const int bp = (int)bpos;
+    int nx = 0, pv = -1;
+    uint32_t nid = 0;
+    if (have) {
+      // everybody in the group derives the same facts from shared memory (read before the owner writes)
+      const int ql = s_len[bp];
+      const int q = bp + ql;
+      nx = q + s_len[q];
+      pv = bp - 1;
+      while (pv >= s && s_len[pv] == 0) --pv;
+    }
+    __syncwarp();
+    if (have) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int p = s + gl + G * j;
+        if (p == bp) {  // owner of the winning pair: merge right into left
+          nid = ni[j];
+          const int q = bp + s_len[bp];
+          s_id[bp] = nid; s_len[bp] = (uint16_t)(nx - bp); s_len[q] = 0;
+        }
+        if (p > bp && p < nx) rk[j] = 0xFFFFFFFFu;  // the swallowed symbol no longer starts a pair
+      }
+    }
+    __syncwarp();
+    if (have) {
+      const uint32_t newid = s_id[bp];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int p = s + gl + G * j;
+        if (p == bp) {
+          rk[j] = 0xFFFFFFFFu;
+          if (nx < e) { const uint64_t v = merge_lookup(t, newid, s_id[nx]); rk[j] = (uint32_t)(v >> 32); ni[j] = (uint32_t)v; }
+        } else if (p == pv) {
+          const uint64_t v = merge_lookup(t, s_id[pv], newid); rk[j] = (uint32_t)(v >> 32); ni[j] = (uint32_t)v;
+        }
+      }
+    }
+  }
+}
+
 #define B2T_ST_AGG (1ull << 62)
 #define B2T_ST_INCL (2ull << 62)
 #define B2T_ST_VAL ((1ull << 62) - 1ull)
@@ -91,13 +289,16 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
   __shared__ __align__(16) uint8_t s_byte[SPAN];
   __shared__ uint16_t s_len[SPAN];
   __shared__ uint32_t s_id[SPAN];
-  __shared__ uint64_t s_val[MODEL == MODEL_BPE ? SPAN : 1];
   __shared__ uint32_t s_startb[NW + 1], s_keptb[NW + 1], s_leadb[NW + 1], s_tokb[NW + 1], s_dsb[TW + 1];
   __shared__ uint16_t s_apref[NW + 1], s_spref[NW + 1], s_lpref[NW + 1], s_tpref[NW + 1];
   __shared__ int16_t s_dlast[TW + 1];
   __shared__ uint16_t s_pt[TILE + 2];
   __shared__ uint16_t s_mq[TILE / THREAD_PATH_MAX + 2];
-  __shared__ int s_tile, s_next, s_nmq, s_P, s_Elast, s_long, s_ntok;
+  __shared__ uint16_t s_list[SPAN];  // P3/P4: pre-tokens the word cache did not resolve; P7: positions of the tokens
+  uint16_t* const s_miss = s_list;
+  uint16_t* const s_tokpos = s_list;
+  __shared__ int s_nmiss;
+  __shared__ int s_tile, s_next, s_nmq, s_P, s_Elast, s_long, s_ntok, s_ntot;
   __shared__ unsigned long long s_excl;
   __shared__ long long s_long_end, s_span_doc_start;
   __shared__ int s_long_chars;
@@ -110,7 +311,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
   constexpr int NWARPS = MODEL_THREADS / 32;
   if (tid == 0) {
     s_tile = (int)atomicAdd(P.ticket, 1u);
-    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0;
+    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0;
   }
   __syncthreads();
   const int64_t t = s_tile;
@@ -147,8 +348,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
     bool lead = ((b & 0xC0u) != 0x80u) && (base + pos < n);
     uint32_t lb = __ballot_sync(0xFFFFFFFFu, lead);
     if (lane == 0) s_leadb[row] = lb;
-    if (MODEL == MODEL_BPE) { s_id[pos] = __ldg(P.t.byte_to_id + b); s_len[pos] = 1; }
-    else s_len[pos] = 0;
+    s_len[pos] = 0;  // token starts are written by whoever resolves the pre-token
   }
   if (tid == 0) s_leadb[NW] = 0u;
   __syncthreads();
@@ -270,105 +470,72 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
   };
 
   if (MODEL == MODEL_BPE) {
-    // -------------------------------------------------------------- P3: ranks of all adjacent byte pairs
-    if (!P.t.ignore_merges) {
-      for (int pos = tid; pos < SPAN; pos += MODEL_THREADS) {
-        uint64_t v = NO_MERGE;
-        if (pos >= first && pos + 1 < Eproc && s_len[pos] && !((s_startb[(pos + 1) >> 5] >> ((pos + 1) & 31)) & 1u))
-          v = merge_lookup(P.t, s_id[pos], s_id[pos + 1]);
-        s_val[pos] = v;
+    // -------------------------------------------------------------- P3: word cache, one pre-token per thread
+    // (static assignment: a lookup costs the same for every lane, so the warp stays converged)
+    for (int k0 = 0; k0 < Pproc; k0 += MODEL_THREADS) {
+      const int k = k0 + tid;
+      int kind = 0;  // 0 = resolved / nothing to do, 1 = miss (<= 32 bytes), 2 = medium (33..256 bytes)
+      if (k < Pproc) {
+        const int s = s_pt[k], e = s_pt[k + 1], len = e - s;
+        if (len > LONG_PRETOK_MIN) kind = 0;  // resolved by the pre-pass
+        else if (len > THREAD_PATH_MAX) kind = 2;
+        else {
+          bool hit = false;
+          if (len <= WC_MAX_BYTES) {
+            WordKey key;
+            wc_make_key(s_byte, s, len, key);
+            hit = wc_lookup(P.wcache, P.wcache_mask, key, s, s_id, s_len);
+          }
+          kind = hit ? 0 : 1;
+        }
       }
+      // warp-aggregated queue appends
+      const unsigned mm = __ballot_sync(0xFFFFFFFFu, kind == 1), mq = __ballot_sync(0xFFFFFFFFu, kind == 2);
+      int bm = 0, bq = 0;
+      if (lane == 0) { if (mm) bm = atomicAdd(&s_nmiss, __popc(mm)); if (mq) bq = atomicAdd(&s_nmq, __popc(mq)); }
+      bm = __shfl_sync(0xFFFFFFFFu, bm, 0); bq = __shfl_sync(0xFFFFFFFFu, bq, 0);
+      if (kind == 1) s_miss[bm + __popc(mm & ((1u << lane) - 1u))] = (uint16_t)k;
+      if (kind == 2) s_mq[bq + __popc(mq & ((1u << lane) - 1u))] = (uint16_t)k;
     }
     __syncthreads();
-    // -------------------------------------------------------------- P4a: one thread per short pre-token
-    while (true) {
-      int k = atomicAdd(&s_next, 1);
-      if (k >= Pproc) break;
-      const int s = s_pt[k], e = s_pt[k + 1], len = e - s;
-      if (len > LONG_PRETOK_MIN) continue;  // resolved by the pre-pass
-      if (P.t.ignore_merges) {
-        // models/bpe/model.rs:558-567: the whole pre-token is a vocab entry -> one token
-        StrHash h; strhash_init(h);
-        for (int p = s; p < e; ++p) strhash_byte(h, s_byte[p]);
-        strhash_fin(h);
-        uint32_t slot = h.h1 & P.t.word_mask;
-        bool hit = false;
-        while (true) {
-          uint4 en = __ldg(P.t.word_tbl + slot);
-          if (en.z == EMPTY_KEY) break;
-          if (en.x == h.h2 && en.y == (uint32_t)len) {
-            const uint8_t* q = P.t.word_pool + en.w;
-            bool same = true;
-            for (int i = 0; i < len; ++i) if (__ldg(q + i) != s_byte[s + i]) { same = false; break; }
-            if (same) { s_id[s] = en.z; hit = true; break; }
-          }
-          slot = (slot + 1) & P.t.word_mask;
+    // -------------------------------------------------------------- P4a: misses, 8 lanes per pre-token (<= 32 bytes)
+    {
+      const int nmiss = s_nmiss;
+      const int grp = tid >> 3, gl = tid & 7;           // 32 groups per block
+      for (int m0 = 0; m0 < nmiss; m0 += MODEL_THREADS / 8) {
+        const int mi = m0 + grp;
+        const bool active0 = mi < nmiss;
+        const int k = active0 ? s_miss[mi] : 0;
+        const int s = active0 ? s_pt[k] : 0, e = active0 ? s_pt[k + 1] : 0;
+        bool active = active0;
+        if (P.t.ignore_merges) {  // models/bpe/model.rs:558-567: the whole pre-token is a vocabulary entry -> one token
+          int whole = 0;
+          if (active0 && gl == 0) { whole = vocab_whole_word(P.t, s_byte, s, e - s, s_id) ? 1 : 0; if (whole) s_len[s] = (uint16_t)(e - s); }
+          whole = __shfl_sync(0xFFFFFFFFu, whole, lane & ~7);
+          active = active0 && !whole;
         }
-        if (hit) {
-          s_len[s] = (uint16_t)len;
-          for (int p = s + 1; p < e; ++p) s_len[p] = 0;
-          continue;
+        coop_bpe<8, 4>(P.t, s_byte, s_id, s_len, s, e, active, gl);
+        __syncwarp();
+        if (active0 && gl == 0 && e - s <= WC_MAX_BYTES) {
+          WordKey key;
+          wc_make_key(s_byte, s, e - s, key);
+          wc_publish(P.wcache, P.wcache_mask, key, s, e, s_id, s_len);
         }
-        if (len <= THREAD_PATH_MAX) {
-          for (int p = s; p + 1 < e; ++p) s_val[p] = merge_lookup(P.t, s_id[p], s_id[p + 1]);
-          s_val[e - 1] = NO_MERGE;
-        }
-      }
-      if (len == 1) continue;
-      if (len > THREAD_PATH_MAX) { s_mq[atomicAdd(&s_nmq, 1)] = (uint16_t)k; continue; }
-      while (true) {
-        uint64_t best = NO_MERGE;
-        int bp = -1, bprev = -1, prev = -1, p = s;
-        while (p < e) {
-          uint64_t v = s_val[p];
-          if (v < best) { best = v; bp = p; bprev = prev; }
-          prev = p; p += s_len[p];
-        }
-        if (bp < 0) break;
-        const int q = bp + s_len[bp];
-        const uint32_t nid = (uint32_t)best;
-        const int nl = s_len[bp] + s_len[q];
-        s_id[bp] = nid; s_len[bp] = (uint16_t)nl; s_len[q] = 0;
-        const int nx = bp + nl;
-        s_val[bp] = nx < e ? merge_lookup(P.t, nid, s_id[nx]) : NO_MERGE;
-        if (bprev >= 0) s_val[bprev] = merge_lookup(P.t, s_id[bprev], nid);
       }
     }
-    __syncthreads();
-    // -------------------------------------------------------------- P4b: one warp per longer pre-token
-    const int nmq = s_nmq;
-    for (int qi = warp; qi < nmq; qi += NWARPS) {
-      const int k = s_mq[qi], s = s_pt[k], e = s_pt[k + 1];
-      if (P.t.ignore_merges) {
-        for (int p = s + lane; p < e; p += 32) s_val[p] = (p + 1 < e) ? merge_lookup(P.t, s_id[p], s_id[p + 1]) : NO_MERGE;
-        __syncwarp();
-      }
-      while (true) {
-        uint32_t brank = 0xFFFFFFFFu;
-        int bpos = 0x7FFFFFFF;
-        for (int p = s + lane; p < e; p += 32) {
-          if (s_len[p]) {
-            uint32_t r = (uint32_t)(s_val[p] >> 32);
-            if (r < brank) { brank = r; bpos = p; }  // positions grow, so the first hit is the leftmost of this lane
-          }
+    // -------------------------------------------------------------- P4b: one warp per longer pre-token (33..256 bytes)
+    {
+      const int nmq = s_nmq;
+      for (int qi = warp; qi < nmq; qi += NWARPS) {
+        const int k = s_mq[qi], s = s_pt[k], e = s_pt[k + 1];
+        bool active = true;
+        if (P.t.ignore_merges) {
+          int whole = 0;
+          if (lane == 0) { whole = vocab_whole_word(P.t, s_byte, s, e - s, s_id) ? 1 : 0; if (whole) s_len[s] = (uint16_t)(e - s); }
+          whole = __shfl_sync(0xFFFFFFFFu, whole, 0);
+          active = !whole;
         }
-        uint32_t mr = __reduce_min_sync(0xFFFFFFFFu, brank);
-        if (mr == 0xFFFFFFFFu) break;
-        int bp = (int)__reduce_min_sync(0xFFFFFFFFu, brank == mr ? (uint32_t)bpos : 0x7FFFFFFFu);
-        if (lane == 0) {
-          const int q = bp + s_len[bp];
-          const uint32_t nid = (uint32_t)s_val[bp];
-          const int nl = s_len[bp] + s_len[q];
-          s_id[bp] = nid; s_len[bp] = (uint16_t)nl; s_len[q] = 0;
-          const int nx = bp + nl;
-          s_val[bp] = nx < e ? merge_lookup(P.t, nid, s_id[nx]) : NO_MERGE;
-          if (bp > s) {
-            int pv = bp - 1;
-            while (s_len[pv] == 0) --pv;
-            s_val[pv] = merge_lookup(P.t, s_id[pv], nid);
-          }
-        }
-        __syncwarp();
+        coop_bpe<32, LONG_PRETOK_MIN / 32>(P.t, s_byte, s_id, s_len, s, e, active, lane);
       }
     }
   } else {
@@ -434,6 +601,17 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
   const bool long_kept = MODEL == MODEL_WORDPIECE && is_long && ((s_keptb[s_pt[Pn - 1] >> 5] >> (s_pt[Pn - 1] & 31)) & 1u);
   if (warp == 0) {
     int tot = warp_prefix_words(s_tokb, s_tpref, NW, lane);
+    if (lane == 0) s_ntok = tot;
+  }
+  __syncthreads();
+  if (warp != 0) {
+    // compact list of token positions (while warp 0 walks the look-back chain)
+    for (int row = warp - 1; row < NW; row += NWARPS - 1) {
+      const uint32_t tb = s_tokb[row];
+      if ((tb >> lane) & 1u) s_tokpos[s_tpref[row] + __popc(tb & ((1u << lane) - 1u))] = (uint16_t)(row * 32 + lane);
+    }
+  } else {
+    const int tot = s_ntok;
     const int A = tot + ((MODEL == MODEL_WORDPIECE && long_kept) ? 1 : 0) + (MODEL == MODEL_BPE ? s_lcum[n_longs] : 0);
     // ---------------------------------------------------------------- P6: decoupled look-back over the pages
     unsigned long long excl = 0;
@@ -450,7 +628,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
         unsigned pend = __ballot_sync(0xFFFFFFFFu, fl == 0u);
         unsigned incl = __ballot_sync(0xFFFFFFFFu, fl == 2u);
         unsigned need = incl ? ((1u << (__ffs((int)incl) - 1)) - 1u) | (1u << (__ffs((int)incl) - 1)) : 0xFFFFFFFFu;
-        if (pend & need) continue;  // a needed predecessor has not published yet
+        if (pend & need) { __nanosleep(40); continue; }  // a needed predecessor has not published yet
         unsigned long long c = ((1u << lane) & need) ? (v & B2T_ST_VAL) : 0ull;
 #pragma unroll
         for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, s);
@@ -461,14 +639,19 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
       if (lane == 0) st[t] = B2T_ST_INCL | (excl + (unsigned long long)A);
     }
     if (lane == 0) {
-      s_excl = excl; s_ntok = A;
+      s_excl = excl; s_ntot = A;
       if (t == P.n_tiles - 1) *P.total_out = excl + (unsigned long long)A;
     }
   }
   __syncthreads();
   const unsigned long long excl = s_excl;
+  // chars / kept splits of the document that spans into this page, counted from its start (pretok_kernels.cuh K1b)
   const uint64_t carry = __ldg(P.page_carry + t);
-  const int carry_chars = (int)(uint32_t)carry, carry_starts = (int)(uint32_t)(carry >> 32);
+  int carry_chars = (int)((uint32_t)carry & 0x7FFFFFFFu), carry_starts = (int)(uint32_t)(carry >> 32);
+  if (!((carry >> 31) & 1ull)) {  // no document start earlier in this scan block: add the block's carry
+    const uint64_t bc = __ldg(P.block_carry + (t >> 10));
+    carry_chars += (int)(uint32_t)bc; carry_starts += (int)(uint32_t)(bc >> 32);
+  }
   const bool want_off = P.flags & F_OFFSETS, want_wid = P.flags & F_WORD_IDS, byte_off = P.flags & F_BYTE_OFFSETS;
 
   // ---------------------------------------------------------------- P7: emit tokens in order
@@ -505,11 +688,10 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
       P.word_ids[out] = (uint32_t)(kept_incl(ts) - 1 - wb);
     }
   };
-  for (int row = warp; row < NW; row += NWARPS) {
-    const uint32_t tb = s_tokb[row];
-    if (!((tb >> lane) & 1u)) continue;
-    const int pos = row * 32 + lane;
-    const unsigned long long out = excl + s_tpref[row] + __popc(tb & ((1u << lane) - 1u)) + long_tokens_before(pos);
+  const int n_normal = s_ntok;
+  for (int j = tid; j < n_normal; j += MODEL_THREADS) {
+    const int pos = s_tokpos[j];
+    const unsigned long long out = excl + (unsigned long long)(j + long_tokens_before(pos));
     const int e = pos + s_len[pos];
     emit(out, s_id[pos], pos, base + e, lc_incl(e - 1), true);
   }
@@ -548,7 +730,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
   }
   if (MODEL == MODEL_WORDPIECE && long_kept && tid == 0) {
     const int ls = s_pt[Pn - 1];
-    const unsigned long long out = excl + (unsigned long long)(s_ntok - 1);
+    const unsigned long long out = excl + (unsigned long long)(s_ntot - 1);
     // chars up to the end of the long split = chars before it in the page + its own
     const int end_chars = lc_incl(ls) - 1 + s_long_chars;
     emit(out, P.t.unk_id, ls, s_long_end, end_chars, true);

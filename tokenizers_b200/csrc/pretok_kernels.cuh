@@ -192,46 +192,91 @@ __global__ void __launch_bounds__(TC) pretok_scan_kernel(const uint8_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ K1b
-// Exclusive segmented scan over the page summaries -> page_carry (single block; n_pages ~ n/2048 entries).
+// Exclusive SEGMENTED scan over the page summaries (segments restart at document starts) -> page_carry.
+// Two tiny kernels: (1) every block scans 1024 pages (one per thread, coalesced) and emits its block summary,
+// (2) one block scans the block summaries.  A page whose block has no document start before it adds its block's
+// carry when it is consumed (bit 31 of the low word says "already absolute").
 __device__ __forceinline__ void sum_unpack(uint64_t s, uint32_t& tc, uint32_t& ts, uint32_t& ac, uint32_t& as, uint32_t& f) {
   tc = (uint32_t)(s & 0xFFFu); ts = (uint32_t)((s >> 12) & 0xFFFu); ac = (uint32_t)((s >> 24) & 0xFFFu);
   as = (uint32_t)((s >> 36) & 0xFFFu); f = (uint32_t)((s >> 48) & 1u);
 }
 
-__global__ void __launch_bounds__(1024) page_scan_kernel(const uint64_t* __restrict__ page_sum, uint64_t* __restrict__ page_carry,
-                                                         int64_t n_pages) {
-  __shared__ uint32_t s_c[1024], s_s[1024], s_f[1024];
-  const int tid = threadIdx.x;
-  const int64_t per = (n_pages + 1023) / 1024;
-  const int64_t lo = (int64_t)tid * per, hi = (lo + per < n_pages) ? lo + per : n_pages;
-  // pass 1: summary of my segment as a function of the incoming carry: out = flag ? after : in + total
-  uint32_t totc = 0, tots = 0, aftc = 0, afts = 0, flag = 0;
-  for (int64_t p = lo; p < hi; ++p) {
-    uint32_t tc, ts, ac, as, f;
-    sum_unpack(page_sum[p], tc, ts, ac, as, f);
-    if (f) { aftc = ac; afts = as; flag = 1; } else { aftc += tc; afts += ts; }
-    totc += tc; tots += ts;
+struct SegVal { uint32_t f, c, s; };  // "carry after" as a function of "carry before": f ? (c, s) : before + (c, s)
+__device__ __forceinline__ SegVal seg_combine(SegVal earlier, SegVal later) {
+  SegVal r;
+  r.f = earlier.f | later.f;
+  r.c = later.f ? later.c : earlier.c + later.c;
+  r.s = later.f ? later.s : earlier.s + later.s;
+  return r;
+}
+// inclusive block scan (1024 threads); returns this thread's inclusive value, *excl = exclusive value
+__device__ __forceinline__ SegVal seg_block_scan(SegVal v, SegVal* excl, SegVal* s_w /*32*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int st = 1; st < 32; st <<= 1) {
+    SegVal o;
+    o.f = __shfl_up_sync(0xFFFFFFFFu, v.f, st); o.c = __shfl_up_sync(0xFFFFFFFFu, v.c, st); o.s = __shfl_up_sync(0xFFFFFFFFu, v.s, st);
+    if (lane >= st) v = seg_combine(o, v);
   }
-  // "aft*" now = chars/splits since the last doc start in the segment (or since segment start if none)
-  s_c[tid] = aftc; s_s[tid] = afts; s_f[tid] = flag;
+  if (lane == 31) s_w[warp] = v;
   __syncthreads();
-  // exclusive segmented scan over the 1024 segment summaries (Hillis-Steele on (value, flag))
-  uint32_t vc = aftc, vs = afts, vf = flag;
-  for (int s = 1; s < 1024; s <<= 1) {
-    uint32_t oc = 0, os = 0, of = 0;
-    if (tid >= s) { oc = s_c[tid - s]; os = s_s[tid - s]; of = s_f[tid - s]; }
-    __syncthreads();
-    if (tid >= s && !vf) { vc += oc; vs += os; vf = of; }
-    s_c[tid] = vc; s_s[tid] = vs; s_f[tid] = vf;
-    __syncthreads();
+  if (warp == 0) {
+    SegVal w = s_w[lane];
+#pragma unroll
+    for (int st = 1; st < 32; st <<= 1) {
+      SegVal o;
+      o.f = __shfl_up_sync(0xFFFFFFFFu, w.f, st); o.c = __shfl_up_sync(0xFFFFFFFFu, w.c, st); o.s = __shfl_up_sync(0xFFFFFFFFu, w.s, st);
+      if (lane >= st) w = seg_combine(o, w);
+    }
+    s_w[lane] = w;  // inclusive over warps
   }
-  uint32_t cc = tid ? s_c[tid - 1] : 0u, cs = tid ? s_s[tid - 1] : 0u;  // carry into my segment
-  // pass 2
-  for (int64_t p = lo; p < hi; ++p) {
-    page_carry[p] = (uint64_t)cc | ((uint64_t)cs << 32);
+  __syncthreads();
+  SegVal before; before.f = 0; before.c = 0; before.s = 0;
+  if (warp > 0) before = s_w[warp - 1];
+  SegVal incl = seg_combine(before, v);
+  SegVal pv;
+  pv.f = __shfl_up_sync(0xFFFFFFFFu, v.f, 1); pv.c = __shfl_up_sync(0xFFFFFFFFu, v.c, 1); pv.s = __shfl_up_sync(0xFFFFFFFFu, v.s, 1);
+  *excl = lane == 0 ? before : seg_combine(before, pv);
+  __syncthreads();
+  return incl;
+}
+
+constexpr int SCAN_BLOCK = 1024;
+
+__global__ void __launch_bounds__(SCAN_BLOCK) page_scan_block_kernel(const uint64_t* __restrict__ page_sum, uint64_t* __restrict__ page_carry,
+                                                                    uint64_t* __restrict__ block_sum, int64_t n_pages) {
+  __shared__ SegVal s_w[32];
+  const int64_t i = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  SegVal v; v.f = 0; v.c = 0; v.s = 0;
+  if (i < n_pages) {
     uint32_t tc, ts, ac, as, f;
-    sum_unpack(page_sum[p], tc, ts, ac, as, f);
-    if (f) { cc = ac; cs = as; } else { cc += tc; cs += ts; }
+    sum_unpack(__ldg(page_sum + i), tc, ts, ac, as, f);
+    v.f = f; v.c = f ? ac : tc; v.s = f ? as : ts;
+  }
+  SegVal ex;
+  SegVal incl = seg_block_scan(v, &ex, s_w);
+  if (i < n_pages) page_carry[i] = (uint64_t)(ex.c | (ex.f << 31)) | ((uint64_t)ex.s << 32);
+  if (threadIdx.x == SCAN_BLOCK - 1) block_sum[blockIdx.x] = (uint64_t)(incl.c | (incl.f << 31)) | ((uint64_t)incl.s << 32);
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) page_scan_top_kernel(const uint64_t* __restrict__ block_sum, uint64_t* __restrict__ block_carry,
+                                                                  int64_t n_blocks) {
+  __shared__ SegVal s_w[32];
+  __shared__ SegVal s_run;
+  if (threadIdx.x == 0) { s_run.f = 0; s_run.c = 0; s_run.s = 0; }
+  __syncthreads();
+  for (int64_t base = 0; base < n_blocks; base += SCAN_BLOCK) {
+    const int64_t i = base + threadIdx.x;
+    SegVal v; v.f = 0; v.c = 0; v.s = 0;
+    if (i < n_blocks) { uint64_t x = __ldg(block_sum + i); v.f = (uint32_t)(x >> 31) & 1u; v.c = (uint32_t)x & 0x7FFFFFFFu; v.s = (uint32_t)(x >> 32); }
+    SegVal ex;
+    SegVal incl = seg_block_scan(v, &ex, s_w);
+    const SegVal run = s_run;
+    const SegVal ex_abs = seg_combine(run, ex);
+    if (i < n_blocks) block_carry[i] = (uint64_t)ex_abs.c | ((uint64_t)ex_abs.s << 32);
+    __syncthreads();
+    if (threadIdx.x == SCAN_BLOCK - 1) s_run = seg_combine(run, incl);
+    __syncthreads();
   }
 }
 
