@@ -129,6 +129,9 @@ def cpu_reference(cfg, data, off, budget_s=15.0):
 
 
 def main():
+    # Only the JSON line may reach stdout (NCCL and others print there): park the real stdout, send fd 1 to stderr.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -163,11 +166,12 @@ def main():
                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": workload, "bytes_per_step": None, "sample": r["sample"]},
                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(out))
+        real_stdout.write(json.dumps(out) + "\n"); real_stdout.flush()
         return
 
     import torch
     from tokenizers_b200 import Tokenizer, _lib
+    from tokenizers_b200.parallel import all_gather_csr
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
@@ -197,24 +201,17 @@ def main():
         def __init__(self, ptr, count, typestr):
             self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
 
-    gbuf = {}
+    gathered = {}
 
     def step_device():
         res = ctypes.c_void_p()
         _lib.check(L.b2t_encode_batch_device(tok.handle, d_bytes.data_ptr(), n, d_off.data_ptr(), n_docs, flags, ctypes.c_void_p(stream.cuda_stream), ctypes.byref(res)))
         T = L.b2t_result_n_tokens(res)
-        if world > 1:  # one all-gather-v of the token CSR (counts, then padded payloads)
-            cnt = torch.tensor([T], dtype=torch.int64, device="cuda")
-            cnts = torch.empty(world, dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(cnts, cnt)
-            mx = int(cnts.max().item())
-            ids = torch.as_tensor(DevArr(L.b2t_result_ids(res), mx, "<i4"), device="cuda")
-            offs = torch.as_tensor(DevArr(L.b2t_result_offsets(res), 2 * mx, "<i4"), device="cuda")
-            if gbuf.get("ids") is None or gbuf["ids"].numel() < world * mx:
-                gbuf["ids"] = torch.empty(world * mx, dtype=torch.int32, device="cuda")
-                gbuf["off"] = torch.empty(2 * world * mx, dtype=torch.int32, device="cuda")
-            dist.all_gather_into_tensor(gbuf["ids"][: world * mx], ids)
-            dist.all_gather_into_tensor(gbuf["off"][: 2 * world * mx], offs)
+        if world > 1:  # one all-gather-v of the token CSR over NCCL (tokenizers_b200/parallel.py)
+            ids = torch.as_tensor(DevArr(L.b2t_result_ids(res), T, "<i4"), device="cuda")
+            offs = torch.as_tensor(DevArr(L.b2t_result_offsets(res), 2 * T, "<i4"), device="cuda")
+            rp = torch.as_tensor(DevArr(L.b2t_result_row_ptr(res), n_docs + 1, "<i8"), device="cuda")
+            gathered["csr"] = all_gather_csr(ids, offs.reshape(-1, 2), rp)
         L.b2t_result_free(res)
         return T
 
@@ -310,7 +307,7 @@ def main():
             out["cpu_baseline"] = {k: v for k, v in cpu_reference(cfg, hbuf[:n], off).items() if k != "seconds"}
         except Exception as ex:  # the wheel is part of the image; if it is missing say so instead of inventing a number
             out["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": len(os.sched_getaffinity(0)), "kind": "reference", "sample": f"unavailable: {ex}"}
-    print(json.dumps(out))
+    real_stdout.write(json.dumps(out) + "\n"); real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

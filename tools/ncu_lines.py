@@ -17,7 +17,7 @@ for ln in lines:
     if not infn: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m: cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln): insn_lines.append(cur)
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln): insn_lines.append(cur)
 print("sass instrs", len(insn_lines), "ncu rows", len(data))
 agg = {}
 tot = sum(int(r[ix]) for r in data)
