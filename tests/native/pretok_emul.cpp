@@ -22,7 +22,7 @@ extern "C" int b2t_emul_pretok(int kind, const uint8_t* bytes, uint64_t n, const
       for (int b = 0; b < 4; ++b) x |= at(c * 32 + j * 4 + b) << (8 * b);
       w[j] = x;
     }
-    M[c] = classify_chunk(w, c * 32, (int64_t)n, at, cls_tbl, kind == PT_WHITESPACE);
+    M[c] = classify_chunk(w, c * 32, (int64_t)n, at, cls_tbl, kind);
   }
   ChunkMasks zero;
   std::memset(&zero, 0, sizeof(zero));

@@ -247,10 +247,12 @@ static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Work
   constexpr int TC = 256;
   const int64_t n_chunks = n / CHUNK + 1;
   const int64_t n_tiles = (n_chunks + TC - 1) / TC;
-  int64_t grid = std::min<int64_t>(n_tiles, (int64_t)e->sm_count * 8);
+  // contiguous tile ranges per block (the kernel pipelines consecutive tiles); ~8 blocks per SM
+  int64_t tiles_per_block = std::max<int64_t>(1, (n_tiles + (int64_t)e->sm_count * 8 - 1) / ((int64_t)e->sm_count * 8));
+  int64_t grid = (n_tiles + tiles_per_block - 1) / tiles_per_block;
   pretok_scan_kernel<KIND, TC><<<(unsigned)grid, TC, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
                                                              ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
-                                                             ws.page_sum.as<uint64_t>(), n_tiles);
+                                                             ws.page_sum.as<uint64_t>(), n_tiles, tiles_per_block);
 }
 
 static void rec(b2t_engine* e, cudaStream_t st, const char* name) {

@@ -68,23 +68,9 @@ __device__ __forceinline__ ChunkMasks classify_global(const uint8_t* __restrict_
   uint32_t w[8];
   load_chunk_words(bytes, base, n, w);
   ByteAtGlobal at{bytes, n};
-  return classify_chunk(w, base, n, at, cls_tbl, KIND == PT_WHITESPACE);
+  return classify_chunk(w, base, n, at, cls_tbl, KIND);
 }
 
-// masks of any chunk: from shared memory when it belongs to the tile (+-1 chunk), else re-classified from global
-template <int KIND, int TC>
-struct TileMaskAt {
-  const ChunkMasks* sm;  // TC + 2 entries, entry 0 = chunk tile_c0 - 1
-  int64_t tile_c0;
-  const uint8_t* __restrict__ bytes;
-  int64_t n;
-  const uint32_t* __restrict__ cls_tbl;
-  __device__ __forceinline__ ChunkMasks operator()(int64_t k) const {
-    int64_t r = k - tile_c0 + 1;
-    if (r >= 0 && r < TC + 2) return sm[r];
-    return classify_global<KIND>(bytes, n, k, cls_tbl);
-  }
-};
 struct DsAtGlobal {
   const uint32_t* __restrict__ doc_bits;
   int64_t n_chunks;
@@ -98,41 +84,128 @@ __device__ __forceinline__ uint64_t pack_sum(uint32_t tot, uint32_t aft, uint32_
          ((uint64_t)((aft >> 16) & 0xFFFu) << 36) | ((uint64_t)(flag & 1u) << 48);
 }
 
+// K1.  Each block owns a contiguous range of tiles (TC chunks = TC * 32 bytes each) and software-pipelines them:
+// phase A of tile t+1 (class masks -> shared memory) runs before phase B of tile t (boundaries from the 64-byte
+// windows), so the halo chunk on the right comes for free and the one on the left is kept from the previous tile.
+//   A1  per lane: 2 x 16-byte loads, ASCII masks by SWAR (ascii_masks), store to shared memory
+//   A2  per warp: the non-ASCII characters of the warp's 1 KB are compacted into a list and classified by all 32
+//       lanes together (decode + 2-bit class table), results OR-ed into the owners' masks with shared atomics --
+//       no lane diverges on "my chunk has 10 Cyrillic letters and yours has none"
+//   B   per lane: windows from the neighbours' masks, boundary algebra (pretok_logic.cuh), 4-byte store of the bitmap
+//       word, page summaries by warp reductions
 template <int KIND, int TC>
 __global__ void __launch_bounds__(TC) pretok_scan_kernel(const uint8_t* __restrict__ bytes, int64_t n,
                                                          const uint32_t* __restrict__ doc_bits,
                                                          const uint32_t* __restrict__ cls_tbl,
                                                          uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
-                                                         uint64_t* __restrict__ page_sum, int64_t n_tiles) {
-  __shared__ ChunkMasks sm[TC + 2];
-  __shared__ uint32_t sds[TC + 2];
-  __shared__ uint32_t s_wsum[(TC / 32) * 3];
+                                                         uint64_t* __restrict__ page_sum, int64_t n_tiles, int64_t tiles_per_block) {
+  constexpr int NWARPS = TC / 32;
+  __shared__ ChunkMasks sm[2][TC];
+  __shared__ ChunkMasks sm_prev;                 // last chunk of the tile before the one in phase B
+  __shared__ uint32_t s_spill[2][NWARPS][4];     // class bits spilling from a warp's last chunk into the next warp's first
+  __shared__ uint16_t s_list[NWARPS][512];       // positions (within the warp's 1 KB) of its non-ASCII lead bytes
+  __shared__ uint32_t s_wsum[NWARPS * 3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_chunks = n / CHUNK + 1;
   ByteAtGlobal at{bytes, n};
   DsAtGlobal dsat{doc_bits, n_chunks};
+  const int64_t t_lo = (int64_t)blockIdx.x * tiles_per_block;
+  const int64_t t_hi = (t_lo + tiles_per_block < n_tiles) ? t_lo + tiles_per_block : n_tiles;
+  if (t_lo >= t_hi) return;
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t c0 = tile * TC, c = c0 + tid;
-    // ---- phase A: class masks of my chunk (+ the two halo chunks) into shared memory
-    sm[tid + 1] = classify_global<KIND>(bytes, n, c, cls_tbl);
-    sds[tid + 1] = dsat(c);
-    if (tid < 2) {
-      int64_t hc = tid == 0 ? c0 - 1 : c0 + TC;
-      sm[tid == 0 ? 0 : TC + 1] = classify_global<KIND>(bytes, n, hc, cls_tbl);
-      sds[tid == 0 ? 0 : TC + 1] = dsat(hc);
+  // ---- phase A of one tile into buffer `buf`
+  auto phase_a = [&](int64_t tile, int buf) {
+    const int64_t c = tile * TC + tid, base = c * CHUNK;
+    ChunkMasks m;
+    uint32_t hi = 0, cont = 0;
+    if (base < n) {
+      uint32_t w[8];
+      load_chunk_words(bytes, base, n, w);
+      ascii_masks(KIND, w, m, &hi, &cont);
+      if (base + CHUNK > n) {
+        const uint32_t valid = 0xFFFFFFFFu >> (32 - (int)(n - base));
+        m.lead &= valid; hi &= valid; cont &= valid;
+      }
+    } else { m.lead = m.L = m.N = m.S = m.SP = m.NL = m.AP = 0u; }
+    sm[buf][tid] = m;
+    // my OUTGOING spill slot (the incoming one may be written by the warp below at any time; slot 0 stays zero)
+    if (lane < 4 && warp + 1 < NWARPS) s_spill[buf][warp + 1][lane] = 0u;
+    __syncwarp();
+    if (__any_sync(0xFFFFFFFFu, hi != 0u)) {
+      // A2: compact the warp's non-ASCII lead bytes, then classify them with all lanes
+      uint32_t nl = hi & ~cont;
+      const int cnt = __popc(nl);
+      int inc = cnt;
+#pragma unroll
+      for (int st = 1; st < 32; st <<= 1) { int o = __shfl_up_sync(0xFFFFFFFFu, inc, st); if (lane >= st) inc += o; }
+      const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+      int off = inc - cnt;
+      while (nl) { s_list[warp][off++] = (uint16_t)(lane * 32 + __ffs((int)nl) - 1); nl &= nl - 1u; }
+      // a character that started in the previous TILE owns my first bytes (tid 0 only; inside the tile the owner
+      // of the lead byte spills its bits into the neighbour below)
+      if (tid == 0 && (cont & 1u)) {
+        int back = 1;
+        while (back < 3 && (at(base - back) & 0xC0u) == 0x80u) ++back;
+        int len;
+        const int64_t q = base - back;
+        const uint32_t cl = decode_class(at(q), at(q + 1), at(q + 2), at(q + 3), cls_tbl, &len);
+        const int cover = len - back;
+        if (cover > 0 && cl != CLS_O) atomicOr(reinterpret_cast<uint32_t*>(&sm[buf][0]) + cl, (1u << cover) - 1u);
+      }
+      __syncwarp();
+      const int64_t wbase = (tile * TC + warp * 32) * CHUNK;
+      for (int i = lane; i < total; i += 32) {
+        const int idx = s_list[warp][i];
+        const int64_t gp = wbase + idx;
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(bytes + (gp & ~(int64_t)3));
+        const uint32_t a0 = __ldg(aw), a1 = ((gp & ~(int64_t)3) + 4 < n) ? __ldg(aw + 1) : 0u;
+        const uint32_t v = __funnelshift_r(a0, a1, (uint32_t)(gp & 3) * 8u);
+        int len;
+        const uint32_t cl = decode_class(v & 0xFFu, (v >> 8) & 0xFFu, (v >> 16) & 0xFFu, v >> 24, cls_tbl, &len);
+        if (cl != CLS_O) {
+          const int owner = idx >> 5, p = idx & 31;
+          const uint64_t bits = ((1ull << len) - 1ull) << p;
+          atomicOr(reinterpret_cast<uint32_t*>(&sm[buf][warp * 32 + owner]) + cl, (uint32_t)bits);
+          const uint32_t hi32 = (uint32_t)(bits >> 32);
+          if (hi32) {
+            if (owner < 31) atomicOr(reinterpret_cast<uint32_t*>(&sm[buf][warp * 32 + owner + 1]) + cl, hi32);
+            else if (warp + 1 < NWARPS) atomicOr(&s_spill[buf][warp + 1][cl], hi32);
+          }
+        }
+      }
+    }
+  };
+  auto load_masks = [&](int buf, int idx) -> ChunkMasks {
+    ChunkMasks m = sm[buf][idx];
+    if ((idx & 31) == 0) { const uint32_t* sp = s_spill[buf][idx >> 5]; m.L |= sp[CLS_L]; m.N |= sp[CLS_N]; m.S |= sp[CLS_S]; }
+    return m;
+  };
+
+  // ---- prologue
+  if (tid < 8) s_spill[tid >> 2][0][tid & 3] = 0u;
+  if (tid == 0) {
+    sm_prev = classify_global<KIND>(bytes, n, t_lo * TC - 1, cls_tbl);
+  }
+  phase_a(t_lo, (int)(t_lo & 1));
+
+  for (int64_t tile = t_lo; tile < t_hi; ++tile) {
+    const int buf = (int)(tile & 1), nbuf = buf ^ 1;
+    if (tile + 1 < t_hi) phase_a(tile + 1, nbuf);
+    else if (tid == 0) {  // first chunk after my range (phase B of my last tile looks 16 bytes into it)
+      sm[nbuf][0] = classify_global<KIND>(bytes, n, (tile + 1) * TC, cls_tbl);
     }
     __syncthreads();
-    // ---- phase B: boundaries of my 32 positions from the 64-byte window
+    // ---- phase B
+    const int64_t c = tile * TC + tid;
     BoundaryOut r;
-    uint32_t own_lead, own_ds;
+    ChunkMasks o = load_masks(buf, tid);
     {
-      const ChunkMasks p = sm[tid], o = sm[tid + 1], x = sm[tid + 2];
+      const ChunkMasks p = tid == 0 ? sm_prev : load_masks(buf, tid - 1);
+      const ChunkMasks x = tid == TC - 1 ? load_masks(nbuf, 0) : load_masks(buf, tid + 1);
       Window w;
       w.lead = win(p.lead, o.lead, x.lead); w.L = win(p.L, o.L, x.L); w.N = win(p.N, o.N, x.N); w.S = win(p.S, o.S, x.S);
-      w.SP = win(p.SP, o.SP, x.SP); w.NL = win(p.NL, o.NL, x.NL); w.AP = win(p.AP, o.AP, x.AP);
-      w.DS = win(sds[tid], sds[tid + 1], sds[tid + 2]);
-      own_lead = o.lead; own_ds = sds[tid + 1];
+      w.SP = win(p.SP, o.SP, x.SP); w.NL = KIND == PT_LLAMA3 ? win(p.NL, o.NL, x.NL) : 0ull; w.AP = win(p.AP, o.AP, x.AP);
+      w.DS = win(dsat(c - 1), dsat(c), dsat(c + 1));
       const int64_t wb = c * CHUNK - 16;
       if (KIND == PT_GPT2) {
         r = boundaries_gpt2(w, wb, at);
@@ -140,7 +213,11 @@ __global__ void __launch_bounds__(TC) pretok_scan_kernel(const uint8_t* __restri
         LlamaCarry cy; cy.n_count_before_window = 0; cy.zone_before_window = false; cy.tail_after_window = false;
         r = boundaries_llama3(w, wb, at, cy);
         if (r.slow) {
-          TileMaskAt<KIND, TC> masks{sm, c0, bytes, n, cls_tbl};
+          // rare: a run reaches beyond the window; the carry walks chunk masks re-classified from global memory
+          struct GlobalMaskAt {
+            const uint8_t* bytes; int64_t n; const uint32_t* cls;
+            __device__ __forceinline__ ChunkMasks operator()(int64_t k) const { return classify_global<KIND>(bytes, n, k, cls); }
+          } masks{bytes, n, cls_tbl};
           cy = llama_carry(c, n_chunks, masks, dsat);
           r = boundaries_llama3(w, wb, at, cy);
         }
@@ -150,44 +227,46 @@ __global__ void __launch_bounds__(TC) pretok_scan_kernel(const uint8_t* __restri
         r.start = (uint32_t)((w.DS & w.lead) >> 16); r.drop = 0; r.slow = 0;
       }
     }
+    const uint32_t own_ds = dsat(c);
     if (c < n_chunks) {
       start_bits[c] = r.start;
       if (KIND == PT_WHITESPACE) drop_bits[c] = r.drop;
     }
-    // ---- page summaries (segmented: counts restart at the last doc start of the page)
+    // ---- page summaries (segmented: counts restart at the last doc start of the page), warp reductions
     {
-      uint32_t kept = r.start & ~r.drop;
-      uint32_t tot = (uint32_t)__popc(own_lead) | ((uint32_t)__popc(kept) << 16);
-      uint32_t flag = own_ds != 0u, aft = 0u;
-      if (flag) {
-        uint32_t from = ~bits_below(31 - __clz((int)own_ds));
-        aft = (uint32_t)__popc(own_lead & from) | ((uint32_t)__popc(kept & from) << 16);
-      }
-#pragma unroll
-      for (int s = 1; s < 32; s <<= 1) {  // combine(mine = earlier, other = later)
-        uint32_t o_tot = __shfl_down_sync(0xFFFFFFFFu, tot, s), o_aft = __shfl_down_sync(0xFFFFFFFFu, aft, s),
-                 o_flag = __shfl_down_sync(0xFFFFFFFFu, flag, s);
-        if (lane + s < 32) {
-          aft = o_flag ? o_aft : aft + o_tot;
-          tot += o_tot;
-          flag |= o_flag;
+      const uint32_t kept = r.start & ~r.drop;
+      const uint32_t tot = (uint32_t)__popc(o.lead) | ((uint32_t)__popc(kept) << 16);
+      const unsigned dsm = __ballot_sync(0xFFFFFFFFu, own_ds != 0u);
+      const uint32_t wtot = __reduce_add_sync(0xFFFFFFFFu, tot);
+      uint32_t waft = 0;
+      if (dsm) {
+        const int last = 31 - __clz((int)dsm);
+        uint32_t mine = 0;
+        if (lane > last) mine = tot;
+        else if (lane == last) {
+          const uint32_t from = ~bits_below(31 - __clz((int)own_ds));
+          mine = (uint32_t)__popc(o.lead & from) | ((uint32_t)__popc(kept & from) << 16);
         }
+        waft = __reduce_add_sync(0xFFFFFFFFu, mine);
       }
-      if (lane == 0) { s_wsum[warp * 3] = tot; s_wsum[warp * 3 + 1] = aft; s_wsum[warp * 3 + 2] = flag; }
-      __syncthreads();
+      if (lane == 0) { s_wsum[warp * 3] = wtot; s_wsum[warp * 3 + 1] = waft; s_wsum[warp * 3 + 2] = dsm != 0u; }
+    }
+    __syncthreads();  // all reads of sm[buf] / sm_prev are done; s_wsum is complete
+    {
       constexpr int WPP = PAGE_CHUNKS / 32;  // warps per page (2)
-      if (tid < TC / 32 / WPP) {
+      if (tid < NWARPS / WPP) {
         uint32_t t0 = s_wsum[(tid * WPP) * 3], a0 = s_wsum[(tid * WPP) * 3 + 1], f0 = s_wsum[(tid * WPP) * 3 + 2];
 #pragma unroll
         for (int k = 1; k < WPP; ++k) {
           uint32_t t1 = s_wsum[(tid * WPP + k) * 3], a1 = s_wsum[(tid * WPP + k) * 3 + 1], f1 = s_wsum[(tid * WPP + k) * 3 + 2];
           a0 = f1 ? a1 : a0 + t1; t0 += t1; f0 |= f1;
         }
-        int64_t page = tile * (TC / PAGE_CHUNKS) + tid;
+        const int64_t page = tile * (TC / PAGE_CHUNKS) + tid;
         if (page * PAGE <= n) page_sum[page] = pack_sum(t0, a0, f0);
       }
+      if (tid == TC - 1) sm_prev = o;
     }
-    __syncthreads();  // shared memory is reused by the next tile
+    // the next iteration's phase A writes sm[buf] and s_wsum is rewritten only after the next barrier
   }
 }
 

@@ -93,67 +93,111 @@ B2T_HD uint32_t decode_at(const ByteAt& at, int64_t p, int64_t end, int* len) {
   return ((b0 & 7u) << 18) | ((b1 & 63u) << 12) | ((b2 & 63u) << 6) | (b3 & 63u);
 }
 
-// Classify the 32 bytes [base, base+32) of a buffer of n bytes.  w[0..7] are the chunk's bytes as little-endian
-// words (bytes at positions >= n must be zero).  `at(pos)` gives random access to any byte in [0, n).
-// rust_classes selects the ASCII fast path of the Whitespace pre-tokenizer's classes (cls_tbl must match).
+// ASCII half of phase A.  Bit-7-per-byte flags are computed with SWAR range checks (3 ops each) and transposed into
+// 32-bit position masks two words at a time (movemask2 gives 8 mask bits per multiply).  Apostrophes and control
+// characters are rare, so their masks are built in a second pass only when a cheap detector saw one.
+// Outputs: m.L / m.N / m.S / m.SP / m.NL / m.AP for ASCII bytes only, *hi = non-ASCII bytes, *cont = continuation bytes.
+// kind: PT_WHITESPACE uses the Rust-regex classes (\w on ASCII = [0-9A-Za-z_], N slot unused).
+B2T_HD void ascii_masks(int kind, const uint32_t w[8], ChunkMasks& m, uint32_t* hi_out, uint32_t* cont_out) {
+  const bool rust = kind == PT_WHITESPACE;
+  uint32_t L = 0, N = 0, SP = 0, CT = 0, HI = 0, any_ctl = 0, any_ap = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    uint32_t fL[2], fN[2], fSP[2], fCT[2], fHI[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t x = w[j + h];
+      const uint32_t asc = ~x & 0x80808080u;            // bit 7 set <=> ASCII byte
+      const uint32_t w7 = x & 0x7F7F7F7Fu;
+      const uint32_t t = w7 | 0x20202020u;
+      uint32_t l = (t + 0x1F1F1F1Fu) & ~(t + 0x05050505u) & asc;             // 'a'..'z' after folding case
+      uint32_t d = (w7 + 0x50505050u) & ~(w7 + 0x46464646u) & asc;           // '0'..'9'
+      if (rust) { l |= d | ((w7 + 0x21212121u) & ~(w7 + 0x20202020u) & asc); d = 0u; }  // + '_' (0x5F)
+      fL[h] = l; fN[h] = d;
+      fSP[h] = (w7 + 0x60606060u) & ~(w7 + 0x5F5F5F5Fu) & asc;               // == 0x20
+      any_ctl |= ~(w7 + 0x60606060u) & asc;                                   // < 0x20
+      any_ap |= (w7 + 0x59595959u) & ~(w7 + 0x58585858u) & asc;              // == 0x27
+      fCT[h] = x & ~(x << 1) & 0x80808080u;                                   // 10xxxxxx
+      fHI[h] = x & 0x80808080u;
+    }
+    const int sh = 4 * j;  // 8 mask bits per pair of words
+    L |= movemask2(fL[0], fL[1]) << sh;
+    if (!rust) N |= movemask2(fN[0], fN[1]) << sh;
+    SP |= movemask2(fSP[0], fSP[1]) << sh;
+    CT |= movemask2(fCT[0], fCT[1]) << sh;
+    HI |= movemask2(fHI[0], fHI[1]) << sh;
+  }
+  uint32_t S = SP, NL = 0, AP = 0;
+  if (any_ctl) {  // \t \n \v \f \r are whitespace; \n and \r are the newlines of the tiktoken pattern
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      uint32_t a[2], b[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t x = w[j + h], asc = ~x & 0x80808080u, w7 = x & 0x7F7F7F7Fu;
+        a[h] = (w7 + 0x77777777u) & ~(w7 + 0x72727272u) & asc;                // 9..13
+        b[h] = (((w7 + 0x76767676u) & ~(w7 + 0x75757575u)) | ((w7 + 0x73737373u) & ~(w7 + 0x72727272u))) & asc;  // 10, 13
+      }
+      S |= movemask2(a[0], a[1]) << (4 * j);
+      NL |= movemask2(b[0], b[1]) << (4 * j);
+    }
+  }
+  if (any_ap) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      uint32_t a[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t x = w[j + h], asc = ~x & 0x80808080u, w7 = x & 0x7F7F7F7Fu;
+        a[h] = (w7 + 0x59595959u) & ~(w7 + 0x58585858u) & asc;
+      }
+      AP |= movemask2(a[0], a[1]) << (4 * j);
+    }
+  }
+  m.L = L; m.N = N; m.S = S; m.SP = SP; m.NL = NL; m.AP = AP; m.lead = ~CT;
+  *hi_out = HI; *cont_out = CT;
+}
+
+// Class and length of the (non-ASCII) character whose UTF-8 bytes are b0 b1 b2 b3 (valid UTF-8 assumed).
+B2T_HD uint32_t decode_class(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, const uint32_t* __restrict__ cls_tbl, int* len) {
+  uint32_t cp;
+  if (b0 < 0xE0u) { *len = 2; cp = ((b0 & 31u) << 6) | (b1 & 63u); }
+  else if (b0 < 0xF0u) { *len = 3; cp = ((b0 & 15u) << 12) | ((b1 & 63u) << 6) | (b2 & 63u); }
+  else { *len = 4; cp = ((b0 & 7u) << 18) | ((b1 & 63u) << 12) | ((b2 & 63u) << 6) | (b3 & 63u); }
+  return class_of(cls_tbl, cp);
+}
+
+// Classify the 32 bytes [base, base+32) of a buffer of n bytes, everything included (generic path: CPU emulation,
+// halo chunks and slow paths on the device).  w[0..7] are the chunk's bytes as little-endian words (bytes at
+// positions >= n must be zero).  `at(pos)` gives random access to any byte in [0, n).
 template <class ByteAt>
 B2T_HD ChunkMasks classify_chunk(const uint32_t w[8], int64_t base, int64_t n, const ByteAt& at,
-                                 const uint32_t* __restrict__ cls_tbl, bool rust_classes) {
+                                 const uint32_t* __restrict__ cls_tbl, int kind) {
   ChunkMasks m;
-  m.lead = m.L = m.N = m.S = m.SP = m.NL = m.AP = 0u;
-  uint32_t hi_any = 0u;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint32_t x = w[j];
-    uint32_t hi = x & 0x80808080u;
-    uint32_t w7 = x & 0x7F7F7F7Fu;
-    uint32_t asc = ~hi;
-    uint32_t fL = swar_range(w7 | 0x20202020u, 'a', 'z') & asc;
-    uint32_t fN = swar_range(w7, '0', '9') & asc;
-    if (rust_classes) {  // Rust regex \w on ASCII = [0-9A-Za-z_]; the N slot is unused
-      fL |= fN | (swar_range(w7, '_', '_') & asc);
-      fN = 0u;
-    }
-    uint32_t fSP = swar_range(w7, 0x20, 0x20) & asc;
-    uint32_t fS = (swar_range(w7, 9, 13) & asc) | fSP;
-    uint32_t fNL = (swar_range(w7, 10, 10) | swar_range(w7, 13, 13)) & asc;
-    uint32_t fAP = swar_range(w7, 0x27, 0x27) & asc;
-    uint32_t cont = hi & ~(x << 1) ;  // bit7 & ~bit6  -> continuation byte 10xxxxxx
-    uint32_t g0 = movemask2(fL, fN), g1 = movemask2(fS, fSP), g2 = movemask2(fNL, fAP), g3 = movemask2(cont & 0x80808080u, hi);
-    m.L |= (g0 & 15u) << (4 * j);
-    m.N |= (g0 >> 4) << (4 * j);
-    m.S |= (g1 & 15u) << (4 * j);
-    m.SP |= (g1 >> 4) << (4 * j);
-    m.NL |= (g2 & 15u) << (4 * j);
-    m.AP |= (g2 >> 4) << (4 * j);
-    m.lead |= (g3 & 15u) << (4 * j);  // temporarily: continuation mask
-    hi_any |= (g3 >> 4) << (4 * j);   // non-ASCII mask
-  }
-  uint32_t cont = m.lead;
-  m.lead = ~cont;
+  uint32_t hi_any, cont;
+  ascii_masks(kind, w, m, &hi_any, &cont);
   if (hi_any) {
-    // characters that start before the chunk but own its first bytes
-    uint32_t todo = hi_any & ~cont;  // non-ASCII lead bytes inside the chunk
-    int lead_in = (cont & 1u) ? 1 : 0;
-    if (lead_in) {
+    // a character that starts before the chunk but owns its first bytes
+    if (cont & 1u) {
       int back = 1;
       while (back < 3 && (at(base - back) & 0xC0u) == 0x80u) ++back;
       int len;
-      uint32_t cp = decode_at(at, base - back, n, &len);
-      uint32_t c = class_of(cls_tbl, cp);
+      const int64_t q = base - back;
+      uint32_t c = decode_class(at(q), at(q + 1), at(q + 2), at(q + 3), cls_tbl, &len);
       int cover = len - back;  // bytes of this char inside the chunk
       if (cover > 0) {
-        uint32_t bits = (cover >= 32) ? 0xFFFFFFFFu : ((1u << cover) - 1u);
+        uint32_t bits = (1u << cover) - 1u;
         if (c == CLS_L) m.L |= bits; else if (c == CLS_N) m.N |= bits; else if (c == CLS_S) m.S |= bits;
       }
     }
+    uint32_t todo = hi_any & ~cont;  // non-ASCII lead bytes inside the chunk
     while (todo) {
       int p = ctz32(todo);
       todo &= todo - 1u;
       int len;
-      uint32_t cp = decode_at(at, base + p, n, &len);
-      uint32_t c = class_of(cls_tbl, cp);
-      uint32_t bits = ((len >= 32 ? 0u : (1u << len)) - 1u) << p;  // bits past 31 fall off: next chunk redoes them
+      const int64_t q = base + p;
+      uint32_t c = decode_class(at(q), at(q + 1), at(q + 2), at(q + 3), cls_tbl, &len);
+      uint32_t bits = ((1u << len) - 1u) << p;  // bits past 31 fall off: the next chunk redoes them
       if (c == CLS_L) m.L |= bits; else if (c == CLS_N) m.N |= bits; else if (c == CLS_S) m.S |= bits;
     }
   }
