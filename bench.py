@@ -99,36 +99,62 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference(cfg, data, off, budget_s=15.0):
-    """The reference's own Rust/rayon encode_batch (tokenizers wheel) on all host cores over a bounded sample."""
-    cores = len(os.sched_getaffinity(0))
-    os.environ.setdefault("TOKENIZERS_PARALLELISM", "true")
-    os.environ.setdefault("RAYON_NUM_THREADS", str(cores))
+def cpu_reference_worker(cfg, threads, budget_s):
+    """Runs in a fresh process (rayon's pool size is fixed at first use): the reference's own Rust encode_batch
+    (tokenizers wheel, bindings/python/src/tokenizer.rs:1312-1340) over a bounded sample of the bench corpus."""
+    os.environ["TOKENIZERS_PARALLELISM"] = "true"
+    os.environ["RAYON_NUM_THREADS"] = str(threads)
     import tokenizers
     tok = tokenizers.Tokenizer.from_str(tokenizer_json(cfg))
-    raw = data.tobytes() if len(data) < (1 << 28) else data[: 1 << 28].tobytes()
-    n_avail = int(np.searchsorted(off, len(raw), side="right")) - 1
+    cap = 96 << 20
+    buf = np.empty(cap + (1 << 20), dtype=np.uint8)
+    n, off = gen_corpus(KIND[cfg], SEED[cfg], 0, cap // 300, cap, buf)
+    raw = buf[:n].tobytes()
+    n_avail = len(off) - 1
 
-    def docs(n):
-        return [raw[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(n)]
+    def docs(k):
+        return [raw[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(k)]
     probe_n = min(n_avail, 16384)
     d = docs(probe_n)
-    tok.encode_batch(d[:2048], add_special_tokens=False)  # warm-up (rayon pool, caches)
-    t0 = time.perf_counter(); enc = tok.encode_batch(d, add_special_tokens=False); t1 = time.perf_counter()
+    tok.encode_batch(d[:2048], add_special_tokens=False)  # warm-up (rayon pool)
+    t0 = time.perf_counter(); tok.encode_batch(d, add_special_tokens=False); t1 = time.perf_counter()
     rate = int(off[probe_n]) / (t1 - t0)
-    n = int(min(n_avail, max(probe_n, np.searchsorted(off, rate * budget_s))))
-    d = docs(n)
+    k = int(min(n_avail, max(probe_n, np.searchsorted(off, rate * budget_s))))
+    d = docs(k)
     best = None
     for _ in range(2):
         t0 = time.perf_counter(); enc = tok.encode_batch(d, add_special_tokens=False); dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    nbytes = int(off[n]); ntok = sum(len(e.ids) for e in enc)
-    return {"value": nbytes / best / 1e9, "unit": "GB/s", "tokens_per_s": ntok / best, "cores": cores, "kind": "reference",
-            "sample": f"tokenizers wheel {tokenizers.__version__} Tokenizer.encode_batch (char offsets) on the first {n} docs / {nbytes / 1e6:.1f} MB of the same corpus, best of 2",
+    nbytes = int(off[k]); ntok = sum(len(e.ids) for e in enc)
+    return {"value": nbytes / best / 1e9, "unit": "GB/s", "tokens_per_s": ntok / best, "cores": threads, "kind": "reference",
+            "sample": f"tokenizers wheel {tokenizers.__version__} Tokenizer.encode_batch (char offsets), RAYON_NUM_THREADS={threads}, "
+                      f"first {k} docs / {nbytes / 1e6:.1f} MB of the bench corpus, best of 2",
             "seconds": best}
 
 
+def cpu_reference(cfg, budget_s=12.0):
+    """Best of a small thread sweep (all visible cores, 32, 8), each in its own process."""
+    cores = len(os.sched_getaffinity(0))
+    tried = []
+    for th in sorted({cores, min(cores, 32), min(cores, 8)}, reverse=True):
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-worker", cfg, str(th), str(budget_s)],
+                                 capture_output=True, text=True, timeout=600)
+            r = json.loads(out.stdout.strip().splitlines()[-1])
+            tried.append(r)
+        except Exception as ex:
+            tried.append({"value": 0.0, "cores": th, "error": str(ex)[:200]})
+    best = max(tried, key=lambda r: r.get("value") or 0.0)
+    best = dict(best)
+    best["host_cores"] = cores
+    best["sweep"] = {str(r["cores"]): round(r.get("value") or 0.0, 5) for r in tried}
+    return best
+
+
 def main():
+    if len(sys.argv) >= 5 and sys.argv[1] == "--cpu-worker":
+        print(json.dumps(cpu_reference_worker(sys.argv[2], int(sys.argv[3]), float(sys.argv[4]))))
+        return
     # Only the JSON line may reach stdout (NCCL and others print there): park the real stdout, send fd 1 to stderr.
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
@@ -153,18 +179,16 @@ def main():
         # the reference's CPU implementation, all host threads, bounded sample per step; rank 0 only
         if rank != 0:
             return
-        buf = np.empty(min(max_bytes, 256 << 20) + (1 << 20), dtype=np.uint8)
-        n, off = gen_corpus(KIND[cfg], SEED[cfg], 0, min(n_docs_target, (256 << 20) // 300), min(max_bytes, 256 << 20), buf)
         per_step = []
-        for s in range(a.warmup + a.steps):
-            r = cpu_reference(cfg, buf[:n], off, budget_s=max(2.0, 60.0 / (a.warmup + a.steps)))
-            if s >= a.warmup:
+        for s_i in range(a.warmup + a.steps):
+            r = cpu_reference(cfg, budget_s=max(2.0, 45.0 / (3 * (a.warmup + a.steps))))
+            if s_i >= a.warmup:
                 per_step.append(r)
         r = max(per_step, key=lambda x: x["value"])
         out = {"impl": "reference", "metric": "encode_batch input throughput", "value": r["value"], "unit": "GB/s", "tokens_per_s": r["tokens_per_s"],
                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": workload, "bytes_per_step": None, "sample": r["sample"]},
-               "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+               "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores", "sweep")},
                "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         real_stdout.write(json.dumps(out) + "\n"); real_stdout.flush()
         return
@@ -291,7 +315,9 @@ def main():
     roof = {"kernel": "pretok_scan_kernel", "bound": "hbm", "achieved": k1_bytes / (k1 * 1e-3) / 1e9, "peak": peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback (of fallback)",
             "unit": "GB/s", "frac": k1_bytes / (k1 * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1,
-            "input_GBps": n / (k1 * 1e-3) / 1e9}
+            "input_GBps": n / (k1 * 1e-3) / 1e9,
+            "note": "achieved uses THIS kernel's layout (bytes + doc bitmap in, split bitmap + page summaries out = 1.25 B per input byte); "
+                    "with SURVEY.md 8(d)'s u32-start-list accounting (N + 4*N_pretok ~ 1.75 B/B) the same time would read frac x 1.4"}
     out = {"metric": "encode_batch input throughput", "value": tot_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
            "tokens_per_s": tot_tok / (ms_per_step * 1e-3), "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -304,7 +330,7 @@ def main():
            "gpu_launches": int(launches), "clocks": clocks}
     if not a.no_cpu and world == 1:
         try:
-            out["cpu_baseline"] = {k: v for k, v in cpu_reference(cfg, hbuf[:n], off).items() if k != "seconds"}
+            out["cpu_baseline"] = {k: v for k, v in cpu_reference(cfg).items() if k != "seconds"}
         except Exception as ex:  # the wheel is part of the image; if it is missing say so instead of inventing a number
             out["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": len(os.sched_getaffinity(0)), "kind": "reference", "sample": f"unavailable: {ex}"}
     real_stdout.write(json.dumps(out) + "\n"); real_stdout.flush()
