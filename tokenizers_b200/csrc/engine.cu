@@ -19,6 +19,7 @@
 #include "host_tables.h"
 #include "long_kernels.cuh"
 #include "model_kernels.cuh"
+#include "prefix_kernels.cuh"
 #include "pretok_kernels.cuh"
 
 using namespace b2t;
@@ -87,6 +88,8 @@ struct Workspace {
   DevBuf page_long, long_desc, lp_id, lp_val, lp_len, lp_plen, lp_aux, lp_out;  // long BPE pre-tokens (long_kernels.cuh)
   unsigned long long pool_cap = 0;
   DevBuf wcache;                      // per-batch word cache (model_kernels.cuh)
+  DevBuf pfx_bytes, pfx_doc_off, pfx_local, pfx_block, prefix_bits, pfx_total;  // add_prefix_space re-pack (prefix_kernels.cuh)
+  int64_t n_eff = 0;                  // bytes of the batch the kernels actually ran on (n + inserted spaces)
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   PinBuf h_ctl;                        // total tokens + error flag read back
@@ -94,6 +97,7 @@ struct Workspace {
     bytes.release(); doc_off.release(); doc_bits.release(); start_bits.release(); drop_bits.release(); page_sum.release();
     page_carry.release(); block_sum.release(); block_carry.release(); page_first_doc.release(); tile_state.release(); ctl.release(); ids.release(); offsets.release();
     word_ids.release(); row_ptr.release(); h_ctl.release();
+    pfx_bytes.release(); pfx_doc_off.release(); pfx_local.release(); pfx_block.release(); prefix_bits.release(); pfx_total.release();
     wcache.release(); page_long.release(); long_desc.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -158,7 +162,6 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
     return fail(B2T_ERR_UNSUPPORTED, "WordPiece is supported behind the Whitespace pre-tokenizer only");
   if (cfg->add_prefix_space && cfg->pretok != B2T_PRETOK_BYTELEVEL && cfg->pretok != B2T_PRETOK_BYTELEVEL_NOREGEX)
     return fail(B2T_ERR_UNSUPPORTED, "add_prefix_space is only meaningful for a top-level ByteLevel pre-tokenizer");
-  if (cfg->add_prefix_space) return fail(B2T_ERR_UNSUPPORTED, "ByteLevel add_prefix_space=true is not on the device path yet");
   if (!cfg->vocab_bytes || !cfg->vocab_off || !cfg->vocab_ids || cfg->n_vocab == 0) return fail(B2T_ERR_INVALID, "empty vocabulary");
 
   HostTables ht;
@@ -268,9 +271,31 @@ static void rec(b2t_engine* e, cudaStream_t st, const char* name) {
 // Runs K0..K2 for a batch resident on the device.  Does not synchronise.  model_pass=false stops after K1b.
 static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_bytes, int64_t n, const uint64_t* d_doc_off,
                                uint32_t n_docs, uint32_t flags, cudaStream_t st, bool model_pass) {
-  if (n >= (1ll << 31)) return fail(B2T_ERR_TOO_LARGE, "batch of %lld bytes exceeds the per-call limit of 2^31-1; split it", (long long)n);
-  const int64_t n_words = n / 32 + 2, n_pages = n / PAGE + 1;
+  if (n + (int64_t)n_docs >= (1ll << 31)) return fail(B2T_ERR_TOO_LARGE, "batch of %lld bytes exceeds the per-call limit of 2^31-1; split it", (long long)n);
   int rc;
+  const uint32_t* d_prefix_bits = nullptr;
+  if (e->add_prefix_space && n_docs > 0 && n > 0) {
+    // re-pack the batch with the prefix spaces inserted (byte_level.rs:121-125); costs one small host sync for the new size
+    const int64_t cap = n + n_docs + 64;
+    const uint32_t nb = (n_docs + PFX_BLOCK - 1) / PFX_BLOCK;
+    if ((rc = ws.pfx_bytes.ensure(cap)) || (rc = ws.pfx_doc_off.ensure(((size_t)n_docs + 1) * 8)) || (rc = ws.pfx_local.ensure((size_t)n_docs * 4)) ||
+        (rc = ws.pfx_block.ensure((size_t)nb * 4 + 16)) || (rc = ws.prefix_bits.ensure((cap / 32 + 2) * 4)) || (rc = ws.pfx_total.ensure(16)) ||
+        (rc = ws.h_ctl.ensure(sizeof(ctl_block), false)))
+      return rc;
+    CU(cudaMemsetAsync(ws.prefix_bits.p, 0, (cap / 32 + 2) * 4, st));
+    pfx_scan_block_kernel<<<nb, PFX_BLOCK, 0, st>>>(d_bytes, d_doc_off, n_docs, ws.pfx_local.as<uint32_t>(), ws.pfx_block.as<uint32_t>());
+    pfx_scan_top_kernel<<<1, PFX_BLOCK, 0, st>>>(ws.pfx_block.as<uint32_t>(), nb, ws.pfx_total.as<unsigned long long>());
+    pfx_offsets_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_bytes, d_doc_off, n_docs, ws.pfx_local.as<uint32_t>(), ws.pfx_block.as<uint32_t>(),
+                                                                ws.pfx_total.as<unsigned long long>(), ws.pfx_doc_off.as<uint64_t>(), ws.prefix_bits.as<uint32_t>());
+    pfx_copy_kernel<<<(unsigned)(((int64_t)n_docs * 32 + 255) / 256), 256, 0, st>>>(d_bytes, d_doc_off, ws.pfx_doc_off.as<uint64_t>(), n_docs, ws.pfx_bytes.as<uint8_t>());
+    unsigned long long added = 0;
+    CU(cudaMemcpyAsync(&added, ws.pfx_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    d_bytes = ws.pfx_bytes.as<uint8_t>(); d_doc_off = ws.pfx_doc_off.as<uint64_t>(); n += (int64_t)added;
+    d_prefix_bits = ws.prefix_bits.as<uint32_t>();
+  }
+  ws.n_eff = n;
+  const int64_t n_words = n / 32 + 2, n_pages = n / PAGE + 1;
   if ((rc = ws.doc_bits.ensure(n_words * 4)) || (rc = ws.start_bits.ensure(n_words * 4)) || (rc = ws.page_sum.ensure(n_pages * 8)) ||
       (rc = ws.page_carry.ensure(n_pages * 8)) || (rc = ws.block_sum.ensure((n_pages / SCAN_BLOCK + 2) * 8)) ||
       (rc = ws.block_carry.ensure((n_pages / SCAN_BLOCK + 2) * 8)) || (rc = ws.page_first_doc.ensure(n_pages * 4)) || (rc = ws.tile_state.ensure(n_pages * 8)) ||
@@ -337,6 +362,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     P.n_tiles = n_pages;
     P.page_long = ws.page_long.as<int32_t>(); P.long_desc = ws.long_desc.as<LongDesc>(); P.long_out = ws.lp_out.as<uint4>();
     P.wcache = ws.wcache.as<uint4>(); P.wcache_mask = WCACHE_SLOTS - 1;
+    P.prefix_bits = d_prefix_bits;
     P.t = e->dt;
     if (e->model == B2T_MODEL_BPE) model_tile_kernel<MODEL_BPE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
     else model_tile_kernel<MODEL_WORDPIECE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
@@ -577,7 +603,8 @@ extern "C" int b2t_pre_tokenize_batch(b2t_engine* e, const uint8_t* bytes, const
   if (n) CU(cudaMemcpyAsync(ws.bytes.p, bytes, n, cudaMemcpyHostToDevice, ws.stream));
   CU(cudaMemcpyAsync(ws.doc_off.p, doc_off, ((size_t)n_docs + 1) * 8, cudaMemcpyHostToDevice, ws.stream));
   if ((rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)n, ws.doc_off.as<uint64_t>(), n_docs, 0, ws.stream, false))) return rc;
-  const size_t n_words = n / 32 + 2;
+  const uint64_t n_eff = (uint64_t)ws.n_eff;
+  const size_t n_words = n_eff / 32 + 2;
   std::vector<uint32_t> sb(n_words), db(n_words, 0u);
   CU(cudaMemcpyAsync(sb.data(), ws.start_bits.p, n_words * 4, cudaMemcpyDeviceToHost, ws.stream));
   if (e->pretok == PT_WHITESPACE) CU(cudaMemcpyAsync(db.data(), ws.drop_bits.p, n_words * 4, cudaMemcpyDeviceToHost, ws.stream));
@@ -586,21 +613,31 @@ extern "C" int b2t_pre_tokenize_batch(b2t_engine* e, const uint8_t* bytes, const
   r->eng = e; r->on_device = 0; r->n_docs = n_docs;
   auto bit = [](const std::vector<uint32_t>& v, uint64_t p) { return (v[p >> 5] >> (p & 31)) & 1u; };
   uint64_t count = 0;
-  for (uint64_t p = 0; p < n; ++p) count += bit(sb, p) && !bit(db, p);
+  for (uint64_t p = 0; p < n_eff; ++p) count += bit(sb, p) && !bit(db, p);
   if ((rc = r->h_offsets.ensure((count + 1) * 8, false)) || (rc = r->h_row_ptr.ensure(((size_t)n_docs + 1) * 8, false))) { e->pool.push_back(r); return rc; }
   uint32_t* off = r->h_offsets.as<uint32_t>();
   uint64_t* rp = r->h_row_ptr.as<uint64_t>();
-  uint64_t k = 0;
+  uint64_t k = 0, shift = 0;
   for (uint32_t d = 0; d < n_docs; ++d) {
     rp[d] = k;
-    uint64_t p = doc_off[d];
-    const uint64_t end = doc_off[d + 1];
+    const uint64_t len = doc_off[d + 1] - doc_off[d];
+    const bool pre = e->add_prefix_space && len > 0 && bytes[doc_off[d]] != ' ';
+    const uint64_t dstart = doc_off[d] + shift;          // start of the document in the (re-packed) device batch
+    const uint64_t end = dstart + len + (pre ? 1 : 0);
+    uint64_t first_len = 1;                               // bytes of the first original character
+    if (pre) { while (first_len < len && (bytes[doc_off[d] + first_len] & 0xC0) == 0x80) ++first_len; }
+    uint64_t p = dstart;
     while (p < end) {
       uint64_t q = p + 1;
       while (q < end && !bit(sb, q)) ++q;
-      if (!bit(db, p)) { off[2 * k] = (uint32_t)(p - doc_off[d]); off[2 * k + 1] = (uint32_t)(q - doc_off[d]); ++k; }
+      if (!bit(db, p)) {
+        uint64_t a = p - dstart, b = q - dstart;
+        if (pre) { b = (b == 1) ? first_len : b - 1; a = a ? a - 1 : 0; }  // the inserted space is aligned to the first character
+        off[2 * k] = (uint32_t)a; off[2 * k + 1] = (uint32_t)b; ++k;
+      }
       p = q;
     }
+    if (pre) ++shift;
   }
   rp[n_docs] = k;
   r->n_tokens = k; r->ids = nullptr; r->word_ids = nullptr; r->offsets = off; r->row_ptr = rp;

@@ -44,6 +44,8 @@ struct ModelParams {
   const int32_t* page_long; const LongDesc* long_desc; const uint4* long_out;
   // per-batch word cache (cleared at the start of every batch): pre-token bytes -> its token list
   uint4* wcache; uint32_t wcache_mask;
+  // ByteLevel add_prefix_space: bit p set <=> byte p of the (re-packed) batch is an inserted prefix space (else NULL)
+  const uint32_t* prefix_bits;
   DeviceTables t;
 };
 
@@ -680,6 +682,19 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
         o0 = (uint32_t)(gs - ds); o1 = (uint32_t)(ge - ds);
       }
       (void)end_known;
+      if (P.prefix_bits) {  // offsets were computed on the document WITH its inserted space: map back (normalizer.rs:503-514)
+        const int64_t dsa = D >= 0 ? base + D : s_span_doc_start;
+        if ((__ldg(P.prefix_bits + (dsa >> 5)) >> (dsa & 31)) & 1u) {
+          if (o1 == 1u && byte_off) {  // the token is the inserted space alone: it is aligned to the whole first character
+            int64_t ge2 = dsa + 2;
+            while (ge2 < n && (__ldg(P.bytes + ge2) & 0xC0u) == 0x80u) ++ge2;
+            o1 = (uint32_t)(ge2 - dsa);
+          }
+          o0 = o0 ? o0 - 1u : 0u;
+          o1 = o1 > 2u ? o1 - 1u : 1u;
+          if (byte_off && o1 < 1u) o1 = 1u;
+        }
+      }
       reinterpret_cast<uint2*>(P.offsets)[out] = make_uint2(o0, o1);
     }
     if (want_wid) {
@@ -721,6 +736,15 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
             while (gs > 0 && (__ldg(P.bytes + gs) & 0xC0u) == 0x80u) --gs;
             while (ge < n && (__ldg(P.bytes + ge) & 0xC0u) == 0x80u) ++ge;
             o0 = (uint32_t)(gs - ds); o1 = (uint32_t)(ge - ds);
+          }
+          if (P.prefix_bits && ((__ldg(P.prefix_bits + (ds >> 5)) >> (ds & 31)) & 1u)) {
+            if (o1 == 1u && byte_off) {
+              int64_t ge2 = ds + 2;
+              while (ge2 < n && (__ldg(P.bytes + ge2) & 0xC0u) == 0x80u) ++ge2;
+              o1 = (uint32_t)(ge2 - ds);
+            }
+            o0 = o0 ? o0 - 1u : 0u;
+            o1 = o1 > 2u ? o1 - 1u : 1u;
           }
           reinterpret_cast<uint2*>(P.offsets)[obase + k] = make_uint2(o0, o1);
         }
