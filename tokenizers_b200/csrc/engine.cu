@@ -85,6 +85,7 @@ struct Workspace {
   DevBuf bytes, doc_off;              // only used by the host path (inputs staged on the device)
   DevBuf doc_bits, start_bits, drop_bits, page_sum, page_carry, block_sum, block_carry, page_first_doc, tile_state, ctl;
   DevBuf ids, offsets, word_ids, row_ptr;
+  DevBuf tmp_ids, tmp_offsets, tmp_word_ids, tile_count, tile_first, tile_lexcl, tile_bsum;  // pass-1 provisional slots + scan
   DevBuf page_long, long_desc, lp_id, lp_val, lp_len, lp_plen, lp_aux, lp_out;  // long BPE pre-tokens (long_kernels.cuh)
   unsigned long long pool_cap = 0;
   DevBuf wcache;                      // per-batch word cache (model_kernels.cuh)
@@ -97,6 +98,7 @@ struct Workspace {
     bytes.release(); doc_off.release(); doc_bits.release(); start_bits.release(); drop_bits.release(); page_sum.release();
     page_carry.release(); block_sum.release(); block_carry.release(); page_first_doc.release(); tile_state.release(); ctl.release(); ids.release(); offsets.release();
     word_ids.release(); row_ptr.release(); h_ctl.release();
+    tmp_ids.release(); tmp_offsets.release(); tmp_word_ids.release(); tile_count.release(); tile_first.release(); tile_lexcl.release(); tile_bsum.release();
     pfx_bytes.release(); pfx_doc_off.release(); pfx_local.release(); pfx_block.release(); prefix_bits.release(); pfx_total.release();
     wcache.release(); page_long.release(); long_desc.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
     if (stream) cudaStreamDestroy(stream);
@@ -298,7 +300,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   const int64_t n_words = n / 32 + 2, n_pages = n / PAGE + 1;
   if ((rc = ws.doc_bits.ensure(n_words * 4)) || (rc = ws.start_bits.ensure(n_words * 4)) || (rc = ws.page_sum.ensure(n_pages * 8)) ||
       (rc = ws.page_carry.ensure(n_pages * 8)) || (rc = ws.block_sum.ensure((n_pages / SCAN_BLOCK + 2) * 8)) ||
-      (rc = ws.block_carry.ensure((n_pages / SCAN_BLOCK + 2) * 8)) || (rc = ws.page_first_doc.ensure(n_pages * 4)) || (rc = ws.tile_state.ensure(n_pages * 8)) ||
+      (rc = ws.block_carry.ensure((n_pages / SCAN_BLOCK + 2) * 8)) || (rc = ws.page_first_doc.ensure(n_pages * 4)) ||
       (rc = ws.ctl.ensure(sizeof(ctl_block))) || (rc = ws.h_ctl.ensure(sizeof(ctl_block), false)))
     return rc;
   if (e->pretok == PT_WHITESPACE && (rc = ws.drop_bits.ensure(n_words * 4))) return rc;
@@ -311,12 +313,14 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
       return rc;
   }
   if (model_pass) {
-    if ((rc = ws.ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.row_ptr.ensure(((size_t)n_docs + 1) * 8))) return rc;
-    if ((flags & B2T_WANT_OFFSETS) && (rc = ws.offsets.ensure((size_t)(n + 1) * 8))) return rc;
-    if ((flags & B2T_WANT_WORD_IDS) && (rc = ws.word_ids.ensure((size_t)(n + 1) * 4))) return rc;
+    if ((rc = ws.ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.tmp_ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.row_ptr.ensure(((size_t)n_docs + 1) * 8)) ||
+        (rc = ws.tile_count.ensure(n_pages * 4)) || (rc = ws.tile_first.ensure(n_pages * 4)) || (rc = ws.tile_lexcl.ensure(n_pages * 8)) ||
+        (rc = ws.tile_bsum.ensure((n_pages / TSCAN + 2) * 8)))
+      return rc;
+    if ((flags & B2T_WANT_OFFSETS) && ((rc = ws.offsets.ensure((size_t)(n + 1) * 8)) || (rc = ws.tmp_offsets.ensure((size_t)(n + 1) * 8)))) return rc;
+    if ((flags & B2T_WANT_WORD_IDS) && ((rc = ws.word_ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.tmp_word_ids.ensure((size_t)(n + 1) * 4)))) return rc;
   }
   CU(cudaMemsetAsync(ws.doc_bits.p, 0, n_words * 4, st));
-  CU(cudaMemsetAsync(ws.tile_state.p, 0, n_pages * 8, st));
   CU(cudaMemsetAsync(ws.ctl.p, 0, sizeof(ctl_block), st));
   if (model_pass && bpe) CU(cudaMemsetAsync(ws.wcache.p, 0, (size_t)WCACHE_SLOTS * 64, st));
   e->last_launches = 0;
@@ -354,11 +358,11 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     P.doc_off = d_doc_off; P.n_docs = n_docs;
     P.flags = ((flags & B2T_WANT_OFFSETS) ? F_OFFSETS : 0u) | ((flags & B2T_WANT_WORD_IDS) ? F_WORD_IDS : 0u) |
               ((flags & B2T_OFFSETS_BYTES) ? F_BYTE_OFFSETS : 0u);
-    P.ids = ws.ids.as<uint32_t>(); P.offsets = ws.offsets.as<uint32_t>(); P.word_ids = ws.word_ids.as<uint32_t>();
+    P.ids = ws.tmp_ids.as<uint32_t>(); P.offsets = ws.tmp_offsets.as<uint32_t>(); P.word_ids = ws.tmp_word_ids.as<uint32_t>();
     P.row_ptr = ws.row_ptr.as<uint64_t>();
-    P.tile_state = ws.tile_state.as<unsigned long long>();
+    P.tile_count = ws.tile_count.as<uint32_t>(); P.tile_first = ws.tile_first.as<uint32_t>();
     ctl_block* ctl = ws.ctl.as<ctl_block>();
-    P.ticket = &ctl->ticket; P.err_flag = &ctl->err; P.total_out = &ctl->total;
+    P.err_flag = &ctl->err;
     P.n_tiles = n_pages;
     P.page_long = ws.page_long.as<int32_t>(); P.long_desc = ws.long_desc.as<LongDesc>(); P.long_out = ws.lp_out.as<uint4>();
     P.wcache = ws.wcache.as<uint4>(); P.wcache_mask = WCACHE_SLOTS - 1;
@@ -367,6 +371,19 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     if (e->model == B2T_MODEL_BPE) model_tile_kernel<MODEL_BPE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
     else model_tile_kernel<MODEL_WORDPIECE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
     rec(e, st, e->model == B2T_MODEL_BPE ? "bpe_tile" : "wordpiece_tile"); e->last_launches++;
+    // pass 2: page token counts -> exclusive scan -> compaction of the provisional slots into the final CSR
+    const int64_t n_tblk = (n_pages + TSCAN - 1) / TSCAN;
+    tile_scan_block_kernel<<<(unsigned)n_tblk, TSCAN, 0, st>>>(ws.tile_count.as<uint32_t>(), ws.tile_lexcl.as<unsigned long long>(),
+                                                             ws.tile_bsum.as<unsigned long long>(), n_pages);
+    tile_scan_top_kernel<<<1, TSCAN, 0, st>>>(ws.tile_bsum.as<unsigned long long>(), n_tblk, &ctl->total);
+    compact_kernel<<<(unsigned)((n_pages * 32 + 255) / 256), 256, 0, st>>>(
+        ws.tile_count.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.tile_lexcl.as<unsigned long long>(), ws.tile_bsum.as<unsigned long long>(), n_pages,
+        ws.tmp_ids.as<uint32_t>(), (flags & B2T_WANT_OFFSETS) ? ws.tmp_offsets.as<uint2>() : nullptr,
+        (flags & B2T_WANT_WORD_IDS) ? ws.tmp_word_ids.as<uint32_t>() : nullptr, ws.ids.as<uint32_t>(),
+        (flags & B2T_WANT_OFFSETS) ? ws.offsets.as<uint2>() : nullptr, (flags & B2T_WANT_WORD_IDS) ? ws.word_ids.as<uint32_t>() : nullptr);
+    row_ptr_fix_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.tile_lexcl.as<unsigned long long>(),
+                                                               ws.tile_bsum.as<unsigned long long>(), ws.row_ptr.as<uint64_t>());
+    rec(e, st, "scan_compact"); e->last_launches += 4;
     CU(cudaMemcpyAsync(ws.h_ctl.p, ws.ctl.p, sizeof(ctl_block), cudaMemcpyDeviceToHost, st));
   }
   CU(cudaGetLastError());

@@ -38,7 +38,10 @@ struct ModelParams {
   const uint64_t* doc_off; uint32_t n_docs;
   uint32_t flags;
   uint32_t* ids; uint32_t* offsets; uint32_t* word_ids; uint64_t* row_ptr;
-  unsigned long long* tile_state; uint32_t* ticket; unsigned long long* total_out; uint32_t* err_flag;
+  // pass 1 writes the tokens of page t at the provisional slots [tile_first[t], tile_first[t] + tile_count[t]) of ids / offsets /
+  // word_ids (first pre-token start of the page: a page never has more tokens than bytes up to the next page's first start),
+  // row_ptr holds page-local token counts; tile_scan + compact_kernel + row_ptr_fix_kernel then produce the final CSR.
+  uint32_t* tile_count; uint32_t* tile_first; uint32_t* err_flag;
   int64_t n_tiles;
   // long BPE pre-tokens resolved by the pre-pass (long_kernels.cuh)
   const int32_t* page_long; const LongDesc* long_desc; const uint4* long_out;
@@ -277,9 +280,6 @@ __device__ __forceinline__ void coop_bpe(const DeviceTables& t, const uint8_t* s
   }
 }
 
-#define B2T_ST_AGG (1ull << 62)
-#define B2T_ST_INCL (2ull << 62)
-#define B2T_ST_VAL ((1ull << 62) - 1ull)
 
 template <int MODEL>
 __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelParams P) {
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARPS = MODEL_THREADS / 32;
   if (tid == 0) {
-    s_tile = (int)atomicAdd(P.ticket, 1u);
+    s_tile = (int)blockIdx.x;
     s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0;
   }
   __syncthreads();
@@ -606,43 +606,20 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
     if (lane == 0) s_ntok = tot;
   }
   __syncthreads();
-  if (warp != 0) {
-    // compact list of token positions (while warp 0 walks the look-back chain)
-    for (int row = warp - 1; row < NW; row += NWARPS - 1) {
+  {
+    // compact list of token positions
+    for (int row = warp; row < NW; row += NWARPS) {
       const uint32_t tb = s_tokb[row];
       if ((tb >> lane) & 1u) s_tokpos[s_tpref[row] + __popc(tb & ((1u << lane) - 1u))] = (uint16_t)(row * 32 + lane);
     }
-  } else {
-    const int tot = s_ntok;
-    const int A = tot + ((MODEL == MODEL_WORDPIECE && long_kept) ? 1 : 0) + (MODEL == MODEL_BPE ? s_lcum[n_longs] : 0);
-    // ---------------------------------------------------------------- P6: decoupled look-back over the pages
-    unsigned long long excl = 0;
-    volatile unsigned long long* st = P.tile_state;
-    if (t == 0) {
-      if (lane == 0) st[0] = B2T_ST_INCL | (unsigned long long)A;
-    } else {
-      if (lane == 0) st[t] = B2T_ST_AGG | (unsigned long long)A;
-      int64_t look = t - 1;
-      while (true) {
-        int64_t idx = look - lane;
-        unsigned long long v = idx >= 0 ? st[idx] : B2T_ST_INCL;
-        unsigned fl = (unsigned)(v >> 62);
-        unsigned pend = __ballot_sync(0xFFFFFFFFu, fl == 0u);
-        unsigned incl = __ballot_sync(0xFFFFFFFFu, fl == 2u);
-        unsigned need = incl ? ((1u << (__ffs((int)incl) - 1)) - 1u) | (1u << (__ffs((int)incl) - 1)) : 0xFFFFFFFFu;
-        if (pend & need) { __nanosleep(40); continue; }  // a needed predecessor has not published yet
-        unsigned long long c = ((1u << lane) & need) ? (v & B2T_ST_VAL) : 0ull;
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, s);
-        excl += c;
-        if (incl) break;
-        look -= 32;
-      }
-      if (lane == 0) st[t] = B2T_ST_INCL | (excl + (unsigned long long)A);
-    }
-    if (lane == 0) {
-      s_excl = excl; s_ntot = A;
-      if (t == P.n_tiles - 1) *P.total_out = excl + (unsigned long long)A;
+    // ---------------------------------------------------------------- P6: page token count (no ordering between pages:
+    // an in-order look-back chain stalled every page behind the slowest of ~1000 pages in flight -- profiles/)
+    if (tid == 0) {
+      const int A = s_ntok + ((MODEL == MODEL_WORDPIECE && long_kept) ? 1 : 0) + (MODEL == MODEL_BPE ? s_lcum[n_longs] : 0);
+      s_ntot = A;
+      s_excl = (unsigned long long)(base + first);  // provisional slot of the page's first token
+      P.tile_count[t] = (uint32_t)A;
+      P.tile_first[t] = (uint32_t)(base + first);
     }
   }
   __syncthreads();
@@ -768,9 +745,92 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_tile_kernel(const ModelPa
       if (pos >= TILE) break;
       // tokens that start before `pos` (a doc start is a pre-token start, so no token straddles it)
       const int before = pos == 0 ? 0 : (int)s_tpref[(pos - 1) >> 5] + __popc(s_tokb[(pos - 1) >> 5] & mask_le((int)((pos - 1) & 31)));
-      P.row_ptr[d] = excl + (unsigned long long)(before + long_tokens_before((int)pos));
+      P.row_ptr[d] = (unsigned long long)(before + long_tokens_before((int)pos));  // page-local; row_ptr_fix_kernel adds the page's base
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------ pass 2
+// Exclusive scan of the page token counts (two levels of 1024), then compaction of the provisional slots.
+constexpr int TSCAN = 1024;
+
+__global__ void __launch_bounds__(TSCAN) tile_scan_block_kernel(const uint32_t* __restrict__ cnt, unsigned long long* __restrict__ local_excl,
+                                                                unsigned long long* __restrict__ block_sum, int64_t n_tiles) {
+  __shared__ unsigned long long s_w[32];
+  const int64_t i = (int64_t)blockIdx.x * TSCAN + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long v = i < n_tiles ? (unsigned long long)cnt[i] : 0ull;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) { unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, s); if (lane >= s) inc += o; }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = s_w[lane], wi = w;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, wi, s); if (lane >= s) wi += o; }
+    s_w[lane] = wi - w;
+    if (lane == 31) block_sum[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  if (i < n_tiles) local_excl[i] = s_w[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(TSCAN) tile_scan_top_kernel(unsigned long long* __restrict__ block_sum, int64_t n_blocks, unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long s_w[32];
+  __shared__ unsigned long long s_run;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t b0 = 0; b0 < n_blocks; b0 += TSCAN) {
+    const int64_t i = b0 + threadIdx.x;
+    const unsigned long long v = i < n_blocks ? block_sum[i] : 0ull;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, s); if (lane >= s) inc += o; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = s_w[lane], wi = w;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) { unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, wi, s); if (lane >= s) wi += o; }
+      s_w[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned long long run = s_run;
+    if (i < n_blocks) block_sum[i] = run + s_w[warp] + inc - v;  // exclusive, in place
+    __syncthreads();
+    if (threadIdx.x == TSCAN - 1) s_run = run + s_w[warp] + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_run;
+}
+
+// one warp per page: provisional slots -> final CSR positions
+__global__ void compact_kernel(const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_first,
+                               const unsigned long long* __restrict__ local_excl, const unsigned long long* __restrict__ block_excl, int64_t n_tiles,
+                               const uint32_t* __restrict__ t_ids, const uint2* __restrict__ t_off, const uint32_t* __restrict__ t_wid,
+                               uint32_t* __restrict__ ids, uint2* __restrict__ off, uint32_t* __restrict__ wid) {
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= n_tiles) return;
+  const uint32_t cnt = tile_count[t];
+  if (!cnt) return;
+  const unsigned long long src = tile_first[t], dst = local_excl[t] + block_excl[t / TSCAN];
+  for (uint32_t j = lane; j < cnt; j += 32) {
+    ids[dst + j] = t_ids[src + j];
+    if (off) off[dst + j] = t_off[src + j];
+    if (wid) wid[dst + j] = t_wid[src + j];
+  }
+}
+
+__global__ void row_ptr_fix_kernel(const uint64_t* __restrict__ doc_off, uint32_t n_docs, const unsigned long long* __restrict__ local_excl,
+                                   const unsigned long long* __restrict__ block_excl, uint64_t* __restrict__ row_ptr) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d > n_docs) return;
+  const int64_t t = (int64_t)(doc_off[d] / TILE);
+  row_ptr[d] += local_excl[t] + block_excl[t / TSCAN];
 }
 
 }  // namespace b2t
