@@ -306,8 +306,8 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   if (e->pretok == PT_WHITESPACE && (rc = ws.drop_bits.ensure(n_words * 4))) return rc;
   const bool bpe = e->model == B2T_MODEL_BPE;
   constexpr uint32_t WCACHE_SLOTS = 1u << 19;  // x 64 B = 32 MiB, L2 resident
+  if (model_pass && (rc = ws.wcache.ensure((size_t)WCACHE_SLOTS * 64))) return rc;
   if (model_pass && bpe) {
-    if ((rc = ws.wcache.ensure((size_t)WCACHE_SLOTS * 64))) return rc;
     if ((rc = ws.page_long.ensure(n_pages * 4)) || (rc = ws.long_desc.ensure((size_t)(n / (LONG_PRETOK_MIN + 1) + 2) * sizeof(LongDesc))) ||
         (rc = ensure_long_pool(ws, 1u << 20)))
       return rc;
@@ -322,7 +322,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   }
   CU(cudaMemsetAsync(ws.doc_bits.p, 0, n_words * 4, st));
   CU(cudaMemsetAsync(ws.ctl.p, 0, sizeof(ctl_block), st));
-  if (model_pass && bpe) CU(cudaMemsetAsync(ws.wcache.p, 0, (size_t)WCACHE_SLOTS * 64, st));
+  if (model_pass) CU(cudaMemsetAsync(ws.wcache.p, 0, (size_t)WCACHE_SLOTS * 64, st));
   e->last_launches = 0;
   rec(e, st, nullptr);
   doc_mark_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.doc_bits.as<uint32_t>(), ws.page_first_doc.as<uint32_t>());

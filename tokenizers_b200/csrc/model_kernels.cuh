@@ -626,12 +626,36 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
       }
     }
   } else {
-    // -------------------------------------------------------------- WordPiece: one thread per kept split
+    // -------------------------------------------------------------- WordPiece P3: word cache, one split per thread
+    for (int k0 = 0; k0 < Pproc; k0 += MODEL_THREADS) {
+      const int k = k0 + tid;
+      bool miss = false;
+      if (k < Pproc) {
+        const int s = s_pt[k], e = s_pt[k + 1], len = e - s;
+        if ((s_keptb[s >> 5] >> (s & 31)) & 1u) {  // not removed whitespace
+          bool hit = false;
+          if (len <= WC_MAX_BYTES) {
+            WordKey key;
+            wc_make_key(s_byte, s, len, key);
+            hit = wc_lookup(P.wcache, P.wcache_mask, key, s, s_id, s_len);
+          }
+          miss = !hit;
+        }
+      }
+      const unsigned mm = __ballot_sync(0xFFFFFFFFu, miss);
+      int bm = 0;
+      if (lane == 0 && mm) bm = atomicAdd(&s_nmiss, __popc(mm));
+      bm = __shfl_sync(0xFFFFFFFFu, bm, 0);
+      if (miss) s_miss[bm + __popc(mm & ((1u << lane) - 1u))] = (uint16_t)k;
+    }
+    __syncthreads();
+    // -------------------------------------------------------------- WordPiece P4: misses, one thread per split
+    const int nmiss = s_nmiss;
     while (true) {
-      int k = atomicAdd(&s_next, 1);
-      if (k >= Pproc) break;
+      const int mi = atomicAdd(&s_next, 1);
+      if (mi >= nmiss) break;
+      const int k = s_miss[mi];
       const int s = s_pt[k], e = s_pt[k + 1], len = e - s;
-      if (!((s_keptb[s >> 5] >> (s & 31)) & 1u)) continue;  // removed whitespace
       // chars = lead bytes in [s, e)
       int chars = (int)s_lpref[(e - 1) >> 5] + __popc(s_leadb[(e - 1) >> 5] & mask_le((e - 1) & 31)) -
                   ((int)s_lpref[s >> 5] + __popc(s_leadb[s >> 5] & (mask_le(s & 31) >> 1)));
@@ -662,6 +686,11 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
       if (bad) {
         for (int p = s; p < e; ++p) s_len[p] = 0;
         s_id[s] = P.t.unk_id; s_len[s] = (uint16_t)len;
+      }
+      if (len <= WC_MAX_BYTES) {
+        WordKey key;
+        wc_make_key(s_byte, s, len, key);
+        wc_publish(P.wcache, P.wcache_mask, key, s, e, s_id, s_len);
       }
     }
     // a LONG split (> 416 bytes) has more than max_input_chars_per_word (<= 100 * 4 bytes) characters: it is [UNK];

@@ -93,8 +93,11 @@ __device__ __forceinline__ uint64_t pack_sum(uint32_t tot, uint32_t aft, uint32_
 //       no lane diverges on "my chunk has 10 Cyrillic letters and yours has none"
 //   B   per lane: windows from the neighbours' masks, boundary algebra (pretok_logic.cuh), 4-byte store of the bitmap
 //       word, page summaries by warp reductions
+#ifndef B2T_K1_MINBLOCKS
+#define B2T_K1_MINBLOCKS 4
+#endif
 template <int KIND, int TC>
-__global__ void __launch_bounds__(TC) pretok_scan_kernel(const uint8_t* __restrict__ bytes, int64_t n,
+__global__ void __launch_bounds__(TC, B2T_K1_MINBLOCKS) pretok_scan_kernel(const uint8_t* __restrict__ bytes, int64_t n,
                                                          const uint32_t* __restrict__ doc_bits,
                                                          const uint32_t* __restrict__ cls_tbl,
                                                          uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
