@@ -166,10 +166,12 @@ def main():
     ap.add_argument("--mb", type=int, default=1024, help="corpus size per GPU in MiB")
     ap.add_argument("--config", default="gpt2", choices=list(ASSET))
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kind", type=int, default=0, help="corpus kind override (5 = length-skew stress of BASELINE configs[4])")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = a.config
+    workload_kind = {5: " [length-skew corpus: Zipf doc lengths 8 B-64 KB, 0.1 % docs hold a 4-64 KB letter/space run]"}.get(a.kind, "")
     workload = {"gpt2": "GPT-2 ByteLevel BPE (50257 vocab trained offline by the reference trainer), synthetic UTF-8 docs avg ~480 B",
                 "llama3": "Llama-3-style BPE (tiktoken regex, 128k vocab, ignore_merges)", "wordpiece": "Whitespace + WordPiece 30522"}[cfg]
     max_bytes = a.mb << 20
@@ -207,7 +209,10 @@ def main():
     hptr = ctypes.c_void_p()
     _lib.check(L.b2t_host_alloc(max_bytes + (1 << 20), ctypes.byref(hptr)))
     hbuf = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint8)), shape=(max_bytes + (1 << 20),))
-    n, off = gen_corpus(KIND[cfg], SEED[cfg], rank * n_docs_target, n_docs_target, max_bytes, hbuf)
+    kind = a.kind or KIND[cfg]
+    if kind == 5:
+        n_docs_target = max_bytes // 200
+    n, off = gen_corpus(kind, 5 if kind == 5 else SEED[cfg], rank * n_docs_target, n_docs_target, max_bytes, hbuf)
     n_docs = len(off) - 1
     hoff_ptr = ctypes.c_void_p()
     _lib.check(L.b2t_host_alloc((n_docs + 1) * 8, ctypes.byref(hoff_ptr)))
@@ -312,16 +317,23 @@ def main():
     peak = peaks.get("hbm_gbs", 6650.0)
     k1 = float(np.mean(kern_ms.get("pretok_scan", [float("nan")])))
     k1_bytes = n * 1.25 + (n / 2048) * 8  # bytes + doc_bits in, start_bits + page summaries out
+    traffic = None
+    try:  # dram bytes of one launch from the committed ncu --set full capture (profiles/), scaled by input size
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        if tj.get("config") == cfg:
+            traffic = tj["dram_bytes_per_input_byte"] * n
+    except Exception:
+        pass
     roof = {"kernel": "pretok_scan_kernel", "bound": "hbm", "achieved": k1_bytes / (k1 * 1e-3) / 1e9, "peak": peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback (of fallback)",
-            "unit": "GB/s", "frac": k1_bytes / (k1 * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1,
+            "unit": "GB/s", "frac": k1_bytes / (k1 * 1e-3) / 1e9 / peak, "traffic": traffic, "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1,
             "input_GBps": n / (k1 * 1e-3) / 1e9,
             "note": "achieved uses THIS kernel's layout (bytes + doc bitmap in, split bitmap + page summaries out = 1.25 B per input byte); "
                     "with SURVEY.md 8(d)'s u32-start-list accounting (N + 4*N_pretok ~ 1.75 B/B) the same time would read frac x 1.4"}
     out = {"metric": "encode_batch input throughput", "value": tot_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
            "tokens_per_s": tot_tok / (ms_per_step * 1e-3), "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": workload + f", {n / 1e6:.0f} MB / {n_docs} docs per GPU, ids + char offsets", "bytes_per_gpu": n, "docs_per_gpu": n_docs,
+           "config": {"workload": workload + workload_kind + f", {n / 1e6:.0f} MB / {n_docs} docs per GPU, ids + char offsets", "bytes_per_gpu": n, "docs_per_gpu": n_docs,
                       "tokens_per_gpu": int(T), "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"docs sharded over {world} rank(s)" + (", NCCL all-gather-v of ids/offsets per step" if world > 1 else "")},
            "kernels_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()},
            "roofline": roof,
