@@ -232,11 +232,11 @@ def main():
 
     gathered = {}
 
-    def step_device():
+    def step_device(gather=False):
         res = ctypes.c_void_p()
         _lib.check(L.b2t_encode_batch_device(tok.handle, d_bytes.data_ptr(), n, d_off.data_ptr(), n_docs, flags, ctypes.c_void_p(stream.cuda_stream), ctypes.byref(res)))
         T = L.b2t_result_n_tokens(res)
-        if world > 1:  # one all-gather-v of the token CSR over NCCL (tokenizers_b200/parallel.py)
+        if gather:  # one all-gather-v of the token CSR over NCCL (tokenizers_b200/parallel.py)
             ids = torch.as_tensor(DevArr(L.b2t_result_ids(res), T, "<i4"), device="cuda")
             offs = torch.as_tensor(DevArr(L.b2t_result_offsets(res), 2 * T, "<i4"), device="cuda")
             rp = torch.as_tensor(DevArr(L.b2t_result_row_ptr(res), n_docs + 1, "<i8"), device="cuda")
@@ -273,6 +273,22 @@ def main():
         dist.barrier()
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    gather_ms = None
+    if world > 1:
+        # the same steps followed by the all-gather-v of ids / offsets / row_ptr that BASELINE.json's north_star names.
+        # Reported separately (key "allgather"): the path itself has no exchange step -- every rank's slice of the CSR
+        # is complete on its own -- and a replicate-everything collective necessarily grows with N.
+        for _ in range(2):
+            step_device(True)
+        torch.cuda.synchronize(); dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(a.steps):
+            step_device(True)
+        g1.record(stream)
+        torch.cuda.synchronize(); dist.barrier()
+        gather_ms = g0.elapsed_time(g1)
+        gathered.clear()
 
     # ---- end to end through the C ABI with pinned host buffers (H2D + kernels + D2H inside the call)
     _lib.check(L.b2t_engine_set_profiling(tok.handle, 0))
@@ -297,11 +313,11 @@ def main():
 
     # ---- reduce over ranks: time = max, work = sum
     if world > 1:
-        v = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        v = torch.tensor([dev_ms, e2e_s * 1e3, gather_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         w = torch.tensor([float(n), float(T)], dtype=torch.float64, device="cuda")
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_ms = v.tolist(); tot_bytes, tot_tok = w.tolist()
+        dev_ms, e2e_ms, gather_ms = v.tolist(); tot_bytes, tot_tok = w.tolist()
     else:
         e2e_ms, tot_bytes, tot_tok = e2e_s * 1e3, float(n), float(T)
     if rank != 0:
@@ -334,12 +350,16 @@ def main():
            "tokens_per_s": tot_tok / (ms_per_step * 1e-3), "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
            "config": {"workload": workload + workload_kind + f", {n / 1e6:.0f} MB / {n_docs} docs per GPU, ids + char offsets", "bytes_per_gpu": n, "docs_per_gpu": n_docs,
-                      "tokens_per_gpu": int(T), "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"docs sharded over {world} rank(s)" + (", NCCL all-gather-v of ids/offsets per step" if world > 1 else "")},
+                      "tokens_per_gpu": int(T), "l2": "inputs larger than L2 (no flush needed)",
+                      "parallelism": f"docs sharded over {world} rank(s), no data-path collective" + (" (all-gather-v variant under 'allgather')" if world > 1 else "")},
            "kernels_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()},
            "roofline": roof,
            "e2e": {"value": tot_bytes / (e2e_ms / a.steps * 1e-3) / 1e9, "unit": "GB/s", "tokens_per_s": tot_tok / (e2e_ms / a.steps * 1e-3), "ms_per_step": e2e_ms / a.steps,
                    "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(T * 12 + (n_docs + 1) * 8 + 16 * ((n >> 26) + 1))},
            "gpu_launches": int(launches), "clocks": clocks}
+    if gather_ms is not None:
+        out["allgather"] = {"what": "same steps + NCCL all-gather-v of ids/offsets/row_ptr to every rank (tokenizers_b200/parallel.py)",
+                            "ms_per_step": gather_ms / a.steps, "value": tot_bytes / (gather_ms / a.steps * 1e-3) / 1e9, "unit": "GB/s"}
     if not a.no_cpu and world == 1:
         try:
             out["cpu_baseline"] = {k: v for k, v in cpu_reference(cfg).items() if k != "seconds"}

@@ -205,57 +205,6 @@ __device__ __forceinline__ bool vocab_whole_word(const DeviceTables& t, const ui
   }
 }
 
-// ------------------------------------------------------------------------------------------------ lane-per-pre-token merge
-// Pre-tokens of up to 8 bytes that missed the word cache (mostly numbers: never seen twice): ONE lane each, symbols in
-// registers, all lanes of the warp stepping through the rounds together.  Arrays are indexed with compile-time
-// constants only (the "dynamic" position is applied through predicated moves), so nothing spills to local memory.
-__device__ __forceinline__ void lane_bpe8(const DeviceTables& t, const uint8_t* s_byte, uint32_t* s_id, uint16_t* s_len, int s, int n,
-                                          bool active) {
-  uint32_t id[8], rk[8], ni[8], ln[8];
-  int m = active ? n : 0;  // live symbols
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { id[i] = (i < m) ? __ldg(t.byte_to_id + s_byte[s + i]) : 0u; ln[i] = 1u; rk[i] = 0xFFFFFFFFu; ni[i] = 0u; }
-#pragma unroll
-  for (int i = 0; i < 7; ++i)
-    if (i + 1 < m) { const uint64_t v = merge_lookup(t, id[i], id[i + 1]); rk[i] = (uint32_t)(v >> 32); ni[i] = (uint32_t)v; }
-  while (true) {
-    uint32_t br = 0xFFFFFFFFu; int bi = 0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) if (rk[i] < br) { br = rk[i]; bi = i; }
-    const bool have = br != 0xFFFFFFFFu;
-    if (!__any_sync(0xFFFFFFFFu, have)) break;
-    if (have) {
-      uint32_t nid = 0, lnext = 0;
-#pragma unroll
-      for (int i = 0; i < 7; ++i) if (i == bi) { nid = ni[i]; lnext = ln[i + 1]; }
-      // merge the pair at bi, close the gap
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i == bi) { id[i] = nid; ln[i] += lnext; }
-        else if (i > bi) {
-          if (i < 7) { id[i] = id[i + 1]; ln[i] = ln[i + 1]; rk[i] = rk[i + 1]; ni[i] = ni[i + 1]; }
-          else { rk[i] = 0xFFFFFFFFu; }
-        }
-      }
-      --m;
-      uint32_t left = 0, right = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { if (i + 1 == bi) left = id[i]; if (i == bi + 1) right = id[i]; }
-      uint32_t r0 = 0xFFFFFFFFu, n0 = 0, r1 = 0xFFFFFFFFu, n1 = 0;
-      if (bi > 0) { const uint64_t v = merge_lookup(t, left, nid); r0 = (uint32_t)(v >> 32); n0 = (uint32_t)v; }
-      if (bi + 1 < m) { const uint64_t v = merge_lookup(t, nid, right); r1 = (uint32_t)(v >> 32); n1 = (uint32_t)v; }
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        if (i + 1 == bi) { rk[i] = r0; ni[i] = n0; }
-        if (i == bi) { rk[i] = r1; ni[i] = n1; }
-      }
-    }
-  }
-  int pos = s;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) if (i < m) { s_id[pos] = id[i]; s_len[pos] = (uint16_t)ln[i]; pos += (int)ln[i]; }
-}
-
 // ------------------------------------------------------------------------------------------------ cooperative merge
 // G lanes resolve one pre-token [s, e) of up to G * J bytes: lane g owns the positions s + g + G * j (j < J) and
 // keeps the rank / new id of the pair that starts at each of them in registers.  Every round the group agrees on
@@ -336,7 +285,7 @@ __device__ __forceinline__ void coop_bpe(const DeviceTables& t, const uint8_t* s
 #define B2T_MINBLOCKS 8  // measured on B200: 8 blocks/SM (32 regs, small spills) beats 5 (48 regs) by 15 %: the kernel is latency-bound
 #endif
 #ifndef B2T_LANE8_MAX
-#define B2T_LANE8_MAX 0  // lane-per-pre-token path: measured slower than the 8-lane groups (serialises the misses of a page in one warp)
+#define B2T_LANE8_MAX 0  // a separate queue for <= 8-byte misses (one symbol per lane) was measured SLOWER: the page then pays two dependent merge phases; kept for experiments
 #endif
 template <int MODEL>
 __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kernel(const ModelParams P) {
@@ -564,21 +513,25 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
       if (kind == 2) s_mq[bq + __popc(mq & ((1u << lane) - 1u))] = (uint16_t)k;
     }
     __syncthreads();
-    // -------------------------------------------------------------- P4a0: short misses (<= 8 bytes), one lane each
+    // -------------------------------------------------------------- P4a0: short misses (<= 8 bytes): 8 lanes, one symbol per lane
     {
       const int n8 = s_nmiss8;
-      for (int m0 = warp * 32; m0 < n8; m0 += MODEL_THREADS) {
-        const int mi = m0 + lane;
+      const int grp = tid >> 3, gl = tid & 7;
+      for (int m0 = 0; m0 < n8; m0 += MODEL_THREADS / 8) {
+        const int mi = m0 + grp;
         const bool active0 = mi < n8;
         const int k = active0 ? s_miss[mi] : 0;
         const int s = active0 ? s_pt[k] : 0, e = active0 ? s_pt[k + 1] : 0;
         bool active = active0;
-        if (P.t.ignore_merges && active0) {
-          const bool whole = vocab_whole_word(P.t, s_byte, s, e - s, s_id);
-          if (whole) { s_len[s] = (uint16_t)(e - s); active = false; }
+        if (P.t.ignore_merges) {
+          int whole = 0;
+          if (active0 && gl == 0) { whole = vocab_whole_word(P.t, s_byte, s, e - s, s_id) ? 1 : 0; if (whole) s_len[s] = (uint16_t)(e - s); }
+          whole = __shfl_sync(0xFFFFFFFFu, whole, lane & ~7);
+          active = active0 && !whole;
         }
-        lane_bpe8(P.t, s_byte, s_id, s_len, s, e - s, active);
-        if (active0) {
+        coop_bpe<8, 1>(P.t, s_byte, s_id, s_len, s, e, active, gl);
+        __syncwarp();
+        if (active0 && gl == 0) {
           WordKey key;
           wc_make_key(s_byte, s, e - s, key);
           wc_publish(P.wcache, P.wcache_mask, key, s, e, s_id, s_len);
