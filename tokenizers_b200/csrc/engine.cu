@@ -247,9 +247,12 @@ static int ensure_long_pool(Workspace& ws, unsigned long long bytes) {
   return B2T_OK;
 }
 
+#ifndef B2T_K1_TC
+#define B2T_K1_TC 256
+#endif
 template <int KIND>
 static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Workspace& ws, cudaStream_t st) {
-  constexpr int TC = 256;
+  constexpr int TC = B2T_K1_TC;
   const int64_t n_chunks = n / CHUNK + 1;
   const int64_t n_tiles = (n_chunks + TC - 1) / TC;
   // contiguous tile ranges per block (the kernel pipelines consecutive tiles); ~8 blocks per SM
@@ -257,7 +260,7 @@ static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Work
   int64_t grid = (n_tiles + tiles_per_block - 1) / tiles_per_block;
   pretok_scan_kernel<KIND, TC><<<(unsigned)grid, TC, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
                                                              ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
-                                                             ws.page_sum.as<uint64_t>(), n_tiles, tiles_per_block);
+                                                             ws.page_sum.as<uint64_t>(), n_tiles, tiles_per_block, 1u);
 }
 
 static void rec(b2t_engine* e, cudaStream_t st, const char* name) {

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(TC, B2T_K1_MINBLOCKS) pretok_scan_kernel(const
                                                          const uint32_t* __restrict__ doc_bits,
                                                          const uint32_t* __restrict__ cls_tbl,
                                                          uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
-                                                         uint64_t* __restrict__ page_sum, int64_t n_tiles, int64_t tiles_per_block) {
+                                                         uint64_t* __restrict__ page_sum, int64_t n_tiles, int64_t tiles_per_block, uint32_t one) {
   constexpr int NWARPS = TC / 32;
   __shared__ ChunkMasks sm[2][TC];
   __shared__ ChunkMasks sm_prev;                 // last chunk of the tile before the one in phase B
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(TC, B2T_K1_MINBLOCKS) pretok_scan_kernel(const
     if (base < n) {
       uint32_t w[8];
       load_chunk_words(bytes, base, n, w);
-      ascii_masks(KIND, w, m, &hi, &cont);
+      ascii_masks(KIND, w, m, &hi, &cont, one);
       if (base + CHUNK > n) {
         const uint32_t valid = 0xFFFFFFFFu >> (32 - (int)(n - base));
         m.lead &= valid; hi &= valid; cont &= valid;
@@ -156,22 +156,29 @@ __global__ void __launch_bounds__(TC, B2T_K1_MINBLOCKS) pretok_scan_kernel(const
         if (cover > 0 && cl != CLS_O) atomicOr(reinterpret_cast<uint32_t*>(&sm[buf][0]) + cl, (1u << cover) - 1u);
       }
       __syncwarp();
-      const int64_t wbase = (tile * TC + warp * 32) * CHUNK;
+      const uint32_t wbase = (uint32_t)((tile * TC + warp * 32) * CHUNK);   // batches are < 2^31 bytes
+      const uint32_t* __restrict__ words = reinterpret_cast<const uint32_t*>(bytes);
+      uint32_t* smw = reinterpret_cast<uint32_t*>(&sm[buf][warp * 32]);
+      constexpr int STRIDE = sizeof(ChunkMasks) / 4;
       for (int i = lane; i < total; i += 32) {
-        const int idx = s_list[warp][i];
-        const int64_t gp = wbase + idx;
-        const uint32_t* aw = reinterpret_cast<const uint32_t*>(bytes + (gp & ~(int64_t)3));
-        const uint32_t a0 = __ldg(aw), a1 = ((gp & ~(int64_t)3) + 4 < n) ? __ldg(aw + 1) : 0u;
-        const uint32_t v = __funnelshift_r(a0, a1, (uint32_t)(gp & 3) * 8u);
-        int len;
-        const uint32_t cl = decode_class(v & 0xFFu, (v >> 8) & 0xFFu, (v >> 16) & 0xFFu, v >> 24, cls_tbl, &len);
+        const uint32_t idx = s_list[warp][i];
+        const uint32_t gp = wbase + idx;
+        const uint32_t a0 = __ldg(words + (gp >> 2)), a1 = ((gp | 3u) + 1u < (uint32_t)n) ? __ldg(words + (gp >> 2) + 1) : 0u;
+        const uint32_t v = __funnelshift_r(a0, a1, (gp & 3u) * 8u);
+        const uint32_t b0 = v & 0xFFu;
+        const int len = 2 + (b0 >= 0xE0u) + (b0 >= 0xF0u);
+        const uint32_t cp2 = ((v & 0x1Fu) << 6) | ((v >> 8) & 0x3Fu);
+        const uint32_t cp3 = ((v & 0x0Fu) << 12) | ((v >> 2) & 0xFC0u) | ((v >> 16) & 0x3Fu);
+        const uint32_t cp4 = ((v & 0x07u) << 18) | ((v << 4) & 0x3F000u) | ((v >> 10) & 0xFC0u) | (v >> 24 & 0x3Fu);
+        uint32_t cp = len == 2 ? cp2 : (len == 3 ? cp3 : cp4);
+        cp = cp < 0x110000u ? cp : 0x10FFFFu;
+        const uint32_t cl = (__ldg(cls_tbl + (cp >> 4)) >> ((cp & 15u) * 2u)) & 3u;
         if (cl != CLS_O) {
-          const int owner = idx >> 5, p = idx & 31;
-          const uint64_t bits = ((1ull << len) - 1ull) << p;
-          atomicOr(reinterpret_cast<uint32_t*>(&sm[buf][warp * 32 + owner]) + cl, (uint32_t)bits);
-          const uint32_t hi32 = (uint32_t)(bits >> 32);
-          if (hi32) {
-            if (owner < 31) atomicOr(reinterpret_cast<uint32_t*>(&sm[buf][warp * 32 + owner + 1]) + cl, hi32);
+          const uint32_t owner = idx >> 5, p = idx & 31u, m = (1u << len) - 1u;
+          atomicOr(smw + owner * STRIDE + cl, m << p);
+          if (p + (uint32_t)len > 32u) {
+            const uint32_t hi32 = m >> (32u - p);
+            if (owner < 31u) atomicOr(smw + (owner + 1u) * STRIDE + cl, hi32);
             else if (warp + 1 < NWARPS) atomicOr(&s_spill[buf][warp + 1][cl], hi32);
           }
         }
