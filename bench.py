@@ -133,10 +133,10 @@ def cpu_reference_worker(cfg, threads, budget_s):
 
 
 def cpu_reference(cfg, budget_s=12.0):
-    """Best of a small thread sweep (all visible cores, 32, 8), each in its own process."""
+    """Best of a small thread sweep (all visible cores, 32, 16, 8, 4), each in its own process."""
     cores = len(os.sched_getaffinity(0))
     tried = []
-    for th in sorted({cores, min(cores, 32), min(cores, 8)}, reverse=True):
+    for th in sorted({cores, min(cores, 32), min(cores, 16), min(cores, 8), min(cores, 4)}, reverse=True):
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-worker", cfg, str(th), str(budget_s)],
                                  capture_output=True, text=True, timeout=600)
