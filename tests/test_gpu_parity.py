@@ -198,3 +198,49 @@ def test_full_size_properties():
         t0, t1 = int(rp[a]), int(rp[a + 2000])
         got = (be.ids[t0:t1], be.offsets[t0:t1], be.word_ids[t0:t1], rp[a:a + 2001] - rp[a])
         helpers.assert_csr_equal(got, exp, None, f"slice at doc {a}")
+
+
+def test_concurrent_callers_share_one_engine():
+    """encode_batch is callable from many host threads (the reference: &self + Send/Sync, mod.rs:1328-1335)."""
+    import threading
+    tok, o, _ = engine("gpt2_style")
+    batches = [fuzzgen.rand_docs(900 + i, 600, max_len=80) for i in range(6)]
+    exp = [o.encode_batch(b) for b in batches]
+    out, errs = [None] * 6, []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                out[i] = gpu_csr(tok, batches[i])
+        except Exception as ex:  # pragma: no cover
+            errs.append(ex)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errs, errs
+    for i in range(6):
+        helpers.assert_csr_equal(out[i], exp[i], batches[i], f"thread {i}")
+
+
+def test_document_larger_than_a_chunk_and_many_empty_docs():
+    _, o, js = engine("gpt2_style")
+    os.environ["B2T_CHUNK_BYTES"] = str(1 << 20)
+    try:
+        tok = Tokenizer.from_str(js)
+    finally:
+        del os.environ["B2T_CHUNK_BYTES"]
+    data, off = corpus.generate(2, 77, 0, 9000)
+    big = data.tobytes()[: 3 << 20].decode("utf-8", "ignore")
+    docs = [""] * 3000 + [big] + ["tail doc"] + [""] * 5000 + ["x"]
+    helpers.assert_csr_equal(gpu_csr(tok, docs), o.encode_batch(docs), None, "big doc + empties")
+
+
+def test_invalid_utf8_does_not_fault():
+    """The ABI takes bytes; Rust's &str can never be invalid UTF-8, so the result is unspecified -- but it must not crash,
+    hang, or write out of bounds (row_ptr stays a valid CSR over ids)."""
+    tok, _, _ = engine("gpt2_style")
+    rng = np.random.default_rng(7)
+    data = rng.integers(0, 256, size=200000, dtype=np.uint8)
+    off = np.arange(0, 200001, 1000, dtype=np.uint64)
+    be = tok.encode_batch_csr(data, off)
+    assert be.row_ptr[0] == 0 and int(be.row_ptr[-1]) == len(be.ids) and np.all(np.diff(be.row_ptr.astype(np.int64)) >= 0)
+    assert be.ids.max() < tok.get_vocab_size()
