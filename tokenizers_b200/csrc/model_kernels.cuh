@@ -9,12 +9,14 @@
 // Work decomposition: the block owns the pre-tokens that START inside its page (they may run into the halo).
 //   * every symbol lives at its byte position in shared memory (id, length, rank of the pair it forms with its right
 //     neighbour), so symbols never move: a merge extends the left symbol and zeroes the length of the right one;
-//   * short pre-tokens (<= 32 bytes) are merged by one thread each (dynamic queue, "leftmost pair of minimal rank"
-//     per round == the reference's heap order (rank, pos) with its stale-entry check);
-//   * longer ones are merged by one warp each (lanes stride over the positions, __reduce_min_sync picks the pair);
-//   * surviving symbol starts are exactly the token starts: a ballot per 32 positions gives the token bitmap, a
-//     decoupled look-back over the pages gives the global token index, and ids / offsets / word ids are written in
-//     order straight into the CSR.
+//   * every pre-token of up to 24 bytes is first looked up in a per-batch word cache shared by all blocks (the
+//     reference caches words too: models/bpe/model.rs:24-90); a hit is a full key compare, so results cannot change;
+//   * misses of up to 32 bytes are merged by 8-lane groups, longer ones (up to 256) by a whole warp, pair ranks held in
+//     registers: every round the group agrees by shuffles on the leftmost pair of minimal rank (== the reference's
+//     heap order (rank, pos) with its stale-entry check) and publishes the result to the cache;
+//   * surviving symbol starts are exactly the token starts: a ballot per 32 positions gives the token bitmap, ids /
+//     offsets / word ids are written at provisional slots (page's first start + j) and a scan + compaction pass moves
+//     them to their final CSR position -- pages never wait for each other.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -284,9 +286,6 @@ __device__ __forceinline__ void coop_bpe(const DeviceTables& t, const uint8_t* s
 #ifndef B2T_MINBLOCKS
 #define B2T_MINBLOCKS 8  // measured on B200: 8 blocks/SM (32 regs, small spills) beats 5 (48 regs) by 15 %: the kernel is latency-bound
 #endif
-#ifndef B2T_LANE8_MAX
-#define B2T_LANE8_MAX 0  // a separate queue for <= 8-byte misses (one symbol per lane) was measured SLOWER: the page then pays two dependent merge phases; kept for experiments
-#endif
 template <int MODEL>
 __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kernel(const ModelParams P) {
   constexpr int HALO = MODEL == MODEL_BPE ? 256 : 416;
@@ -305,7 +304,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   __shared__ uint16_t s_list[SPAN];  // P3/P4: pre-tokens the word cache did not resolve; P7: positions of the tokens
   uint16_t* const s_miss = s_list;
   uint16_t* const s_tokpos = s_list;
-  __shared__ int s_nmiss, s_nmiss8;
+  __shared__ int s_nmiss;
   __shared__ int s_tile, s_next, s_nmq, s_P, s_Elast, s_long, s_ntok, s_ntot;
   __shared__ unsigned long long s_excl;
   __shared__ long long s_long_end, s_span_doc_start;
@@ -319,7 +318,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   constexpr int NWARPS = MODEL_THREADS / 32;
   if (tid == 0) {
     s_tile = (int)blockIdx.x;
-    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0; s_nmiss8 = 0;
+    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0;
   }
   __syncthreads();
   const int64_t t = s_tile;
@@ -497,47 +496,15 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
           kind = hit ? 0 : 1;
         }
       }
-      // warp-aggregated queue appends (short misses fill s_miss from the front, 9..32-byte ones from the back)
-      const bool short8 = kind == 1 && (int)s_pt[k + 1] - (int)s_pt[k] <= B2T_LANE8_MAX;
-      const unsigned m8 = __ballot_sync(0xFFFFFFFFu, short8), mm = __ballot_sync(0xFFFFFFFFu, kind == 1 && !short8),
-                     mq = __ballot_sync(0xFFFFFFFFu, kind == 2);
-      int b8 = 0, bm = 0, bq = 0;
-      if (lane == 0) {
-        if (m8) b8 = atomicAdd(&s_nmiss8, __popc(m8));
-        if (mm) bm = atomicAdd(&s_nmiss, __popc(mm));
-        if (mq) bq = atomicAdd(&s_nmq, __popc(mq));
-      }
-      b8 = __shfl_sync(0xFFFFFFFFu, b8, 0); bm = __shfl_sync(0xFFFFFFFFu, bm, 0); bq = __shfl_sync(0xFFFFFFFFu, bq, 0);
-      if (short8) s_miss[b8 + __popc(m8 & ((1u << lane) - 1u))] = (uint16_t)k;
-      else if (kind == 1) s_miss[SPAN - 1 - (bm + __popc(mm & ((1u << lane) - 1u)))] = (uint16_t)k;
+      // warp-aggregated queue appends
+      const unsigned mm = __ballot_sync(0xFFFFFFFFu, kind == 1), mq = __ballot_sync(0xFFFFFFFFu, kind == 2);
+      int bm = 0, bq = 0;
+      if (lane == 0) { if (mm) bm = atomicAdd(&s_nmiss, __popc(mm)); if (mq) bq = atomicAdd(&s_nmq, __popc(mq)); }
+      bm = __shfl_sync(0xFFFFFFFFu, bm, 0); bq = __shfl_sync(0xFFFFFFFFu, bq, 0);
+      if (kind == 1) s_miss[bm + __popc(mm & ((1u << lane) - 1u))] = (uint16_t)k;
       if (kind == 2) s_mq[bq + __popc(mq & ((1u << lane) - 1u))] = (uint16_t)k;
     }
     __syncthreads();
-    // -------------------------------------------------------------- P4a0: short misses (<= 8 bytes): 8 lanes, one symbol per lane
-    {
-      const int n8 = s_nmiss8;
-      const int grp = tid >> 3, gl = tid & 7;
-      for (int m0 = 0; m0 < n8; m0 += MODEL_THREADS / 8) {
-        const int mi = m0 + grp;
-        const bool active0 = mi < n8;
-        const int k = active0 ? s_miss[mi] : 0;
-        const int s = active0 ? s_pt[k] : 0, e = active0 ? s_pt[k + 1] : 0;
-        bool active = active0;
-        if (P.t.ignore_merges) {
-          int whole = 0;
-          if (active0 && gl == 0) { whole = vocab_whole_word(P.t, s_byte, s, e - s, s_id) ? 1 : 0; if (whole) s_len[s] = (uint16_t)(e - s); }
-          whole = __shfl_sync(0xFFFFFFFFu, whole, lane & ~7);
-          active = active0 && !whole;
-        }
-        coop_bpe<8, 1>(P.t, s_byte, s_id, s_len, s, e, active, gl);
-        __syncwarp();
-        if (active0 && gl == 0) {
-          WordKey key;
-          wc_make_key(s_byte, s, e - s, key);
-          wc_publish(P.wcache, P.wcache_mask, key, s, e, s_id, s_len);
-        }
-      }
-    }
     // -------------------------------------------------------------- P4a: misses, 8 lanes per pre-token (<= 32 bytes)
     {
       const int nmiss = s_nmiss;
@@ -545,7 +512,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
       for (int m0 = 0; m0 < nmiss; m0 += MODEL_THREADS / 8) {
         const int mi = m0 + grp;
         const bool active0 = mi < nmiss;
-        const int k = active0 ? s_miss[SPAN - 1 - mi] : 0;
+        const int k = active0 ? s_miss[mi] : 0;
         const int s = active0 ? s_pt[k] : 0, e = active0 ? s_pt[k + 1] : 0;
         bool active = active0;
         if (P.t.ignore_merges) {  // models/bpe/model.rs:558-567: the whole pre-token is a vocabulary entry -> one token
@@ -556,7 +523,9 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
         }
         coop_bpe<8, 4>(P.t, s_byte, s_id, s_len, s, e, active, gl);
         __syncwarp();
-        if (active0 && gl == 0 && e - s <= WC_MAX_BYTES) {
+        // long numbers rarely repeat: publishing them only fills the table (measured: -5 % kernel time without them)
+        const bool numeric = active0 && (e - s) >= 5 && (unsigned)(s_byte[s + 1] - '0') < 10u && (unsigned)(s_byte[e - 1] - '0') < 10u;
+        if (active0 && gl == 0 && e - s <= WC_MAX_BYTES && !numeric) {
           WordKey key;
           wc_make_key(s_byte, s, e - s, key);
           wc_publish(P.wcache, P.wcache_mask, key, s, e, s_id, s_len);
