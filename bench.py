@@ -64,7 +64,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -245,14 +245,14 @@ def main():
         return T
 
     names = (ctypes.c_char_p * 16)(); ms = (ctypes.c_float * 16)()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # samples every 50 ms from the warm-up through the timed device and e2e regions
     for _ in range(a.warmup):
         T = step_device()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     kern_ms = {}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -272,7 +272,6 @@ def main():
     if world > 1:
         dist.barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     gather_ms = None
     if world > 1:
         # the same steps followed by the all-gather-v of ids / offsets / row_ptr that BASELINE.json's north_star names.
@@ -310,6 +309,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert Te == T
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- reduce over ranks: time = max, work = sum
     if world > 1:
