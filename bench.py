@@ -317,9 +317,14 @@ def main():
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         w = torch.tensor([float(n), float(T)], dtype=torch.float64, device="cuda")
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        mine = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        allr = torch.empty(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank_ms = [round(x / a.steps, 3) for x in allr.tolist()]
         dev_ms, e2e_ms, gather_ms = v.tolist(); tot_bytes, tot_tok = w.tolist()
     else:
         e2e_ms, tot_bytes, tot_tok = e2e_s * 1e3, float(n), float(T)
+        per_rank_ms = [round(dev_ms / a.steps, 3)]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -352,7 +357,7 @@ def main():
            "config": {"workload": workload + workload_kind + f", {n / 1e6:.0f} MB / {n_docs} docs per GPU, ids + char offsets", "bytes_per_gpu": n, "docs_per_gpu": n_docs,
                       "tokens_per_gpu": int(T), "l2": "inputs larger than L2 (no flush needed)",
                       "parallelism": f"docs sharded over {world} rank(s), no data-path collective" + (" (all-gather-v variant under 'allgather')" if world > 1 else "")},
-           "kernels_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()},
+           "kernels_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()}, "per_rank_ms_per_step": per_rank_ms,
            "roofline": roof,
            "e2e": {"value": tot_bytes / (e2e_ms / a.steps * 1e-3) / 1e9, "unit": "GB/s", "tokens_per_s": tot_tok / (e2e_ms / a.steps * 1e-3), "ms_per_step": e2e_ms / a.steps,
                    "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(T * 12 + (n_docs + 1) * 8 + 16 * ((n >> 26) + 1))},
