@@ -1,6 +1,6 @@
 // long_kernels.cuh -- the path for BPE pre-tokens longer than LONG_PRETOK_MIN bytes (URLs, base64 blobs, 64 KB letter / space
 // runs of the length-skew stress config).  They do not fit the per-page shared-memory scheme of model_kernels.cuh and
-// must not stall the look-back chain, so they are resolved by a pre-pass:
+// would stall their page for milliseconds, so they are resolved by a pre-pass:
 //   K1c long_find : one warp per page finds the pre-tokens that start in the page and are longer than LONG_PRETOK_MIN, gives
 //                   them consecutive slots (page_long[page] = first slot) and a region of the long pool;
 //   K2L bpe_long  : one block per long pre-token runs the merge loop of models/bpe/word.rs:162-250 on arrays in global

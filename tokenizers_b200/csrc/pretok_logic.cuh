@@ -67,12 +67,6 @@ B2T_HD uint32_t class_of(const uint32_t* __restrict__ tbl, uint32_t cp) {
 }
 
 // ---------------------------------------------------------------------------------------------- phase A
-// per byte (ASCII only, bit 7 of each byte of w7 clear): bit 7 set iff lo <= b <= hi
-B2T_HD uint32_t swar_range(uint32_t w7, uint32_t lo, uint32_t hi) {
-  uint32_t ge = w7 + (0x80u - lo) * 0x01010101u;
-  uint32_t gt = w7 + (0x7Fu - hi) * 0x01010101u;
-  return ge & ~gt & 0x80808080u;
-}
 // two "bit 7 per byte" flag words -> one byte: low nibble = flags of a (byte 0 -> bit 0), high nibble = flags of b
 B2T_HD uint32_t movemask2(uint32_t a, uint32_t b) {
   uint32_t x = (a >> 7) | (b >> 3);
