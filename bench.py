@@ -59,12 +59,12 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu):
-        self.gpu, self.p, self.lines = gpu, None, []
+    def __init__(self, gpus):
+        self.gpus, self.p, self.lines = list(gpus), None, []
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", ",".join(map(str, self.gpus)), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -83,20 +83,22 @@ class ClockSampler:
             self.p.wait(timeout=2)
         except Exception:
             self.p.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons = {}, [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.setdefault(int(f[0]), []).append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        med = {g: float(np.median(v)) for g, v in sorted(sm.items())}
+        # sm_mhz: the slowest GPU's median under load (every rank's GPU is sampled, not only rank 0's)
+        return {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": min((len(v) for v in sm.values()), default=0), "per_gpu_sm_mhz": [med[g] for g in sorted(med)]}
 
 
 def cpu_reference_worker(cfg, threads, budget_s):
@@ -245,7 +247,7 @@ def main():
         return T
 
     names = (ctypes.c_char_p * 16)(); ms = (ctypes.c_float * 16)()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(range(world))  # one node: local ranks 0..world-1 are GPUs 0..world-1
     if rank == 0:
         sampler.start()  # samples every 50 ms from the warm-up through the timed device and e2e regions
     for _ in range(a.warmup):
@@ -317,14 +319,17 @@ def main():
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         w = torch.tensor([float(n), float(T)], dtype=torch.float64, device="cuda")
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        mine = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-        allr = torch.empty(world, dtype=torch.float64, device="cuda")
+        mine = torch.tensor([dev_ms / a.steps, sum(float(np.mean(v)) for v in kern_ms.values())], dtype=torch.float64, device="cuda")
+        allr = torch.empty(2 * world, dtype=torch.float64, device="cuda")
         dist.all_gather_into_tensor(allr, mine)
-        per_rank_ms = [round(x / a.steps, 3) for x in allr.tolist()]
+        allr = allr.reshape(world, 2).tolist()
+        per_rank_ms = [round(x[0], 3) for x in allr]
+        per_rank_kern = [round(x[1], 3) for x in allr]  # kernels only: the rest of a rank's step is host launch / sync gaps
         dev_ms, e2e_ms, gather_ms = v.tolist(); tot_bytes, tot_tok = w.tolist()
     else:
         e2e_ms, tot_bytes, tot_tok = e2e_s * 1e3, float(n), float(T)
         per_rank_ms = [round(dev_ms / a.steps, 3)]
+        per_rank_kern = [round(sum(float(np.mean(v)) for v in kern_ms.values()), 3)]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,6 +363,7 @@ def main():
                       "tokens_per_gpu": int(T), "l2": "inputs larger than L2 (no flush needed)",
                       "parallelism": f"docs sharded over {world} rank(s), no data-path collective" + (" (all-gather-v variant under 'allgather')" if world > 1 else "")},
            "kernels_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()}, "per_rank_ms_per_step": per_rank_ms,
+           "per_rank_kernel_ms_per_step": per_rank_kern,
            "roofline": roof,
            "e2e": {"value": tot_bytes / (e2e_ms / a.steps * 1e-3) / 1e9, "unit": "GB/s", "tokens_per_s": tot_tok / (e2e_ms / a.steps * 1e-3), "ms_per_step": e2e_ms / a.steps,
                    "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(T * 12 + (n_docs + 1) * 8 + 16 * ((n >> 26) + 1))},

@@ -167,10 +167,10 @@ __global__ void __launch_bounds__(TC, B2T_K1_MINBLOCKS) pretok_scan_kernel(const
         const uint32_t v = __funnelshift_r(a0, a1, (gp & 3u) * 8u);
         const uint32_t b0 = v & 0xFFu;
         const int len = 2 + (b0 >= 0xE0u) + (b0 >= 0xF0u);
-        const uint32_t cp2 = ((v & 0x1Fu) << 6) | ((v >> 8) & 0x3Fu);
-        const uint32_t cp3 = ((v & 0x0Fu) << 12) | ((v >> 2) & 0xFC0u) | ((v >> 16) & 0x3Fu);
-        const uint32_t cp4 = ((v & 0x07u) << 18) | ((v << 4) & 0x3F000u) | ((v >> 10) & 0xFC0u) | (v >> 24 & 0x3Fu);
-        uint32_t cp = len == 2 ? cp2 : (len == 3 ? cp3 : cp4);
+        // branch-free decode (the three lengths are mixed inside a warp): the low 6 bits of all four bytes as if the
+        // character had 4 bytes, shifted down by the bytes it does not have, lead-byte marker bits masked off
+        const uint32_t t24 = ((v & 0x3Fu) << 18) | ((v << 4) & 0x3F000u) | ((v >> 10) & 0xFC0u) | ((v >> 24) & 0x3Fu);
+        uint32_t cp = (t24 >> (6 * (4 - len))) & ((2u << (5 * len)) - 1u);
         cp = cp < 0x110000u ? cp : 0x10FFFFu;
         const uint32_t cl = (__ldg(cls_tbl + (cp >> 4)) >> ((cp & 15u) * 2u)) & 3u;
         if (cl != CLS_O) {
@@ -209,13 +209,16 @@ __global__ void __launch_bounds__(TC, B2T_K1_MINBLOCKS) pretok_scan_kernel(const
     const int64_t c = tile * TC + tid;
     BoundaryOut r;
     ChunkMasks o = load_masks(buf, tid);
+    // doc-start words of chunks c-1, c, c+1 (chunk indices fit 32 bits: batches are < 2^31 bytes; c - 1 wraps to "outside")
+    auto ds32 = [&](uint32_t k) -> uint32_t { return k < (uint32_t)n_chunks ? __ldg(doc_bits + k) : 0u; };
+    const uint32_t own_ds = ds32((uint32_t)c);
     {
       const ChunkMasks p = tid == 0 ? sm_prev : load_masks(buf, tid - 1);
       const ChunkMasks x = tid == TC - 1 ? load_masks(nbuf, 0) : load_masks(buf, tid + 1);
       Window w;
       w.lead = win(p.lead, o.lead, x.lead); w.L = win(p.L, o.L, x.L); w.N = win(p.N, o.N, x.N); w.S = win(p.S, o.S, x.S);
       w.SP = win(p.SP, o.SP, x.SP); w.NL = KIND == PT_LLAMA3 ? win(p.NL, o.NL, x.NL) : 0ull; w.AP = win(p.AP, o.AP, x.AP);
-      w.DS = win(dsat(c - 1), dsat(c), dsat(c + 1));
+      w.DS = win(ds32((uint32_t)c - 1u), own_ds, ds32((uint32_t)c + 1u));
       const int64_t wb = c * CHUNK - 16;
       if (KIND == PT_GPT2) {
         r = boundaries_gpt2(w, wb, at);
@@ -237,7 +240,6 @@ __global__ void __launch_bounds__(TC, B2T_K1_MINBLOCKS) pretok_scan_kernel(const
         r.start = (uint32_t)((w.DS & w.lead) >> 16); r.drop = 0; r.slow = 0;
       }
     }
-    const uint32_t own_ds = dsat(c);
     if (c < n_chunks) {
       start_bits[c] = r.start;
       if (KIND == PT_WHITESPACE) drop_bits[c] = r.drop;

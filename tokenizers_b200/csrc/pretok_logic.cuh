@@ -137,13 +137,15 @@ B2T_HD void ascii_masks(int kind, const uint32_t w[8], ChunkMasks& m, uint32_t* 
       for (int h = 0; h < 2; ++h) {
         const uint32_t x = w[j + h], asc = ~x & 0x80808080u, w7 = x & 0x7F7F7F7Fu;
         a[h] = (w7 * one + 0x77777777u) & ~(w7 * one + 0x72727272u) & asc;                // 9..13
-        b[h] = (((w7 * one + 0x76767676u) & ~(w7 * one + 0x75757575u)) | ((w7 * one + 0x73737373u) & ~(w7 * one + 0x72727272u))) & asc;  // 10, 13
+        b[h] = 0u;
+        if (kind == PT_LLAMA3)  // only the tiktoken pattern distinguishes newlines
+          b[h] = (((w7 * one + 0x76767676u) & ~(w7 * one + 0x75757575u)) | ((w7 * one + 0x73737373u) & ~(w7 * one + 0x72727272u))) & asc;  // 10, 13
       }
       S |= movemask2(a[0], a[1]) << (4 * j);
-      NL |= movemask2(b[0], b[1]) << (4 * j);
+      if (kind == PT_LLAMA3) NL |= movemask2(b[0], b[1]) << (4 * j);
     }
   }
-  if (any_ap) {
+  if (any_ap && !rust) {  // apostrophes only matter to the contraction alternatives of the ByteLevel / tiktoken patterns
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       uint32_t a[2];
