@@ -95,6 +95,7 @@ __device__ __forceinline__ uint32_t mask_le(int b) { return b >= 31 ? 0xFFFFFFFF
 //   q0 = {tag lo, tag hi, key[0], key[1]}   q1 = {key[2..5]}   q2 = {ntok | len0..2, len3..5 | -, id0, id1}   q3 = {id2..id5}
 // tag: 0 = free, BUSY | fp = being written, READY | fp = valid.  Writers publish with payload -> fence -> tag.
 constexpr int WC_MAX_BYTES = 24, WC_MAX_TOK = 6, WC_PROBES = 4;
+constexpr int P4_SPLIT_BYTES = 12;  // cache misses longer than this are merged by different warps than the short ones
 #define B2T_WC_READY (1ull << 63)
 #define B2T_WC_BUSY (1ull << 62)
 #define B2T_WC_FP ((1ull << 62) - 1ull)
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   __shared__ uint16_t s_list[SPAN];  // P3/P4: pre-tokens the word cache did not resolve; P7: positions of the tokens
   uint16_t* const s_miss = s_list;
   uint16_t* const s_tokpos = s_list;
-  __shared__ int s_nmiss;
+  __shared__ int s_nmiss, s_nmiss_hi;  // misses queued from the front (short) and from the back (longer) of s_miss
   __shared__ int s_tile, s_next, s_nmq, s_P, s_Elast, s_long, s_ntok, s_ntot;
   __shared__ unsigned long long s_excl;
   __shared__ long long s_long_end, s_span_doc_start;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   constexpr int NWARPS = MODEL_THREADS / 32;
   if (tid == 0) {
     s_tile = (int)blockIdx.x;
-    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0;
+    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0; s_nmiss_hi = 0;
   }
   __syncthreads();
   const int64_t t = s_tile;
@@ -497,22 +498,33 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
         }
       }
       // warp-aggregated queue appends
-      const unsigned mm = __ballot_sync(0xFFFFFFFFu, kind == 1), mq = __ballot_sync(0xFFFFFFFFu, kind == 2);
-      int bm = 0, bq = 0;
-      if (lane == 0) { if (mm) bm = atomicAdd(&s_nmiss, __popc(mm)); if (mq) bq = atomicAdd(&s_nmq, __popc(mq)); }
-      bm = __shfl_sync(0xFFFFFFFFu, bm, 0); bq = __shfl_sync(0xFFFFFFFFu, bq, 0);
-      if (kind == 1) s_miss[bm + __popc(mm & ((1u << lane) - 1u))] = (uint16_t)k;
+      // the four groups of a warp step through their merges together, so pre-tokens of similar length should share a
+      // warp: short misses queue from the front of s_miss, longer ones from the back (measured: -1.5 % kernel time)
+      const bool longer = kind == 1 && (int)s_pt[k + 1] - (int)s_pt[k] > P4_SPLIT_BYTES;
+      const unsigned mm = __ballot_sync(0xFFFFFFFFu, kind == 1 && !longer), mh = __ballot_sync(0xFFFFFFFFu, longer),
+                     mq = __ballot_sync(0xFFFFFFFFu, kind == 2);
+      int bm = 0, bh = 0, bq = 0;
+      if (lane == 0) {
+        if (mm) bm = atomicAdd(&s_nmiss, __popc(mm));
+        if (mh) bh = atomicAdd(&s_nmiss_hi, __popc(mh));
+        if (mq) bq = atomicAdd(&s_nmq, __popc(mq));
+      }
+      bm = __shfl_sync(0xFFFFFFFFu, bm, 0); bh = __shfl_sync(0xFFFFFFFFu, bh, 0); bq = __shfl_sync(0xFFFFFFFFu, bq, 0);
+      if (kind == 1 && !longer) s_miss[bm + __popc(mm & ((1u << lane) - 1u))] = (uint16_t)k;
+      if (longer) s_miss[SPAN - 1 - (bh + __popc(mh & ((1u << lane) - 1u)))] = (uint16_t)k;
       if (kind == 2) s_mq[bq + __popc(mq & ((1u << lane) - 1u))] = (uint16_t)k;
     }
     __syncthreads();
     // -------------------------------------------------------------- P4a: misses, 8 lanes per pre-token (<= 32 bytes)
     {
-      const int nmiss = s_nmiss;
+      const int n_front = s_nmiss, nmiss = n_front + s_nmiss_hi;
+      // longer pre-tokens first (they take the most rounds), then the short ones
+      auto miss_at = [&](int i) -> int { const int nh = nmiss - n_front; return i < nh ? s_miss[SPAN - 1 - i] : s_miss[i - nh]; };
       const int grp = tid >> 3, gl = tid & 7;           // 32 groups per block
       for (int m0 = 0; m0 < nmiss; m0 += MODEL_THREADS / 8) {
         const int mi = m0 + grp;
         const bool active0 = mi < nmiss;
-        const int k = active0 ? s_miss[mi] : 0;
+        const int k = active0 ? miss_at(mi) : 0;
         const int s = active0 ? s_pt[k] : 0, e = active0 ? s_pt[k + 1] : 0;
         bool active = active0;
         if (P.t.ignore_merges) {  // models/bpe/model.rs:558-567: the whole pre-token is a vocabulary entry -> one token
