@@ -95,7 +95,14 @@ __device__ __forceinline__ uint32_t mask_le(int b) { return b >= 31 ? 0xFFFFFFFF
 //   q0 = {tag lo, tag hi, key[0], key[1]}   q1 = {key[2..5]}   q2 = {ntok | len0..2, len3..5 | -, id0, id1}   q3 = {id2..id5}
 // tag: 0 = free, BUSY | fp = being written, READY | fp = valid.  Writers publish with payload -> fence -> tag.
 constexpr int WC_MAX_BYTES = 24, WC_MAX_TOK = 6, WC_PROBES = 4;
-constexpr int P4_SPLIT_BYTES = 12;  // cache misses longer than this are merged by different warps than the short ones
+// Cache misses of up to P4_SPLIT_BYTES bytes are merged by 8 lanes x 2 positions, longer ones (<= THREAD_PATH_MAX) by
+// 8 lanes x 4, in separate passes: the groups of a warp step through their merge rounds together, so a warp should
+// hold words of similar length.  Measured on B200 (512 MB, bpe_tile): one mixed pass 8.15 ms, split at 12: 8.07 (one
+// loop) / 8.62 (two passes), split at 16 in two passes 7.95; 4 or 2 lanes per short word 9.0 / 12.8 ms (more words per
+// warp = more rounds per pass: the rounds are L2-latency bound, not lane bound).
+constexpr int P4_SPLIT_BYTES = 16;
+constexpr int P4_SHORT_G = 8;
+template <int V> struct IntTag { static constexpr int value = V; };
 #define B2T_WC_READY (1ull << 63)
 #define B2T_WC_BUSY (1ull << 62)
 #define B2T_WC_FP ((1ull << 62) - 1ull)
@@ -515,34 +522,39 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
       if (kind == 2) s_mq[bq + __popc(mq & ((1u << lane) - 1u))] = (uint16_t)k;
     }
     __syncthreads();
-    // -------------------------------------------------------------- P4a: misses, 8 lanes per pre-token (<= 32 bytes)
+    // -------------------------------------------------------------- P4a: misses, G lanes per pre-token (<= 32 bytes)
     {
-      const int n_front = s_nmiss, nmiss = n_front + s_nmiss_hi;
-      // longer pre-tokens first (they take the most rounds), then the short ones
-      auto miss_at = [&](int i) -> int { const int nh = nmiss - n_front; return i < nh ? s_miss[SPAN - 1 - i] : s_miss[i - nh]; };
-      const int grp = tid >> 3, gl = tid & 7;           // 32 groups per block
-      for (int m0 = 0; m0 < nmiss; m0 += MODEL_THREADS / 8) {
-        const int mi = m0 + grp;
-        const bool active0 = mi < nmiss;
-        const int k = active0 ? miss_at(mi) : 0;
-        const int s = active0 ? s_pt[k] : 0, e = active0 ? s_pt[k + 1] : 0;
-        bool active = active0;
-        if (P.t.ignore_merges) {  // models/bpe/model.rs:558-567: the whole pre-token is a vocabulary entry -> one token
-          int whole = 0;
-          if (active0 && gl == 0) { whole = vocab_whole_word(P.t, s_byte, s, e - s, s_id) ? 1 : 0; if (whole) s_len[s] = (uint16_t)(e - s); }
-          whole = __shfl_sync(0xFFFFFFFFu, whole, lane & ~7);
-          active = active0 && !whole;
+      const int n_short = s_nmiss, n_longer = s_nmiss_hi;
+      // G lanes x J positions resolve the logical misses [0, count): longer ones live at the back of s_miss
+      auto run_misses = [&](auto gtag, auto jtag, int count, bool back) {
+        constexpr int G = decltype(gtag)::value, J = decltype(jtag)::value;
+        const int grp = tid / G, gl = tid % G;
+        for (int m0 = 0; m0 < count; m0 += MODEL_THREADS / G) {
+          const int mi = m0 + grp;
+          const bool active0 = mi < count;
+          const int k = active0 ? (back ? s_miss[SPAN - 1 - mi] : s_miss[mi]) : 0;
+          const int s = active0 ? s_pt[k] : 0, e = active0 ? s_pt[k + 1] : 0;
+          bool active = active0;
+          if (P.t.ignore_merges) {  // models/bpe/model.rs:558-567: the whole pre-token is a vocabulary entry -> one token
+            int whole = 0;
+            if (active0 && gl == 0) { whole = vocab_whole_word(P.t, s_byte, s, e - s, s_id) ? 1 : 0; if (whole) s_len[s] = (uint16_t)(e - s); }
+            whole = __shfl_sync(0xFFFFFFFFu, whole, lane & ~(G - 1));
+            active = active0 && !whole;
+          }
+          coop_bpe<G, J>(P.t, s_byte, s_id, s_len, s, e, active, gl);
+          __syncwarp();
+          // long numbers rarely repeat: publishing them only fills the table (measured: -5 % kernel time without them)
+          const bool numeric = active0 && (e - s) >= 5 && (unsigned)(s_byte[s + 1] - '0') < 10u && (unsigned)(s_byte[e - 1] - '0') < 10u;
+          if (active0 && gl == 0 && e - s <= WC_MAX_BYTES && !numeric) {
+            WordKey key;
+            wc_make_key(s_byte, s, e - s, key);
+            wc_publish(P.wcache, P.wcache_mask, key, s, e, s_id, s_len);
+          }
         }
-        coop_bpe<8, 4>(P.t, s_byte, s_id, s_len, s, e, active, gl);
-        __syncwarp();
-        // long numbers rarely repeat: publishing them only fills the table (measured: -5 % kernel time without them)
-        const bool numeric = active0 && (e - s) >= 5 && (unsigned)(s_byte[s + 1] - '0') < 10u && (unsigned)(s_byte[e - 1] - '0') < 10u;
-        if (active0 && gl == 0 && e - s <= WC_MAX_BYTES && !numeric) {
-          WordKey key;
-          wc_make_key(s_byte, s, e - s, key);
-          wc_publish(P.wcache, P.wcache_mask, key, s, e, s_id, s_len);
-        }
-      }
+      };
+      // longer pre-tokens first (they take the most rounds), then the short ones with fewer lanes / positions each
+      run_misses(IntTag<8>{}, IntTag<THREAD_PATH_MAX / 8>{}, n_longer, true);
+      run_misses(IntTag<P4_SHORT_G>{}, IntTag<(P4_SPLIT_BYTES + P4_SHORT_G - 1) / P4_SHORT_G>{}, n_short, false);
     }
     // -------------------------------------------------------------- P4b: one warp per longer pre-token (33..256 bytes)
     {
