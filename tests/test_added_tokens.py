@@ -1,0 +1,125 @@
+"""Host steps either side of the hot path: added-token extraction (added_vocabulary.rs:430-564) and the single-sequence
+special-token template (processors/template.rs).  CPU: tokenizers_b200's host logic in front of the oracle, against the
+reference wheel (when importable) and against committed golden vectors.  GPU: the same through the real engine."""
+import gzip, json, os
+import numpy as np
+import pytest
+from helpers import GOLDEN, asset_json, with_added_tokens, added_token_docs, oracle_backed_tokenizer, wheel
+
+CONFIGS = [("gpt2_style", False), ("gpt2_style", True), ("llama3_style", False), ("wordpiece", True)]
+
+
+def _patched(asset, prefix_space=None):
+    js = json.loads(asset_json(asset))
+    if prefix_space is not None and js["pre_tokenizer"]["type"] == "ByteLevel":
+        js["pre_tokenizer"]["add_prefix_space"] = prefix_space
+    return json.dumps(js)
+
+
+def _flat(encs):
+    return [{"ids": list(e.ids), "offsets": [list(o) for o in e.offsets], "word_ids": list(e.word_ids),
+             "type_ids": list(e.type_ids), "special": list(e.special_tokens_mask)} for e in encs]
+
+
+def _compare(got, exp, docs, what):
+    assert len(got) == len(exp)
+    for d, (g, e) in enumerate(zip(got, exp)):
+        assert g == e, f"{what}: doc {d} {docs[d]!r}\n exp {e}\n got {g}"
+
+
+@pytest.mark.parametrize("asset,template", CONFIGS)
+@pytest.mark.parametrize("prefix_space", [False, True])
+def test_host_logic_vs_wheel(asset, template, prefix_space):
+    tk = wheel()
+    if tk is None:
+        pytest.skip("reference wheel not importable")
+    if prefix_space and asset != "gpt2_style":
+        pytest.skip("add_prefix_space only varies for the ByteLevel pre-tokenizer")
+    tj = with_added_tokens(_patched(asset, prefix_space), template)
+    ref = tk.Tokenizer.from_str(tj)
+    mine = oracle_backed_tokenizer(tj)
+    docs = added_token_docs(7, 1500)
+    for special in (False, True):
+        exp = _flat(ref.encode_batch(docs, add_special_tokens=special))
+        got = _flat(mine.encode_batch(docs, add_special_tokens=special))
+        _compare(got, exp, docs, f"{asset} template={template} add_special_tokens={special}")
+    assert mine.token_to_id("<mask>") == ref.token_to_id("<mask>")
+    assert mine.id_to_token(mine.token_to_id("<a><b>")) == "<a><b>"
+    assert mine.get_vocab_size() == ref.get_vocab_size() and mine.get_vocab_size(False) == ref.get_vocab_size(False)
+
+
+def test_byte_offsets_and_fast_vs_wheel():
+    tk = wheel()
+    if tk is None:
+        pytest.skip("reference wheel not importable")
+    tj = with_added_tokens(asset_json("gpt2_style"), True)
+    mine = oracle_backed_tokenizer(tj)
+    docs = added_token_docs(11, 400)
+    full = mine.encode_batch(docs, add_special_tokens=True)
+    fast = mine.encode_batch_fast(docs, add_special_tokens=True)
+    assert [e.ids for e in full] == [e.ids for e in fast]
+    # byte offsets of the CSR entry point == char offsets mapped through the document's UTF-8 encoding
+    data = np.frombuffer("".join(docs).encode("utf-8"), dtype=np.uint8)
+    off = np.zeros(len(docs) + 1, dtype=np.uint64)
+    np.cumsum([len(d.encode("utf-8")) for d in docs], out=off[1:])
+    be_c = mine.encode_batch_csr(data, off)
+    be_b = mine.encode_batch_csr(data, off, byte_offsets=True)
+    assert np.array_equal(be_c.ids, be_b.ids) and np.array_equal(be_c.row_ptr, be_b.row_ptr)
+    for d, doc in enumerate(docs):
+        a, b = int(be_c.row_ptr[d]), int(be_c.row_ptr[d + 1])
+        for (c0, c1), (b0, b1) in zip(be_c.offsets[a:b].tolist(), be_b.offsets[a:b].tolist()):
+            assert len(doc[:c0].encode("utf-8")) == b0 and len(doc[:c1].encode("utf-8")) == b1, (doc, c0, c1, b0, b1)
+
+
+def test_unsupported_post_processors():
+    from tokenizers_b200.tokenizer import parse_tokenizer_json, UnsupportedConfig
+    js = json.loads(asset_json("gpt2_style"))
+    js["post_processor"] = {"type": "ByteLevel", "add_prefix_space": True, "trim_offsets": True, "use_regex": True}
+    with pytest.raises(UnsupportedConfig):
+        parse_tokenizer_json(js)
+    js["post_processor"] = {"type": "RobertaProcessing", "sep": ["</s>", 2], "cls": ["<s>", 0], "trim_offsets": False, "add_prefix_space": False}
+    assert parse_tokenizer_json(js)["template"] == {"pre": [(0, 0)], "post": [(2, 0)], "type_id": 0}
+    js["post_processor"] = {"type": "Sequence", "processors": [{"type": "ByteLevel", "trim_offsets": False},
+                                                               {"type": "BertProcessing", "sep": ["[SEP]", 102], "cls": ["[CLS]", 101]}]}
+    assert parse_tokenizer_json(js)["template"]["pre"] == [(101, 0)]
+
+
+def _golden_cases():
+    g = json.loads(gzip.open(os.path.join(GOLDEN, "golden_added_tokens.json.gz")).read().decode("utf-8"))
+    return g
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_host_logic_vs_golden(idx):
+    g = _golden_cases()["configs"][idx]
+    tj = with_added_tokens(_patched(g["asset"], g["prefix_space"]), g["template"])
+    mine = oracle_backed_tokenizer(tj)
+    docs = g["docs"]
+    for special in (False, True):
+        _compare(_flat(mine.encode_batch(docs, add_special_tokens=special)), g["expected"][str(special)], docs, f"golden {g['asset']}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(4))
+def test_gpu_added_tokens_vs_golden(idx):
+    from tokenizers_b200 import Tokenizer
+    g = _golden_cases()["configs"][idx]
+    tok = Tokenizer.from_str(with_added_tokens(_patched(g["asset"], g["prefix_space"]), g["template"]))
+    docs = g["docs"]
+    for special in (False, True):
+        _compare(_flat(tok.encode_batch(docs, add_special_tokens=special)), g["expected"][str(special)], docs, f"gpu golden {g['asset']}")
+    ids_fast = [e.ids for e in tok.encode_batch_fast(docs, add_special_tokens=True)]
+    assert ids_fast == [c["ids"] for c in g["expected"]["True"]]
+
+
+@pytest.mark.gpu
+def test_gpu_decreasing_doc_off_is_rejected():
+    """rows handed to the kernels must be ordered: the C ABI refuses anything else instead of indexing out of bounds"""
+    import ctypes
+    from tokenizers_b200 import Tokenizer, _lib
+    tok = Tokenizer.from_str(asset_json("gpt2_style"))
+    data = np.frombuffer(b"hello world, hello", dtype=np.uint8)
+    off = np.array([0, 11, 5, 18], dtype=np.uint64)
+    res = ctypes.c_void_p()
+    rc = _lib.lib().b2t_encode_batch(tok.handle, data.ctypes.data, off.ctypes.data, 3, _lib.WANT_OFFSETS, ctypes.byref(res))
+    assert rc == _lib.B2T_ERR_INVALID and b"non-decreasing" in _lib.lib().b2t_last_error()

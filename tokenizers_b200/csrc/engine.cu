@@ -483,6 +483,8 @@ struct Chunk { uint32_t d0, d1; uint64_t b0, b1; uint64_t tok_base; };
 static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, uint32_t flags, bool pretok_only,
                        b2t_result** out) {
   if (doc_off[0] != 0) return fail(B2T_ERR_INVALID, "doc_off[0] must be 0");
+  for (uint32_t d = 0; d < n_docs; ++d)  // the kernels index the buffer with these: a decreasing offset must never reach them
+    if (doc_off[d + 1] < doc_off[d]) return fail(B2T_ERR_INVALID, "doc_off must be non-decreasing (document %u)", d);
   const uint64_t total_bytes = doc_off[n_docs];
   // ---- split into chunks of whole documents
   std::vector<Chunk> chunks;
@@ -617,6 +619,8 @@ extern "C" int b2t_pre_tokenize_batch(b2t_engine* e, const uint8_t* bytes, const
   std::lock_guard<std::mutex> lk(e->mu);
   CU(cudaSetDevice(e->device));
   if (doc_off[0] != 0) return fail(B2T_ERR_INVALID, "doc_off[0] must be 0");
+  for (uint32_t d = 0; d < n_docs; ++d)  // the kernels index the buffer with these: a decreasing offset must never reach them
+    if (doc_off[d + 1] < doc_off[d]) return fail(B2T_ERR_INVALID, "doc_off must be non-decreasing (document %u)", d);
   const uint64_t n = doc_off[n_docs];
   Workspace& ws = e->slot[0];
   int rc;

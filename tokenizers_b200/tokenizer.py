@@ -3,12 +3,13 @@
 Mirrors `tokenizers.Tokenizer` (bindings/python/src/tokenizer.rs:510-1461 in the reference tree): `from_file`,
 `from_str`, `encode`, `encode_batch`, `encode_batch_fast`, `token_to_id`, `id_to_token`, `get_vocab_size`, and
 `tokenizers.Encoding` (bindings/python/src/encoding.rs:133-225): `ids`, `tokens`, `offsets`, `word_ids`, `type_ids`,
-`attention_mask`, `special_tokens_mask`.  All compute happens in libb2t.so on the GPU; configurations outside the
-hot path raise `UnsupportedConfig` (there is no CPU fallback).
+`attention_mask`, `special_tokens_mask`.  All tokenization happens in libb2t.so on the GPU; configurations outside the
+hot path raise `UnsupportedConfig` (there is no CPU fallback).  The two host steps the reference runs around the path are
+mirrored here: added-token extraction before it (`added.py`) and the special-token template after it (`post_process`).
 """
 import ctypes, json
 import numpy as np
-from . import _lib
+from . import _lib, added
 from ._lib import B2TError
 
 LLAMA3_PATTERN = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*"
@@ -27,15 +28,54 @@ def _pack(strings):
     return np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8).copy(), off
 
 
+def parse_post_processor(pp):
+    """post_processor of tokenizer.json -> None (nothing to add) or {"pre": [(id, type_id)], "post": [...], "type_id": t}
+    for SINGLE sequences (processors/template.rs:646-, processors/bert.rs, processors/roberta.rs, processors/sequence.rs).
+    Offset trimming (ByteLevel / Roberta `trim_offsets`, pre_tokenizers/byte_level.rs:202-234) is not implemented."""
+    if pp is None:
+        return None
+    ty = pp.get("type")
+    if ty == "ByteLevel":
+        if pp.get("trim_offsets", True):
+            raise UnsupportedConfig("ByteLevel post-processor with trim_offsets=true is not supported")
+        return None
+    if ty == "Sequence":
+        out = None
+        for sub in pp.get("processors", []):
+            t = parse_post_processor(sub)
+            if t is not None:
+                if out is not None:
+                    raise UnsupportedConfig("more than one special-token post-processor in a Sequence")
+                out = t
+        return out
+    if ty in ("BertProcessing", "RobertaProcessing"):
+        if ty == "RobertaProcessing" and pp.get("trim_offsets", True):
+            raise UnsupportedConfig("RobertaProcessing with trim_offsets=true is not supported")
+        return {"pre": [(int(pp["cls"][1]), 0)], "post": [(int(pp["sep"][1]), 0)], "type_id": 0}
+    if ty == "TemplateProcessing":
+        pre, post, seen, seq_type = [], [], False, 0
+        for piece in pp.get("single", []):
+            if "Sequence" in piece:
+                if seen or piece["Sequence"].get("id") != "A":
+                    raise UnsupportedConfig("TemplateProcessing.single must contain sequence A exactly once")
+                seen, seq_type = True, int(piece["Sequence"].get("type_id", 0))
+            else:
+                sp = piece["SpecialToken"]
+                ids = pp["special_tokens"][sp["id"]]["ids"]
+                (post if seen else pre).extend((int(i), int(sp.get("type_id", 0))) for i in ids)
+        if not seen:
+            raise UnsupportedConfig("TemplateProcessing.single without a sequence")
+        return {"pre": pre, "post": post, "type_id": seq_type}
+    raise UnsupportedConfig(f"post-processor {ty} is not supported")
+
+
 def parse_tokenizer_json(js):
     """tokenizer.json (tokenizer/serialization.rs:15-48 in the reference) -> engine configuration dict."""
     if js.get("normalizer") is not None:
         raise UnsupportedConfig("normalizers stay on the host and are not part of the accelerated path")
     if js.get("truncation") is not None or js.get("padding") is not None:
         raise UnsupportedConfig("truncation / padding are host post-processing and not supported here")
-    pp = js.get("post_processor")
-    if pp is not None and not (pp.get("type") == "ByteLevel" and not pp.get("trim_offsets", True)):
-        raise UnsupportedConfig("post-processors other than a no-op ByteLevel(trim_offsets=False) are not supported")
+    template = parse_post_processor(js.get("post_processor"))
     pt, m = js.get("pre_tokenizer"), js["model"]
     cfg = dict(add_prefix_space=0, ignore_merges=0, unk=None, prefix="##", max_chars=100, merges=[])
     if pt is None:
@@ -72,16 +112,20 @@ def parse_tokenizer_json(js):
     else:
         raise UnsupportedConfig(f"model {m['type']} is not on the accelerated path")
     cfg["vocab"] = m["vocab"]
-    cfg["added_tokens"] = [t["content"] for t in js.get("added_tokens", [])]
+    cfg["added_tokens"] = list(js.get("added_tokens", []))
+    cfg["template"] = template
     return cfg
+
+
+NO_WORD = 0xFFFFFFFF  # word id of a token the post-processor added (the reference reports None)
 
 
 class Encoding:
     """One sequence of the batch CSR, with the attribute names of `tokenizers.Encoding`."""
-    __slots__ = ("_tok", "ids", "_offsets", "_word_ids")
+    __slots__ = ("_tok", "ids", "_offsets", "_word_ids", "_type_ids", "_special")
 
-    def __init__(self, tok, ids, offsets, word_ids):
-        self._tok, self.ids, self._offsets, self._word_ids = tok, ids, offsets, word_ids
+    def __init__(self, tok, ids, offsets, word_ids, type_ids=None, special=None):
+        self._tok, self.ids, self._offsets, self._word_ids, self._type_ids, self._special = tok, ids, offsets, word_ids, type_ids, special
 
     def __len__(self):
         return len(self.ids)
@@ -94,7 +138,9 @@ class Encoding:
 
     @property
     def word_ids(self):
-        return None if self._word_ids is None else self._word_ids.tolist()
+        if self._word_ids is None:
+            return None
+        return [None if w == NO_WORD else w for w in self._word_ids.tolist()]
 
     words = word_ids
 
@@ -104,7 +150,7 @@ class Encoding:
 
     @property
     def type_ids(self):
-        return [0] * len(self.ids)
+        return [0] * len(self.ids) if self._type_ids is None else self._type_ids.tolist()
 
     @property
     def attention_mask(self):
@@ -112,11 +158,13 @@ class Encoding:
 
     @property
     def special_tokens_mask(self):
-        return [0] * len(self.ids)
+        return [0] * len(self.ids) if self._special is None else self._special.tolist()
 
     @property
     def sequence_ids(self):
-        return [0] * len(self.ids)
+        if self._special is None:
+            return [0] * len(self.ids)
+        return [None if sp else 0 for sp in self._special.tolist()]
 
     @property
     def n_sequences(self):
@@ -131,14 +179,44 @@ class Encoding:
 
 
 class BatchEncoding:
-    """The whole batch as a CSR (numpy views copied out of the engine's pinned buffers)."""
+    """The whole batch as a CSR (numpy arrays copied out of the engine's pinned buffers).  `type_ids` and
+    `special_tokens_mask` are None unless a special-token template was applied; tokens it added carry offsets (0, 0)
+    and word id NO_WORD."""
 
-    def __init__(self, ids, offsets, word_ids, row_ptr):
+    def __init__(self, ids, offsets, word_ids, row_ptr, type_ids=None, special_tokens_mask=None):
         self.ids, self.offsets, self.word_ids, self.row_ptr = ids, offsets, word_ids, row_ptr
+        self.type_ids, self.special_tokens_mask = type_ids, special_tokens_mask
 
     @property
     def n_tokens(self):
         return int(self.row_ptr[-1])
+
+
+def post_process(be, template):
+    """TokenizerImpl::post_process for single sequences (tokenizer/mod.rs:1265-1317 -> processors/template.rs
+    `apply_template`): the template's special tokens go in front of / behind every sequence of the CSR."""
+    pre, post = template["pre"], template["post"]
+    n = len(be.row_ptr) - 1
+    counts = np.diff(be.row_ptr).astype(np.int64)
+    T, extra = int(counts.sum()), len(pre) + len(post)
+    new_rp = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(counts + extra, out=new_rp[1:])
+    NT = int(new_rp[-1])
+    pos = np.arange(T, dtype=np.int64) + np.repeat(np.arange(n, dtype=np.int64) * extra + len(pre), counts)
+    ids = np.zeros(NT, dtype=np.uint32); ids[pos] = be.ids
+    type_ids = np.zeros(NT, dtype=np.uint32); type_ids[pos] = template["type_id"]
+    special = np.ones(NT, dtype=np.uint8); special[pos] = 0
+    offs = wid = None
+    if be.offsets is not None:
+        offs = np.zeros((NT, 2), dtype=np.uint32); offs[pos] = be.offsets
+    if be.word_ids is not None:
+        wid = np.full(NT, NO_WORD, dtype=np.uint32); wid[pos] = be.word_ids
+    starts, ends = new_rp[:-1].astype(np.int64), new_rp[1:].astype(np.int64)
+    for j, (tid, ty) in enumerate(pre):
+        ids[starts + j] = tid; type_ids[starts + j] = ty
+    for j, (tid, ty) in enumerate(post):
+        ids[ends - len(post) + j] = tid; type_ids[ends - len(post) + j] = ty
+    return BatchEncoding(ids, offs, wid, new_rp, type_ids, special)
 
 
 def _view(ptr, count, dtype):
@@ -151,11 +229,27 @@ def _view(ptr, count, dtype):
 class Tokenizer:
     def __init__(self, tokenizer_json, device=-1):
         js = json.loads(tokenizer_json) if isinstance(tokenizer_json, (str, bytes)) else tokenizer_json
-        cfg = parse_tokenizer_json(js)
+        self._init_host(parse_tokenizer_json(js))
+        self._create_engine(device)
+
+    def _init_host(self, cfg):
         self._cfg = cfg
         self._vocab = cfg["vocab"]
         self._vocab_r = None
-        self._added = cfg["added_tokens"]
+        self._template = cfg["template"]
+        self._added = None
+        if any(t.get("content") for t in cfg["added_tokens"]):
+            self._added = added.AddedVocabulary(cfg["added_tokens"], self._rust_class_table())
+
+    @staticmethod
+    def _rust_class_table():
+        """Rust-regex \\w / \\s classes per code point from the library's own tables (a host-only call, no GPU work)."""
+        tbl = np.zeros(0x110000, dtype=np.uint8)
+        _lib.check(_lib.lib().b2t_unicode_class_table(1, tbl.ctypes.data))
+        return tbl
+
+    def _create_engine(self, device):
+        cfg = self._cfg
         L = _lib.lib()
         toks = list(self._vocab.keys())
         vb, vo = _pack(toks)
@@ -196,14 +290,21 @@ class Tokenizer:
         with opener(path, "rb") as f:
             return Tokenizer(f.read().decode("utf-8"), device)
 
-    # ---- vocabulary helpers
+    # ---- vocabulary helpers (added tokens shadow the model's vocabulary: added_vocabulary.rs:205-238)
     def get_vocab_size(self, with_added_tokens=True):
-        return len(self._vocab)
+        n = len(self._vocab)
+        if with_added_tokens and self._added is not None:
+            n += sum(1 for t in self._added.tokens.values() if self._vocab.get(t.content) != t.id)
+        return n
 
     def token_to_id(self, token):
+        if self._added is not None and token in self._added.by_content:
+            return self._added.by_content[token].id
         return self._vocab.get(token)
 
     def id_to_token(self, i):
+        if self._added is not None and int(i) in self._added.tokens:
+            return self._added.tokens[int(i)].content
         if self._vocab_r is None:
             self._vocab_r = {v: k for k, v in self._vocab.items()}
         return self._vocab_r.get(int(i))
@@ -213,67 +314,83 @@ class Tokenizer:
         return self._h
 
     # ---- encode
-    def _check_added(self, joined):
-        for t in self._added:
-            if t and t in joined:
-                raise UnsupportedConfig(f"input contains the added token {t!r}: added-token extraction "
-                                        "(added_vocabulary.rs:523-564) runs on the host in the reference and is not supported here yet")
-
-    def encode_batch_csr(self, data, doc_off, offsets=True, word_ids=True, byte_offsets=False):
-        """Packed batch in (np.uint8[N], np.uint64[n+1]) -> BatchEncoding.  Host buffers; copies happen inside."""
-        data = np.ascontiguousarray(data, dtype=np.uint8)
-        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
-        n_docs = len(doc_off) - 1
-        flags = (_lib.WANT_OFFSETS if offsets else 0) | (_lib.WANT_WORD_IDS if word_ids else 0) | (_lib.OFFSETS_BYTES if byte_offsets else 0)
+    def _engine_rows(self, data, row_off, flags):
+        """The C-ABI call: packed rows in host memory -> row CSR (ids, offsets or None, word ids or None, row_ptr)."""
+        n_rows = len(row_off) - 1
         L = _lib.lib()
         res = ctypes.c_void_p()
-        _lib.check(L.b2t_encode_batch(self._h, data.ctypes.data if data.size else None, doc_off.ctypes.data, n_docs, flags, ctypes.byref(res)))
+        _lib.check(L.b2t_encode_batch(self._h, data.ctypes.data if data.size else None, row_off.ctypes.data, n_rows, flags, ctypes.byref(res)))
         try:
             T = L.b2t_result_n_tokens(res)
             ids = _view(L.b2t_result_ids(res), T, np.uint32).copy()
-            offs = _view(L.b2t_result_offsets(res), 2 * T, np.uint32).reshape(-1, 2).copy() if offsets else None
-            wid = _view(L.b2t_result_word_ids(res), T, np.uint32).copy() if word_ids else None
-            rp = _view(L.b2t_result_row_ptr(res), n_docs + 1, np.uint64).copy()
+            offs = _view(L.b2t_result_offsets(res), 2 * T, np.uint32).reshape(-1, 2).copy() if flags & _lib.WANT_OFFSETS else None
+            wid = _view(L.b2t_result_word_ids(res), T, np.uint32).copy() if flags & _lib.WANT_WORD_IDS else None
+            rp = _view(L.b2t_result_row_ptr(res), n_rows + 1, np.uint64).copy()
         finally:
             L.b2t_result_free(res)
-        return BatchEncoding(ids, offs, wid, rp)
+        return ids, offs, wid, rp
 
-    def _encode_list(self, docs, offsets, word_ids):
+    def encode_batch_csr(self, data, doc_off, offsets=True, word_ids=True, byte_offsets=False, add_special_tokens=False,
+                         extract_added_tokens=True, _raw=None):
+        """Packed batch in (np.uint8[N], np.uint64[n+1]) -> BatchEncoding.  Host buffers; copies happen inside.
+
+        extract_added_tokens: run the reference's added-token extraction (added_vocabulary.rs:523-564) on the host before
+        the engine when the tokenizer has added tokens -- a byte search over the whole buffer; pass False when the
+        caller knows the text holds none (then this is exactly one b2t_encode_batch call).
+        add_special_tokens: apply the post-processor's single-sequence template (default False here: the CSR entry
+        point is the raw hot path; `encode_batch` follows the reference's default of True)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        flags = (_lib.WANT_OFFSETS if offsets else 0) | (_lib.WANT_WORD_IDS if word_ids else 0) | (_lib.OFFSETS_BYTES if byte_offsets else 0)
+        parts, cut = None, False
+        row_off = doc_off
+        if extract_added_tokens and self._added is not None:
+            row_off, parts, cut = added.split_batch(self._added, data if _raw is None else _raw, doc_off)
+        ids, offs, wid, rp = self._engine_rows(data, row_off, flags)
+        if cut:
+            ids, offs, wid, rp = added.stitch_rows(data if _raw is None else _raw, doc_off, parts, ids, offs, wid, rp, byte_offsets)
+        be = BatchEncoding(ids, offs, wid, rp)
+        if add_special_tokens and self._template is not None:
+            be = post_process(be, self._template)
+        return be
+
+    def _encode_list(self, docs, offsets, word_ids, add_special_tokens):
         for d in docs:
             if not isinstance(d, str):
                 raise UnsupportedConfig("only raw single sequences (str) are supported; pairs and pre-tokenized input are not")
         bs = [d.encode("utf-8") for d in docs]
         joined = b"".join(bs)
-        if self._added:
-            self._check_added(joined.decode("utf-8"))
         off = np.zeros(len(bs) + 1, dtype=np.uint64)
         if bs:
             np.cumsum(np.fromiter(map(len, bs), dtype=np.int64, count=len(bs)), out=off[1:])
-        be = self.encode_batch_csr(np.frombuffer(joined, dtype=np.uint8), off, offsets, word_ids)
+        be = self.encode_batch_csr(np.frombuffer(joined, dtype=np.uint8), off, offsets, word_ids,
+                                   add_special_tokens=add_special_tokens, _raw=joined)
         rp = be.row_ptr
         out = []
         for i in range(len(docs)):
             a, b = int(rp[i]), int(rp[i + 1])
             out.append(Encoding(self, be.ids[a:b].tolist(), None if be.offsets is None else be.offsets[a:b],
-                                None if be.word_ids is None else be.word_ids[a:b]))
+                                None if be.word_ids is None else be.word_ids[a:b],
+                                None if be.type_ids is None else be.type_ids[a:b],
+                                None if be.special_tokens_mask is None else be.special_tokens_mask[a:b]))
         return out
 
     def encode_batch(self, input, is_pretokenized=False, add_special_tokens=True):
         """tokenizer.rs:1312-1340 -> TokenizerImpl::encode_batch_char_offsets (tokenizer/mod.rs:1360-1379)."""
         if is_pretokenized:
             raise UnsupportedConfig("is_pretokenized=True is not on the accelerated path")
-        return self._encode_list(list(input), True, True)
+        return self._encode_list(list(input), True, True, add_special_tokens)
 
     def encode_batch_fast(self, input, is_pretokenized=False, add_special_tokens=True):
         """tokenizer.rs:1433-1461 -> encode_batch_fast (tokenizer/mod.rs:1382-1401): ids only."""
         if is_pretokenized:
             raise UnsupportedConfig("is_pretokenized=True is not on the accelerated path")
-        return self._encode_list(list(input), False, False)
+        return self._encode_list(list(input), False, False, add_special_tokens)
 
     def encode(self, sequence, pair=None, is_pretokenized=False, add_special_tokens=True):
         if pair is not None or is_pretokenized:
             raise UnsupportedConfig("pairs / pre-tokenized input are not on the accelerated path")
-        return self._encode_list([sequence], True, True)[0]
+        return self._encode_list([sequence], True, True, add_special_tokens)[0]
 
     def pre_tokenize_batch(self, docs):
         """PreTokenizer seam: per document the list of (start_byte, end_byte) of its splits."""
