@@ -71,14 +71,46 @@ def test_byte_offsets_and_fast_vs_wheel():
             assert len(doc[:c0].encode("utf-8")) == b0 and len(doc[:c1].encode("utf-8")) == b1, (doc, c0, c1, b0, b1)
 
 
+def _post_processors(js):
+    by = {e["content"]: e["id"] for e in js["added_tokens"]}
+    cls, sep = ["<|endoftext|>", by["<|endoftext|>"]], ["<mask>", by["<mask>"]]
+    tmpl = {"type": "TemplateProcessing", "single": [{"SpecialToken": {"id": "<a>", "type_id": 0}}, {"Sequence": {"id": "A", "type_id": 0}}],
+            "pair": [{"Sequence": {"id": "A", "type_id": 0}}, {"Sequence": {"id": "B", "type_id": 1}}],
+            "special_tokens": {"<a>": {"id": "<a>", "ids": [by["<a>"]], "tokens": ["<a>"]}}}
+    return [{"type": "ByteLevel", "add_prefix_space": True, "trim_offsets": True, "use_regex": True},
+            {"type": "ByteLevel", "add_prefix_space": False, "trim_offsets": True, "use_regex": True},
+            {"type": "RobertaProcessing", "sep": sep, "cls": cls, "trim_offsets": True, "add_prefix_space": True},
+            {"type": "RobertaProcessing", "sep": sep, "cls": cls, "trim_offsets": False, "add_prefix_space": False},
+            {"type": "BertProcessing", "sep": sep, "cls": cls},
+            {"type": "Sequence", "processors": [{"type": "ByteLevel", "add_prefix_space": True, "trim_offsets": True, "use_regex": True}, tmpl]}]
+
+
+@pytest.mark.parametrize("asset,prefix_space", [("gpt2_style", False), ("gpt2_style", True), ("llama3_style", None)])
+def test_post_processors_vs_wheel(asset, prefix_space):
+    """offset trimming (byte_level.rs:202-234) and the Bert / Roberta / Template / Sequence processors for single sequences"""
+    tk = wheel()
+    if tk is None:
+        pytest.skip("reference wheel not importable")
+    base = json.loads(with_added_tokens(_patched(asset, prefix_space)))
+    docs = added_token_docs(13, 600) + ["  two  spaces  ", " x", "x ", "   ", " <mask> y", "a  <both>  b"]
+    for pp in _post_processors(base):
+        js = dict(base, post_processor=pp)
+        tj = json.dumps(js)
+        ref, mine = tk.Tokenizer.from_str(tj), oracle_backed_tokenizer(tj)
+        for special in (False, True):
+            _compare(_flat(mine.encode_batch(docs, add_special_tokens=special)), _flat(ref.encode_batch(docs, add_special_tokens=special)),
+                     docs, f"{asset} {pp['type']} trim={pp.get('trim_offsets')} aps={pp.get('add_prefix_space')} special={special}")
+
+
 def test_unsupported_post_processors():
     from tokenizers_b200.tokenizer import parse_tokenizer_json, UnsupportedConfig
-    js = json.loads(asset_json("gpt2_style"))
+    js = json.loads(asset_json("wordpiece"))
     js["post_processor"] = {"type": "ByteLevel", "add_prefix_space": True, "trim_offsets": True, "use_regex": True}
     with pytest.raises(UnsupportedConfig):
-        parse_tokenizer_json(js)
+        parse_tokenizer_json(js)  # offset trimming is defined on the byte-level alphabet
+    js = json.loads(asset_json("gpt2_style"))
     js["post_processor"] = {"type": "RobertaProcessing", "sep": ["</s>", 2], "cls": ["<s>", 0], "trim_offsets": False, "add_prefix_space": False}
-    assert parse_tokenizer_json(js)["template"] == {"pre": [(0, 0)], "post": [(2, 0)], "type_id": 0}
+    assert parse_tokenizer_json(js)["template"] == {"pre": [(0, 0)], "post": [(2, 0)], "type_id": 0, "trim": None}
     js["post_processor"] = {"type": "Sequence", "processors": [{"type": "ByteLevel", "trim_offsets": False},
                                                                {"type": "BertProcessing", "sep": ["[SEP]", 102], "cls": ["[CLS]", 101]}]}
     assert parse_tokenizer_json(js)["template"]["pre"] == [(101, 0)]

@@ -210,6 +210,7 @@ def stitch_rows(data, doc_off, parts, ids, offs, wid, row_ptr, byte_offsets):
     n_docs = len(doc_off) - 1
     buf = data.tobytes() if isinstance(data, np.ndarray) else bytes(data)
     o_ids, o_offs, o_wid = [], [], []
+    added_at = []  # (index of the token in the output, absolute byte span) of every added token, for offset trimming
     rp = np.zeros(n_docs + 1, dtype=np.uint64)
     row, run_start_row, total = 0, 0, 0  # untouched documents are copied in bulk
 
@@ -241,6 +242,7 @@ def stitch_rows(data, doc_off, parts, ids, offs, wid, row_ptr, byte_offsets):
                 o_ids.append(np.array([tid], dtype=np.uint32))
                 if offs is not None: o_offs.append(np.array([[ua, ub]], dtype=np.uint32))
                 if wid is not None: o_wid.append(np.array([words], dtype=np.uint32))
+                added_at.append((total, base + a, base + b))
                 words += 1
                 total += 1
                 continue
@@ -258,4 +260,4 @@ def stitch_rows(data, doc_off, parts, ids, offs, wid, row_ptr, byte_offsets):
     flush(row)
     cat = lambda xs, shape, dt: np.concatenate(xs) if xs else np.zeros(shape, dtype=dt)
     return (cat(o_ids, 0, np.uint32), None if offs is None else cat(o_offs, (0, 2), np.uint32),
-            None if wid is None else cat(o_wid, 0, np.uint32), rp)
+            None if wid is None else cat(o_wid, 0, np.uint32), rp, added_at)

@@ -29,29 +29,32 @@ def _pack(strings):
 
 
 def parse_post_processor(pp):
-    """post_processor of tokenizer.json -> None (nothing to add) or {"pre": [(id, type_id)], "post": [...], "type_id": t}
-    for SINGLE sequences (processors/template.rs:646-, processors/bert.rs, processors/roberta.rs, processors/sequence.rs).
-    Offset trimming (ByteLevel / Roberta `trim_offsets`, pre_tokenizers/byte_level.rs:202-234) is not implemented."""
+    """post_processor of tokenizer.json -> None (nothing to do) or
+    {"pre": [(id, type_id)], "post": [...], "type_id": t, "trim": None | add_prefix_space} for SINGLE sequences
+    (processors/template.rs:646-, processors/bert.rs, processors/roberta.rs, processors/sequence.rs;
+    "trim": ByteLevel / Roberta `trim_offsets`, pre_tokenizers/byte_level.rs:174-234)."""
     if pp is None:
         return None
     ty = pp.get("type")
+    none = {"pre": [], "post": [], "type_id": 0, "trim": None}
     if ty == "ByteLevel":
-        if pp.get("trim_offsets", True):
-            raise UnsupportedConfig("ByteLevel post-processor with trim_offsets=true is not supported")
-        return None
+        return dict(none, trim=bool(pp.get("add_prefix_space", True))) if pp.get("trim_offsets", True) else None
     if ty == "Sequence":
         out = None
         for sub in pp.get("processors", []):
             t = parse_post_processor(sub)
-            if t is not None:
-                if out is not None:
-                    raise UnsupportedConfig("more than one special-token post-processor in a Sequence")
+            if t is None:
+                continue
+            if out is None:
                 out = t
+            elif (out["pre"] or out["post"]) and (t["pre"] or t["post"] or t["trim"] is not None):
+                raise UnsupportedConfig("post-processor Sequence: only [offset trimming, one special-token template] in that order")
+            else:
+                out = dict(t, trim=out["trim"] if t["trim"] is None else t["trim"])
         return out
     if ty in ("BertProcessing", "RobertaProcessing"):
-        if ty == "RobertaProcessing" and pp.get("trim_offsets", True):
-            raise UnsupportedConfig("RobertaProcessing with trim_offsets=true is not supported")
-        return {"pre": [(int(pp["cls"][1]), 0)], "post": [(int(pp["sep"][1]), 0)], "type_id": 0}
+        trim = bool(pp.get("add_prefix_space", True)) if ty == "RobertaProcessing" and pp.get("trim_offsets", True) else None
+        return {"pre": [(int(pp["cls"][1]), 0)], "post": [(int(pp["sep"][1]), 0)], "type_id": 0, "trim": trim}
     if ty == "TemplateProcessing":
         pre, post, seen, seq_type = [], [], False, 0
         for piece in pp.get("single", []):
@@ -65,7 +68,7 @@ def parse_post_processor(pp):
                 (post if seen else pre).extend((int(i), int(sp.get("type_id", 0))) for i in ids)
         if not seen:
             raise UnsupportedConfig("TemplateProcessing.single without a sequence")
-        return {"pre": pre, "post": post, "type_id": seq_type}
+        return {"pre": pre, "post": post, "type_id": seq_type, "trim": None}
     raise UnsupportedConfig(f"post-processor {ty} is not supported")
 
 
@@ -113,6 +116,8 @@ def parse_tokenizer_json(js):
         raise UnsupportedConfig(f"model {m['type']} is not on the accelerated path")
     cfg["vocab"] = m["vocab"]
     cfg["added_tokens"] = list(js.get("added_tokens", []))
+    if template is not None and template["trim"] is not None and (cfg["model"] != _lib.MODEL_BPE or cfg["pretok"] == _lib.PRETOK_WHITESPACE):
+        raise UnsupportedConfig("trim_offsets needs a byte-level BPE pipeline")
     cfg["template"] = template
     return cfg
 
@@ -190,6 +195,27 @@ class BatchEncoding:
     @property
     def n_tokens(self):
         return int(self.row_ptr[-1])
+
+
+def trim_offsets(be, lead, trail, add_prefix_space, added_ws):
+    """ByteLevel::process_offsets (pre_tokenizers/byte_level.rs:202-234) on the whole CSR: offsets shrink by the token's
+    leading / trailing spaces.  lead / trail: per token id the count of leading / trailing byte-level space characters of
+    its vocabulary string; added_ws: [(token index, leading, trailing)] for added tokens (their text is the matched span)."""
+    if be.offsets is None or be.ids.size == 0:
+        return be
+    ld, tr = lead[be.ids].astype(np.int64), trail[be.ids].astype(np.int64)
+    for i, l, t in added_ws:
+        ld[i], tr[i] = l, t
+    o0, o1 = be.offsets[:, 0].astype(np.int64), be.offsets[:, 1].astype(np.int64)
+    first = np.zeros(be.ids.size, dtype=bool)
+    starts = be.row_ptr[:-1][np.diff(be.row_ptr) > 0].astype(np.int64)
+    first[starts] = True
+    first |= o0 == 0
+    keep = first & bool(add_prefix_space) & (ld == 1)
+    n0 = np.where((ld > 0) & ~keep, np.minimum(o0 + ld, o1), o0)
+    n1 = np.where((tr > 0) & (o1 >= tr), np.maximum(o1 - tr, n0), o1)
+    offs = np.stack([n0, n1], axis=1).astype(np.uint32)
+    return BatchEncoding(be.ids, offs, be.word_ids, be.row_ptr, be.type_ids, be.special_tokens_mask)
 
 
 def post_process(be, template):
@@ -347,12 +373,37 @@ class Tokenizer:
         if extract_added_tokens and self._added is not None:
             row_off, parts, cut = added.split_batch(self._added, data if _raw is None else _raw, doc_off)
         ids, offs, wid, rp = self._engine_rows(data, row_off, flags)
+        added_at = []
         if cut:
-            ids, offs, wid, rp = added.stitch_rows(data if _raw is None else _raw, doc_off, parts, ids, offs, wid, rp, byte_offsets)
+            ids, offs, wid, rp, added_at = added.stitch_rows(data if _raw is None else _raw, doc_off, parts, ids, offs, wid, rp, byte_offsets)
         be = BatchEncoding(ids, offs, wid, rp)
-        if add_special_tokens and self._template is not None:
-            be = post_process(be, self._template)
+        tp = self._template
+        if tp is not None and tp["trim"] is not None and offsets:
+            lead, trail = self._trim_tables()
+            raw = data if _raw is None else _raw
+            be = trim_offsets(be, lead, trail, tp["trim"], [(i,) + self._span_spaces(raw, a, b) for i, a, b in added_at])
+        if add_special_tokens and tp is not None and (tp["pre"] or tp["post"]):
+            be = post_process(be, tp)
         return be
+
+    def _trim_tables(self):
+        """per token id: leading / trailing 'G-dot' characters (the byte-level image of U+0020) of its vocabulary string"""
+        if getattr(self, "_trim", None) is None:
+            n = max(max(self._vocab.values()), max(self._added.tokens) if self._added is not None else 0) + 1
+            lead, trail = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+            for t, i in self._vocab.items():
+                lead[i] = len(t) - len(t.lstrip("\u0120"))
+                trail[i] = len(t) - len(t.rstrip("\u0120"))
+            self._trim = (lead, trail)
+        return self._trim
+
+    def _span_spaces(self, raw, a, b):
+        """leading / trailing whitespace characters of an added token's matched span (char::is_whitespace or G-dot)"""
+        t = bytes(raw[a:b]).decode("utf-8", "replace")
+        ws = lambda c: c == "\u0120" or self._added._class(ord(c)) == added.CLS_S
+        lead = next((k for k, c in enumerate(t) if not ws(c)), len(t))
+        trail = next((k for k, c in enumerate(reversed(t)) if not ws(c)), len(t))
+        return lead, trail
 
     def _encode_list(self, docs, offsets, word_ids, add_special_tokens):
         for d in docs:
