@@ -55,7 +55,7 @@ __global__ void long_find_kernel(const uint32_t* __restrict__ start_bits, int64_
   if (page >= n_pages) return;
   const int64_t n_words = n / 32 + 1;
   const int64_t w0 = page * (PAGE / 32);
-  constexpr int PW = PAGE / 32;          // 64 words per page
+  static_assert(PAGE / 32 == 64, "a lane handles words lane and lane + 32 of the page");
   constexpr int LW = LONG_PRETOK_MIN / 32;      // 8
   // lane handles words lane and lane + 32 of the page
   int nlong_lane = 0;
