@@ -102,6 +102,49 @@ def test_post_processors_vs_wheel(asset, prefix_space):
                      docs, f"{asset} {pp['type']} trim={pp.get('trim_offsets')} aps={pp.get('add_prefix_space')} special={special}")
 
 
+def _flat_full(encs):
+    def one(e):
+        return {"ids": list(e.ids), "offsets": [list(o) for o in e.offsets], "word_ids": list(e.word_ids), "type_ids": list(e.type_ids),
+                "special": list(e.special_tokens_mask), "attention": list(e.attention_mask), "overflowing": [one(o) for o in e.overflowing]}
+    return [one(e) for e in encs]
+
+
+@pytest.mark.parametrize("asset,template", [("gpt2_style", True), ("wordpiece", False)])
+def test_truncation_and_padding_vs_wheel(asset, template):
+    """TokenizerImpl::post_process steps 1 and 3 (utils/truncation.rs, Encoding::truncate, utils/padding.rs) for single sequences"""
+    tk = wheel()
+    if tk is None:
+        pytest.skip("reference wheel not importable")
+    tj = with_added_tokens(asset_json(asset), template)
+    ref, mine = tk.Tokenizer.from_str(tj), oracle_backed_tokenizer(tj)
+    docs = added_token_docs(17, 250) + ["", "a", "a b c d e f g h i j k l m n o p q r s t u v w x y z " * 3]
+    cases = [dict(max_length=8, stride=0, direction="right"), dict(max_length=8, stride=3, direction="right"),
+             dict(max_length=7, stride=2, direction="left"), dict(max_length=3, stride=0, direction="left"),
+             dict(max_length=16, stride=5, direction="right", strategy="only_first")]
+    pads = [None, dict(), dict(direction="left", pad_id=3, pad_type_id=1, pad_token="<pad>"), dict(length=12), dict(pad_to_multiple_of=8)]
+    for ci, tc in enumerate(cases):
+        for pi, pc in enumerate(pads):
+            for t in (ref, mine):
+                t.enable_truncation(**tc)
+                t.no_padding() if pc is None else t.enable_padding(**pc)
+            for special in (False, True):
+                exp = _flat_full(ref.encode_batch(docs, add_special_tokens=special))
+                got = _flat_full(mine.encode_batch(docs, add_special_tokens=special))
+                _compare(got, exp, docs, f"{asset} trunc={tc} pad={pc} special={special}")
+    # padding without truncation, settings read from tokenizer.json
+    js = json.loads(tj)
+    js["truncation"] = {"direction": "Right", "max_length": 10, "strategy": "LongestFirst", "stride": 2}
+    js["padding"] = {"strategy": {"Fixed": 14}, "direction": "Right", "pad_to_multiple_of": None, "pad_id": 1, "pad_type_id": 0, "pad_token": "[PAD]"}
+    ref, mine = tk.Tokenizer.from_str(json.dumps(js)), oracle_backed_tokenizer(json.dumps(js))
+    assert mine.truncation == ref.truncation and mine.padding["length"] == 14
+    _compare(_flat_full(mine.encode_batch(docs)), _flat_full(ref.encode_batch(docs)), docs, "settings from tokenizer.json")
+    # (known difference: the text of an lstrip / rstrip token is its matched span in the reference, its content here)
+    plain = [d for d in docs if not any(t in d for t in ("<mask>", "[SEP2]", "<both>", "wörd"))][:80]
+    assert [e.tokens for e in mine.encode_batch(plain)] == [e.tokens for e in ref.encode_batch(plain)]
+    ref.no_truncation(); mine.no_truncation()
+    _compare(_flat_full(mine.encode_batch(docs)), _flat_full(ref.encode_batch(docs)), docs, "padding only")
+
+
 def test_unsupported_post_processors():
     from tokenizers_b200.tokenizer import parse_tokenizer_json, UnsupportedConfig
     js = json.loads(asset_json("wordpiece"))

@@ -72,12 +72,29 @@ def parse_post_processor(pp):
     raise UnsupportedConfig(f"post-processor {ty} is not supported")
 
 
+def parse_truncation(t):
+    """tokenizer.json `truncation` (utils/truncation.rs:42-58) -> dict with the Python binding's spelling, or None"""
+    if t is None:
+        return None
+    strategy = {"LongestFirst": "longest_first", "OnlyFirst": "only_first", "OnlySecond": "only_second"}[t.get("strategy", "LongestFirst")]
+    return {"max_length": int(t["max_length"]), "stride": int(t.get("stride", 0)), "strategy": strategy,
+            "direction": t.get("direction", "Right").lower()}
+
+
+def parse_padding(p):
+    """tokenizer.json `padding` (utils/padding.rs:21-48) -> dict with the Python binding's spelling, or None"""
+    if p is None:
+        return None
+    st = p.get("strategy", "BatchLongest")
+    return {"length": None if st == "BatchLongest" else int(st["Fixed"]), "direction": p.get("direction", "Right").lower(),
+            "pad_to_multiple_of": p.get("pad_to_multiple_of"), "pad_id": int(p.get("pad_id", 0)),
+            "pad_type_id": int(p.get("pad_type_id", 0)), "pad_token": p.get("pad_token", "[PAD]")}
+
+
 def parse_tokenizer_json(js):
     """tokenizer.json (tokenizer/serialization.rs:15-48 in the reference) -> engine configuration dict."""
     if js.get("normalizer") is not None:
         raise UnsupportedConfig("normalizers stay on the host and are not part of the accelerated path")
-    if js.get("truncation") is not None or js.get("padding") is not None:
-        raise UnsupportedConfig("truncation / padding are host post-processing and not supported here")
     template = parse_post_processor(js.get("post_processor"))
     pt, m = js.get("pre_tokenizer"), js["model"]
     cfg = dict(add_prefix_space=0, ignore_merges=0, unk=None, prefix="##", max_chars=100, merges=[])
@@ -119,6 +136,8 @@ def parse_tokenizer_json(js):
     if template is not None and template["trim"] is not None and (cfg["model"] != _lib.MODEL_BPE or cfg["pretok"] == _lib.PRETOK_WHITESPACE):
         raise UnsupportedConfig("trim_offsets needs a byte-level BPE pipeline")
     cfg["template"] = template
+    cfg["truncation"] = parse_truncation(js.get("truncation"))
+    cfg["padding"] = parse_padding(js.get("padding"))
     return cfg
 
 
@@ -127,10 +146,11 @@ NO_WORD = 0xFFFFFFFF  # word id of a token the post-processor added (the referen
 
 class Encoding:
     """One sequence of the batch CSR, with the attribute names of `tokenizers.Encoding`."""
-    __slots__ = ("_tok", "ids", "_offsets", "_word_ids", "_type_ids", "_special")
+    __slots__ = ("_tok", "ids", "_offsets", "_word_ids", "_type_ids", "_special", "_attn", "_pad_token", "overflowing")
 
     def __init__(self, tok, ids, offsets, word_ids, type_ids=None, special=None):
         self._tok, self.ids, self._offsets, self._word_ids, self._type_ids, self._special = tok, ids, offsets, word_ids, type_ids, special
+        self._attn, self._pad_token, self.overflowing = None, None, []
 
     def __len__(self):
         return len(self.ids)
@@ -151,7 +171,9 @@ class Encoding:
 
     @property
     def tokens(self):
-        return [self._tok.id_to_token(i) for i in self.ids]
+        if self._attn is None:
+            return [self._tok.id_to_token(i) for i in self.ids]
+        return [self._tok.id_to_token(i) if m else self._pad_token for i, m in zip(self.ids, self._attn.tolist())]
 
     @property
     def type_ids(self):
@@ -159,7 +181,7 @@ class Encoding:
 
     @property
     def attention_mask(self):
-        return [1] * len(self.ids)
+        return [1] * len(self.ids) if self._attn is None else self._attn.tolist()
 
     @property
     def special_tokens_mask(self):
@@ -175,9 +197,24 @@ class Encoding:
     def n_sequences(self):
         return 1
 
-    @property
-    def overflowing(self):
-        return []
+    def _pad(self, target, pad_id, pad_type_id, pad_token, left):
+        """Encoding::pad (tokenizer/encoding.rs:465-560)"""
+        for o in self.overflowing:
+            o._pad(target, pad_id, pad_type_id, pad_token, left)
+        k = target - len(self.ids)
+        if k <= 0:
+            return
+        n = len(self.ids)
+        cat = (lambda pad, x: np.concatenate([pad, x])) if left else (lambda pad, x: np.concatenate([x, pad]))
+        self._attn = cat(np.zeros(k, dtype=np.uint8), np.ones(n, dtype=np.uint8) if self._attn is None else self._attn)
+        self._special = cat(np.ones(k, dtype=np.uint8), np.zeros(n, dtype=np.uint8) if self._special is None else self._special)
+        self._type_ids = cat(np.full(k, pad_type_id, dtype=np.uint32), np.zeros(n, dtype=np.uint32) if self._type_ids is None else self._type_ids)
+        self.ids = [pad_id] * k + self.ids if left else self.ids + [pad_id] * k
+        if self._offsets is not None:
+            self._offsets = cat(np.zeros((k, 2), dtype=np.uint32), self._offsets)
+        if self._word_ids is not None:
+            self._word_ids = cat(np.full(k, NO_WORD, dtype=np.uint32), self._word_ids)
+        self._pad_token = pad_token
 
     def __repr__(self):
         return f"Encoding(num_tokens={len(self.ids)}, attributes=[ids, type_ids, tokens, offsets, attention_mask, special_tokens_mask, overflowing])"
@@ -197,25 +234,69 @@ class BatchEncoding:
         return int(self.row_ptr[-1])
 
 
-def trim_offsets(be, lead, trail, add_prefix_space, added_ws):
+def trim_offsets(be, ld, tr, add_prefix_space):
     """ByteLevel::process_offsets (pre_tokenizers/byte_level.rs:202-234) on the whole CSR: offsets shrink by the token's
-    leading / trailing spaces.  lead / trail: per token id the count of leading / trailing byte-level space characters of
-    its vocabulary string; added_ws: [(token index, leading, trailing)] for added tokens (their text is the matched span)."""
+    leading / trailing spaces.  ld / tr: per token, the number of leading / trailing space characters of its text."""
     if be.offsets is None or be.ids.size == 0:
         return be
-    ld, tr = lead[be.ids].astype(np.int64), trail[be.ids].astype(np.int64)
-    for i, l, t in added_ws:
-        ld[i], tr[i] = l, t
+    ld, tr = ld.astype(np.int64), tr.astype(np.int64)
     o0, o1 = be.offsets[:, 0].astype(np.int64), be.offsets[:, 1].astype(np.int64)
     first = np.zeros(be.ids.size, dtype=bool)
-    starts = be.row_ptr[:-1][np.diff(be.row_ptr) > 0].astype(np.int64)
-    first[starts] = True
+    first[be.row_ptr[:-1][np.diff(be.row_ptr) > 0].astype(np.int64)] = True
     first |= o0 == 0
     keep = first & bool(add_prefix_space) & (ld == 1)
     n0 = np.where((ld > 0) & ~keep, np.minimum(o0 + ld, o1), o0)
     n1 = np.where((tr > 0) & (o1 >= tr), np.maximum(o1 - tr, n0), o1)
     offs = np.stack([n0, n1], axis=1).astype(np.uint32)
     return BatchEncoding(be.ids, offs, be.word_ids, be.row_ptr, be.type_ids, be.special_tokens_mask)
+
+
+def truncate_csr(be, extra, max_length, stride, direction):
+    """Encoding::truncate (tokenizer/encoding.rs:307-388) for every sequence of the CSR: a sequence longer than max_length
+    becomes several rows -- the kept part first, then its overflowing parts (each max_length long, consecutive ones
+    sharing `stride` tokens).  extra: per-token arrays cut the same way.
+    -> (BatchEncoding of all parts, extra arrays, part_doc int64[parts] = document of each part)"""
+    counts = np.diff(be.row_ptr).astype(np.int64)
+    starts = be.row_ptr[:-1].astype(np.int64)
+    seg_a, seg_b, seg_doc = [], [], []
+    long_docs = np.flatnonzero(counts > max_length)
+    is_long = np.zeros(len(counts), dtype=bool); is_long[long_docs] = True
+    if max_length > 0 and stride >= max_length and long_docs.size:
+        raise ValueError(f"`stride` must be strictly less than `max_len={max_length}` (the maximum length minus the special tokens)")
+    per_doc = {}
+    for d in long_docs.tolist():
+        n = int(counts[d])
+        if max_length == 0:
+            per_doc[d] = [(0, 0), (0, n)]  # an empty kept part, the whole sequence overflows (encoding.rs:313-317)
+            continue
+        step, parts = max_length - stride, []
+        if direction == "right":
+            for a in range(0, n, step):
+                b = min(a + max_length, n)
+                parts.append((a, b))
+                if b == n:
+                    break
+        else:
+            for stop in range(n, 0, -step):
+                a = max(stop - max_length, 0)
+                parts.append((a, stop))
+                if a == 0:
+                    break
+        per_doc[d] = parts
+    for d in range(len(counts)):
+        if not is_long[d]:
+            seg_a.append(int(starts[d])); seg_b.append(int(starts[d] + counts[d])); seg_doc.append(d)
+        else:
+            for a, b in per_doc[d]:
+                seg_a.append(int(starts[d]) + a); seg_b.append(int(starts[d]) + b); seg_doc.append(d)
+    seg_a, seg_b = np.asarray(seg_a, dtype=np.int64), np.asarray(seg_b, dtype=np.int64)
+    lens = seg_b - seg_a
+    rp = np.zeros(len(lens) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=rp[1:])
+    idx = np.repeat(seg_a - rp[:-1].astype(np.int64), lens) + np.arange(int(rp[-1]), dtype=np.int64)
+    take = lambda x: None if x is None else x[idx]
+    return (BatchEncoding(be.ids[idx], take(be.offsets), take(be.word_ids), rp), [take(x) for x in extra],
+            np.asarray(seg_doc, dtype=np.int64))
 
 
 def post_process(be, template):
@@ -263,6 +344,8 @@ class Tokenizer:
         self._vocab = cfg["vocab"]
         self._vocab_r = None
         self._template = cfg["template"]
+        self._truncation, self._padding = cfg["truncation"], cfg["padding"]
+        self._trim = None
         self._added = None
         if any(t.get("content") for t in cfg["added_tokens"]):
             self._added = added.AddedVocabulary(cfg["added_tokens"], self._rust_class_table())
@@ -356,39 +439,81 @@ class Tokenizer:
             L.b2t_result_free(res)
         return ids, offs, wid, rp
 
+    # ---- truncation / padding (bindings/python/src/tokenizer.rs:700-820)
+    def enable_truncation(self, max_length, stride=0, strategy="longest_first", direction="right"):
+        if strategy not in ("longest_first", "only_first", "only_second") or direction not in ("left", "right"):
+            raise ValueError("unknown truncation strategy / direction")
+        self._truncation = {"max_length": int(max_length), "stride": int(stride), "strategy": strategy, "direction": direction}
+
+    def no_truncation(self):
+        self._truncation = None
+
+    @property
+    def truncation(self):
+        return None if self._truncation is None else dict(self._truncation)
+
+    def enable_padding(self, direction="right", pad_id=0, pad_type_id=0, pad_token="[PAD]", length=None, pad_to_multiple_of=None):
+        if direction not in ("left", "right"):
+            raise ValueError("unknown padding direction")
+        self._padding = {"length": length, "direction": direction, "pad_to_multiple_of": pad_to_multiple_of, "pad_id": int(pad_id),
+                         "pad_type_id": int(pad_type_id), "pad_token": pad_token}
+
+    def no_padding(self):
+        self._padding = None
+
+    @property
+    def padding(self):
+        return None if self._padding is None else dict(self._padding)
+
+    def _encode_core(self, data, doc_off, flags, raw, extract_added_tokens):
+        """added-token extraction -> engine -> stitching.  -> (BatchEncoding of the plain sequences, trim counts or None)"""
+        parts, cut, row_off, added_at = None, False, doc_off, []
+        if extract_added_tokens and self._added is not None:
+            row_off, parts, cut = added.split_batch(self._added, raw, doc_off)
+        ids, offs, wid, rp = self._engine_rows(data, row_off, flags)
+        if cut:
+            ids, offs, wid, rp, added_at = added.stitch_rows(raw, doc_off, parts, ids, offs, wid, rp, bool(flags & _lib.OFFSETS_BYTES))
+        trim = None
+        tp = self._template
+        if tp is not None and tp["trim"] is not None and offs is not None:
+            lead, trail = self._trim_tables()
+            ld, tr = lead[ids], trail[ids]
+            for i, a, b in added_at:
+                ld[i], tr[i] = self._span_spaces(raw, a, b)
+            trim = (ld, tr)
+        return BatchEncoding(ids, offs, wid, rp), trim
+
+    def _finish(self, be, trim, add_special_tokens):
+        """the post-processor: offset trimming, then the special-token template"""
+        tp = self._template
+        if trim is not None:
+            be = trim_offsets(be, trim[0], trim[1], tp["trim"])
+        if add_special_tokens and tp is not None and (tp["pre"] or tp["post"]):
+            be = post_process(be, tp)
+        return be
+
     def encode_batch_csr(self, data, doc_off, offsets=True, word_ids=True, byte_offsets=False, add_special_tokens=False,
-                         extract_added_tokens=True, _raw=None):
+                         extract_added_tokens=True):
         """Packed batch in (np.uint8[N], np.uint64[n+1]) -> BatchEncoding.  Host buffers; copies happen inside.
 
         extract_added_tokens: run the reference's added-token extraction (added_vocabulary.rs:523-564) on the host before
         the engine when the tokenizer has added tokens -- a byte search over the whole buffer; pass False when the
         caller knows the text holds none (then this is exactly one b2t_encode_batch call).
         add_special_tokens: apply the post-processor's single-sequence template (default False here: the CSR entry
-        point is the raw hot path; `encode_batch` follows the reference's default of True)."""
+        point is the raw hot path; `encode_batch` follows the reference's default of True).
+        Truncation / padding settings change the shape of the result (overflowing parts, pad tokens) and are honoured
+        by `encode_batch` / `encode`, not here."""
+        if self._truncation is not None or self._padding is not None:
+            raise UnsupportedConfig("truncation / padding are enabled: use encode_batch (the CSR entry point returns plain sequences)")
         data = np.ascontiguousarray(data, dtype=np.uint8)
         doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
         flags = (_lib.WANT_OFFSETS if offsets else 0) | (_lib.WANT_WORD_IDS if word_ids else 0) | (_lib.OFFSETS_BYTES if byte_offsets else 0)
-        parts, cut = None, False
-        row_off = doc_off
-        if extract_added_tokens and self._added is not None:
-            row_off, parts, cut = added.split_batch(self._added, data if _raw is None else _raw, doc_off)
-        ids, offs, wid, rp = self._engine_rows(data, row_off, flags)
-        added_at = []
-        if cut:
-            ids, offs, wid, rp, added_at = added.stitch_rows(data if _raw is None else _raw, doc_off, parts, ids, offs, wid, rp, byte_offsets)
-        be = BatchEncoding(ids, offs, wid, rp)
-        tp = self._template
-        if tp is not None and tp["trim"] is not None and offsets:
-            lead, trail = self._trim_tables()
-            raw = data if _raw is None else _raw
-            be = trim_offsets(be, lead, trail, tp["trim"], [(i,) + self._span_spaces(raw, a, b) for i, a, b in added_at])
-        if add_special_tokens and tp is not None and (tp["pre"] or tp["post"]):
-            be = post_process(be, tp)
-        return be
+        be, trim = self._encode_core(data, doc_off, flags, data, extract_added_tokens)
+        return self._finish(be, trim, add_special_tokens)
 
     def _trim_tables(self):
         """per token id: leading / trailing 'G-dot' characters (the byte-level image of U+0020) of its vocabulary string"""
-        if getattr(self, "_trim", None) is None:
+        if self._trim is None:
             n = max(max(self._vocab.values()), max(self._added.tokens) if self._added is not None else 0) + 1
             lead, trail = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
             for t, i in self._vocab.items():
@@ -414,16 +539,42 @@ class Tokenizer:
         off = np.zeros(len(bs) + 1, dtype=np.uint64)
         if bs:
             np.cumsum(np.fromiter(map(len, bs), dtype=np.int64, count=len(bs)), out=off[1:])
-        be = self.encode_batch_csr(np.frombuffer(joined, dtype=np.uint8), off, offsets, word_ids,
-                                   add_special_tokens=add_special_tokens, _raw=joined)
+        flags = (_lib.WANT_OFFSETS if offsets else 0) | (_lib.WANT_WORD_IDS if word_ids else 0)
+        be, trim = self._encode_core(np.frombuffer(joined, dtype=np.uint8), off, flags, joined, True)
+        # TokenizerImpl::post_process (tokenizer/mod.rs:1265-1317): 1. truncate, 2. post-processor, 3. pad
+        part_doc = np.arange(len(docs), dtype=np.int64)
+        tr = self._truncation
+        if tr is not None:
+            if tr["strategy"] == "only_second":
+                raise ValueError("Truncation error: Second sequence not provided")
+            tp = self._template
+            n_added = len(tp["pre"]) + len(tp["post"]) if (add_special_tokens and tp is not None) else 0
+            if tr["max_length"] < n_added:
+                raise ValueError("truncation max_length is smaller than the number of special tokens the post-processor adds")
+            be, cut, part_doc = truncate_csr(be, list(trim) if trim is not None else [], tr["max_length"] - n_added, tr["stride"], tr["direction"])
+            trim = tuple(cut) if trim is not None else None
+        be = self._finish(be, trim, add_special_tokens)
         rp = be.row_ptr
-        out = []
-        for i in range(len(docs)):
+        out, prev = [], -1
+        for i in range(len(part_doc)):
             a, b = int(rp[i]), int(rp[i + 1])
-            out.append(Encoding(self, be.ids[a:b].tolist(), None if be.offsets is None else be.offsets[a:b],
-                                None if be.word_ids is None else be.word_ids[a:b],
-                                None if be.type_ids is None else be.type_ids[a:b],
-                                None if be.special_tokens_mask is None else be.special_tokens_mask[a:b]))
+            enc = Encoding(self, be.ids[a:b].tolist(), None if be.offsets is None else be.offsets[a:b],
+                           None if be.word_ids is None else be.word_ids[a:b],
+                           None if be.type_ids is None else be.type_ids[a:b],
+                           None if be.special_tokens_mask is None else be.special_tokens_mask[a:b])
+            if int(part_doc[i]) == prev:
+                out[-1].overflowing.append(enc)  # the parts of a truncated sequence follow its kept part
+            else:
+                out.append(enc); prev = int(part_doc[i])
+        pd = self._padding
+        if pd is not None and out:
+            # utils/padding.rs:50-81 (the per-sequence padding of post_process step 3 is subsumed by the batch-level one)
+            target = pd["length"] if pd["length"] is not None else max(len(e.ids) for e in out)
+            m = pd["pad_to_multiple_of"]
+            if m and target % m:
+                target += m - target % m
+            for e in out:
+                e._pad(target, pd["pad_id"], pd["pad_type_id"], pd["pad_token"], pd["direction"] == "left")
         return out
 
     def encode_batch(self, input, is_pretokenized=False, add_special_tokens=True):
