@@ -102,6 +102,23 @@ def test_post_processors_vs_wheel(asset, prefix_space):
                      docs, f"{asset} {pp['type']} trim={pp.get('trim_offsets')} aps={pp.get('add_prefix_space')} special={special}")
 
 
+def test_candidate_start_inside_a_run_across_documents():
+    """the batch-wide prefilter must report EVERY candidate start: with the added token "  " and a document that ends
+    in a space, the next document's leading "  " is the second candidate of the run "   " (regression)"""
+    from helpers import added_token_entries
+    js = json.loads(asset_json("gpt2_style"))
+    js["added_tokens"] = added_token_entries(js["model"]["vocab"], [("  ", False, False, False, False, True)])
+    tid = js["added_tokens"][0]["id"]
+    mine = oracle_backed_tokenizer(json.dumps(js))
+    encs = mine.encode_batch(["a ", "  x>", "b", "   "], add_special_tokens=False)
+    assert encs[1].ids[0] == tid and encs[1].offsets[0] == (0, 2)
+    assert encs[3].ids[0] == tid and encs[3].offsets[:2] == [(0, 2), (2, 3)]
+    tk = wheel()
+    if tk is not None:
+        ref = tk.Tokenizer.from_str(json.dumps(js)).encode_batch(["a ", "  x>", "b", "   "], add_special_tokens=False)
+        _compare(_flat(encs), _flat(ref), ["a ", "  x>", "b", "   "], "boundary run")
+
+
 def _flat_full(encs):
     def one(e):
         return {"ids": list(e.ids), "offsets": [list(o) for o in e.offsets], "word_ids": list(e.word_ids), "type_ids": list(e.type_ids),

@@ -69,6 +69,15 @@ class AddedVocabulary:
         # prefilter keys: the first two bytes of every token (the whole token if it has one byte); a document without any
         # of them cannot hold an added token.  bytes.find is a C loop, unlike a regex alternation over the whole buffer
         self.keys = sorted({t.content.encode("utf-8")[:2] for t in by_content.values()})
+        alts = []
+        for b0 in sorted({k[:1] for k in self.keys}):
+            if b0 in self.keys:
+                alts.append(re.escape(b0))  # a one-byte token: every occurrence of the byte is a candidate
+            else:
+                # the second byte is a lookahead so that every candidate START is reported, also inside runs ("   " holds
+                # two candidates for the token "  ", and the first may belong to the previous document)
+                alts.append(re.escape(b0) + b"(?=[" + b"".join(re.escape(k[1:2]) for k in self.keys if k[:1] == b0) + b"])")
+        self.prefilter = re.compile(b"|".join(alts)) if alts else None
 
     @staticmethod
     def _compile(tokens):
@@ -156,24 +165,20 @@ def split_batch(av, data, doc_off):
     -> (row_off uint64[r+1], parts, cut) with parts[d] = None for an untouched document d, else
        (first_row, n_rows, [(id or None, row index or None, start, stop)])"""
     n_docs = len(doc_off) - 1
-    buf = data.tobytes() if isinstance(data, np.ndarray) else bytes(data)
+    arr = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
     parts = [None] * n_docs
-    if av is None or not av.keys:
+    if av is None or av.prefilter is None or arr.size == 0:
         return np.asarray(doc_off, dtype=np.uint64), parts, False
-    hits = []
-    for key in av.keys:
-        p = buf.find(key)
-        while p >= 0:
-            hits.append(p)
-            p = buf.find(key, p + 1)
-    if not hits:
+    # candidate positions: one pass of a two-byte-prefix regex over the buffer (no copy: re takes any bytes-like object;
+    # its literal-prefix scan runs at memchr speed when the first bytes are rare in the text)
+    pos = np.fromiter((m.start() for m in av.prefilter.finditer(memoryview(arr))), dtype=np.int64)
+    if pos.size == 0:
         return np.asarray(doc_off, dtype=np.uint64), parts, False
-    pos = np.asarray(hits, dtype=np.int64)
     docs = np.unique(np.searchsorted(np.asarray(doc_off, dtype=np.int64), pos, side="right") - 1)
     cuts = {}
     for d in docs.tolist():
         a, b = int(doc_off[d]), int(doc_off[d + 1])
-        sp = av.extract(buf[a:b])
+        sp = av.extract(arr[a:b].tobytes())
         if len(sp) == 1 and sp[0][0] is None:
             continue  # the candidate did not survive (e.g. single_word): the document stays one row
         cuts[d] = sp
@@ -208,7 +213,7 @@ def split_batch(av, data, doc_off):
 def stitch_rows(data, doc_off, parts, ids, offs, wid, row_ptr, byte_offsets):
     """Row CSR (engine output for `split_batch`'s rows) -> document CSR.  offs / wid may be None."""
     n_docs = len(doc_off) - 1
-    buf = data.tobytes() if isinstance(data, np.ndarray) else bytes(data)
+    arr = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
     o_ids, o_offs, o_wid = [], [], []
     added_at = []  # (index of the token in the output, absolute byte span) of every added token, for offset trimming
     rp = np.zeros(n_docs + 1, dtype=np.uint64)
@@ -235,9 +240,9 @@ def stitch_rows(data, doc_off, parts, ids, offs, wid, row_ptr, byte_offsets):
         for tid, r, a, b in plist:
             if byte_offsets:
                 ua, ub = a, b
-            else:
-                ua = len(buf[base:base + a].decode("utf-8", "replace"))
-                ub = ua + len(buf[base + a:base + b].decode("utf-8", "replace"))
+            else:  # characters = bytes that are not UTF-8 continuation bytes
+                ua = int(np.count_nonzero((arr[base:base + a] & 0xC0) != 0x80))
+                ub = ua + int(np.count_nonzero((arr[base + a:base + b] & 0xC0) != 0x80))
             if tid is not None:
                 o_ids.append(np.array([tid], dtype=np.uint32))
                 if offs is not None: o_offs.append(np.array([[ua, ub]], dtype=np.uint32))
