@@ -92,7 +92,7 @@ def test_post_processors_vs_wheel(asset, prefix_space):
     if tk is None:
         pytest.skip("reference wheel not importable")
     base = json.loads(with_added_tokens(_patched(asset, prefix_space)))
-    docs = added_token_docs(13, 600) + ["  two  spaces  ", " x", "x ", "   ", " <mask> y", "a  <both>  b"]
+    docs = added_token_docs(13, 300) + ["  two  spaces  ", " x", "x ", "   ", " <mask> y", "a  <both>  b"]
     for pp in _post_processors(base):
         js = dict(base, post_processor=pp)
         tj = json.dumps(js)
@@ -134,11 +134,11 @@ def test_truncation_and_padding_vs_wheel(asset, template):
         pytest.skip("reference wheel not importable")
     tj = with_added_tokens(asset_json(asset), template)
     ref, mine = tk.Tokenizer.from_str(tj), oracle_backed_tokenizer(tj)
-    docs = added_token_docs(17, 250) + ["", "a", "a b c d e f g h i j k l m n o p q r s t u v w x y z " * 3]
+    docs = added_token_docs(17, 150) + ["", "a", "a b c d e f g h i j k l m n o p q r s t u v w x y z " * 3]
     cases = [dict(max_length=8, stride=0, direction="right"), dict(max_length=8, stride=3, direction="right"),
              dict(max_length=7, stride=2, direction="left"), dict(max_length=3, stride=0, direction="left"),
              dict(max_length=16, stride=5, direction="right", strategy="only_first")]
-    pads = [None, dict(), dict(direction="left", pad_id=3, pad_type_id=1, pad_token="<pad>"), dict(length=12), dict(pad_to_multiple_of=8)]
+    pads = [None, dict(direction="left", pad_id=3, pad_type_id=1, pad_token="<pad>"), dict(length=12), dict(pad_to_multiple_of=8)]
     for ci, tc in enumerate(cases):
         for pi, pc in enumerate(pads):
             for t in (ref, mine):
