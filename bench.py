@@ -89,16 +89,16 @@ class ClockSampler:
             if len(f) < 8:
                 continue
             try:
-                sm.setdefault(int(f[0]), []).append(float(f[1])); mx.append(float(f[2]))
+                sm.setdefault(f[0], []).append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        med = {g: float(np.median(v)) for g, v in sorted(sm.items())}
+        med = {g: float(np.median(v)) for g, v in sorted(sm.items(), key=lambda kv: (len(kv[0]), kv[0]))}
         # sm_mhz: the slowest GPU's median under load (every rank's GPU is sampled, not only rank 0's)
         return {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": min((len(v) for v in sm.values()), default=0), "per_gpu_sm_mhz": [med[g] for g in sorted(med)]}
+                "samples": min((len(v) for v in sm.values()), default=0), "per_gpu_sm_mhz": list(med.values())}
 
 
 def cpu_reference_worker(cfg, threads, budget_s):
@@ -247,7 +247,9 @@ def main():
         return T
 
     names = (ctypes.c_char_p * 16)(); ms = (ctypes.c_float * 16)()
-    sampler = ClockSampler(range(world))  # one node: local ranks 0..world-1 are GPUs 0..world-1
+    # one node: local rank r runs on the r-th visible GPU (nvidia-smi does not honour CUDA_VISIBLE_DEVICES, so map it)
+    vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    sampler = ClockSampler(vis[:world] if len(vis) >= world else range(world))
     if rank == 0:
         sampler.start()  # samples every 50 ms from the warm-up through the timed device and e2e regions
     for _ in range(a.warmup):
