@@ -144,94 +144,109 @@ def parse_tokenizer_json(js):
 NO_WORD = 0xFFFFFFFF  # word id of a token the post-processor added (the reference reports None)
 
 
-class Encoding:
-    """One sequence of the batch CSR, with the attribute names of `tokenizers.Encoding`."""
-    __slots__ = ("_tok", "ids", "_offsets", "_word_ids", "_type_ids", "_special", "_attn", "_pad_token", "overflowing")
+class BatchEncoding:
+    """The whole batch as a CSR (numpy arrays copied out of the engine's pinned buffers).  `type_ids`,
+    `special_tokens_mask` and `attention_mask` are None unless a special-token template / padding was applied; tokens
+    those added carry offsets (0, 0) and word id NO_WORD."""
 
-    def __init__(self, tok, ids, offsets, word_ids, type_ids=None, special=None):
-        self._tok, self.ids, self._offsets, self._word_ids, self._type_ids, self._special = tok, ids, offsets, word_ids, type_ids, special
-        self._attn, self._pad_token, self.overflowing = None, None, []
+    def __init__(self, ids, offsets, word_ids, row_ptr, type_ids=None, special_tokens_mask=None, attention_mask=None):
+        self.ids, self.offsets, self.word_ids, self.row_ptr = ids, offsets, word_ids, row_ptr
+        self.type_ids, self.special_tokens_mask, self.attention_mask = type_ids, special_tokens_mask, attention_mask
+
+    @property
+    def n_tokens(self):
+        return int(self.row_ptr[-1])
+
+
+class Encoding:
+    """One row of a BatchEncoding with the attribute names of `tokenizers.Encoding` (bindings/python/src/encoding.rs:
+    133-225).  A view: the lists are made when an attribute is read, so a batch of millions of sequences costs nothing
+    for the attributes nobody looks at."""
+    __slots__ = ("_tok", "_be", "_a", "_b", "_pad_token", "overflowing")
+
+    def __init__(self, tok, be, row):
+        self._tok, self._be = tok, be
+        self._a, self._b = int(be.row_ptr[row]), int(be.row_ptr[row + 1])
+        self._pad_token, self.overflowing = None, []
 
     def __len__(self):
-        return len(self.ids)
+        return self._b - self._a
+
+    def _col(self, arr):
+        return None if arr is None else arr[self._a:self._b]
+
+    @property
+    def ids(self):
+        return self._be.ids[self._a:self._b].tolist()
 
     @property
     def offsets(self):
-        if self._offsets is None:
+        if self._be.offsets is None:
             raise ValueError("offsets were not requested (encode_batch_fast)")
-        return [tuple(x) for x in self._offsets.tolist()]
+        return [tuple(x) for x in self._be.offsets[self._a:self._b].tolist()]
 
     @property
     def word_ids(self):
-        if self._word_ids is None:
+        if self._be.word_ids is None:
             return None
-        return [None if w == NO_WORD else w for w in self._word_ids.tolist()]
+        return [None if w == NO_WORD else w for w in self._be.word_ids[self._a:self._b].tolist()]
 
     words = word_ids
 
     @property
     def tokens(self):
-        if self._attn is None:
-            return [self._tok.id_to_token(i) for i in self.ids]
-        return [self._tok.id_to_token(i) if m else self._pad_token for i, m in zip(self.ids, self._attn.tolist())]
+        ids, attn = self.ids, self._col(self._be.attention_mask)
+        if attn is None:
+            return [self._tok.id_to_token(i) for i in ids]
+        return [self._tok.id_to_token(i) if m else self._pad_token for i, m in zip(ids, attn.tolist())]
 
     @property
     def type_ids(self):
-        return [0] * len(self.ids) if self._type_ids is None else self._type_ids.tolist()
+        t = self._col(self._be.type_ids)
+        return [0] * len(self) if t is None else t.tolist()
 
     @property
     def attention_mask(self):
-        return [1] * len(self.ids) if self._attn is None else self._attn.tolist()
+        m = self._col(self._be.attention_mask)
+        return [1] * len(self) if m is None else m.tolist()
 
     @property
     def special_tokens_mask(self):
-        return [0] * len(self.ids) if self._special is None else self._special.tolist()
+        m = self._col(self._be.special_tokens_mask)
+        return [0] * len(self) if m is None else m.tolist()
 
     @property
     def sequence_ids(self):
-        if self._special is None:
-            return [0] * len(self.ids)
-        return [None if sp else 0 for sp in self._special.tolist()]
+        m = self._col(self._be.special_tokens_mask)
+        return [0] * len(self) if m is None else [None if sp else 0 for sp in m.tolist()]
 
     @property
     def n_sequences(self):
         return 1
 
     def _pad(self, target, pad_id, pad_type_id, pad_token, left):
-        """Encoding::pad (tokenizer/encoding.rs:465-560)"""
+        """Encoding::pad (tokenizer/encoding.rs:465-560): this row gets arrays of its own"""
         for o in self.overflowing:
             o._pad(target, pad_id, pad_type_id, pad_token, left)
-        k = target - len(self.ids)
+        n = len(self)
+        k = target - n
         if k <= 0:
             return
-        n = len(self.ids)
+        be = self._be
         cat = (lambda pad, x: np.concatenate([pad, x])) if left else (lambda pad, x: np.concatenate([x, pad]))
-        self._attn = cat(np.zeros(k, dtype=np.uint8), np.ones(n, dtype=np.uint8) if self._attn is None else self._attn)
-        self._special = cat(np.ones(k, dtype=np.uint8), np.zeros(n, dtype=np.uint8) if self._special is None else self._special)
-        self._type_ids = cat(np.full(k, pad_type_id, dtype=np.uint32), np.zeros(n, dtype=np.uint32) if self._type_ids is None else self._type_ids)
-        self.ids = [pad_id] * k + self.ids if left else self.ids + [pad_id] * k
-        if self._offsets is not None:
-            self._offsets = cat(np.zeros((k, 2), dtype=np.uint32), self._offsets)
-        if self._word_ids is not None:
-            self._word_ids = cat(np.full(k, NO_WORD, dtype=np.uint32), self._word_ids)
-        self._pad_token = pad_token
+        col = lambda arr, default: default if arr is None else arr[self._a:self._b]
+        self._be = BatchEncoding(
+            cat(np.full(k, pad_id, dtype=np.uint32), col(be.ids, None)),
+            None if be.offsets is None else cat(np.zeros((k, 2), dtype=np.uint32), col(be.offsets, None)),
+            None if be.word_ids is None else cat(np.full(k, NO_WORD, dtype=np.uint32), col(be.word_ids, None)),
+            np.array([0, target], dtype=np.uint64),
+            cat(np.full(k, pad_type_id, dtype=np.uint32), col(be.type_ids, np.zeros(n, dtype=np.uint32))),
+            cat(np.ones(k, dtype=np.uint8), col(be.special_tokens_mask, np.zeros(n, dtype=np.uint8))),
+            cat(np.zeros(k, dtype=np.uint8), col(be.attention_mask, np.ones(n, dtype=np.uint8))))
+        self._a, self._b, self._pad_token = 0, target, pad_token
 
     def __repr__(self):
-        return f"Encoding(num_tokens={len(self.ids)}, attributes=[ids, type_ids, tokens, offsets, attention_mask, special_tokens_mask, overflowing])"
-
-
-class BatchEncoding:
-    """The whole batch as a CSR (numpy arrays copied out of the engine's pinned buffers).  `type_ids` and
-    `special_tokens_mask` are None unless a special-token template was applied; tokens it added carry offsets (0, 0)
-    and word id NO_WORD."""
-
-    def __init__(self, ids, offsets, word_ids, row_ptr, type_ids=None, special_tokens_mask=None):
-        self.ids, self.offsets, self.word_ids, self.row_ptr = ids, offsets, word_ids, row_ptr
-        self.type_ids, self.special_tokens_mask = type_ids, special_tokens_mask
-
-    @property
-    def n_tokens(self):
-        return int(self.row_ptr[-1])
+        return f"Encoding(num_tokens={len(self)}, attributes=[ids, type_ids, tokens, offsets, attention_mask, special_tokens_mask, overflowing])"
 
 
 def trim_offsets(be, ld, tr, add_prefix_space):
@@ -554,14 +569,9 @@ class Tokenizer:
             be, cut, part_doc = truncate_csr(be, list(trim) if trim is not None else [], tr["max_length"] - n_added, tr["stride"], tr["direction"])
             trim = tuple(cut) if trim is not None else None
         be = self._finish(be, trim, add_special_tokens)
-        rp = be.row_ptr
         out, prev = [], -1
         for i in range(len(part_doc)):
-            a, b = int(rp[i]), int(rp[i + 1])
-            enc = Encoding(self, be.ids[a:b].tolist(), None if be.offsets is None else be.offsets[a:b],
-                           None if be.word_ids is None else be.word_ids[a:b],
-                           None if be.type_ids is None else be.type_ids[a:b],
-                           None if be.special_tokens_mask is None else be.special_tokens_mask[a:b])
+            enc = Encoding(self, be, i)
             if int(part_doc[i]) == prev:
                 out[-1].overflowing.append(enc)  # the parts of a truncated sequence follow its kept part
             else:
@@ -569,7 +579,7 @@ class Tokenizer:
         pd = self._padding
         if pd is not None and out:
             # utils/padding.rs:50-81 (the per-sequence padding of post_process step 3 is subsumed by the batch-level one)
-            target = pd["length"] if pd["length"] is not None else max(len(e.ids) for e in out)
+            target = pd["length"] if pd["length"] is not None else max(len(e) for e in out)
             m = pd["pad_to_multiple_of"]
             if m and target % m:
                 target += m - target % m
