@@ -164,10 +164,9 @@ class Encoding:
     for the attributes nobody looks at."""
     __slots__ = ("_tok", "_be", "_a", "_b", "_pad_token", "overflowing")
 
-    def __init__(self, tok, be, row):
-        self._tok, self._be = tok, be
-        self._a, self._b = int(be.row_ptr[row]), int(be.row_ptr[row + 1])
-        self._pad_token, self.overflowing = None, []
+    def __init__(self, tok, be, a, b):
+        self._tok, self._be, self._a, self._b = tok, be, a, b  # tokens [a, b) of be
+        self._pad_token, self.overflowing = None, ()           # overflowing: parts cut off by truncation (a list then)
 
     def __len__(self):
         return self._b - self._a
@@ -546,10 +545,10 @@ class Tokenizer:
         return lead, trail
 
     def _encode_list(self, docs, offsets, word_ids, add_special_tokens):
-        for d in docs:
-            if not isinstance(d, str):
-                raise UnsupportedConfig("only raw single sequences (str) are supported; pairs and pre-tokenized input are not")
-        bs = [d.encode("utf-8") for d in docs]
+        try:
+            bs = [d.encode("utf-8") for d in docs]
+        except AttributeError:
+            raise UnsupportedConfig("only raw single sequences (str) are supported; pairs and pre-tokenized input are not") from None
         joined = b"".join(bs)
         off = np.zeros(len(bs) + 1, dtype=np.uint64)
         if bs:
@@ -569,13 +568,17 @@ class Tokenizer:
             be, cut, part_doc = truncate_csr(be, list(trim) if trim is not None else [], tr["max_length"] - n_added, tr["stride"], tr["direction"])
             trim = tuple(cut) if trim is not None else None
         be = self._finish(be, trim, add_special_tokens)
-        out, prev = [], -1
-        for i in range(len(part_doc)):
-            enc = Encoding(self, be, i)
-            if int(part_doc[i]) == prev:
-                out[-1].overflowing.append(enc)  # the parts of a truncated sequence follow its kept part
-            else:
-                out.append(enc); prev = int(part_doc[i])
+        rp = be.row_ptr.tolist()
+        if tr is None:
+            out = [Encoding(self, be, a, b) for a, b in zip(rp[:-1], rp[1:])]
+        else:
+            out, prev = [], -1
+            for i, d in enumerate(part_doc.tolist()):
+                enc = Encoding(self, be, rp[i], rp[i + 1])
+                if d == prev:
+                    out[-1].overflowing = list(out[-1].overflowing) + [enc]  # the parts of a truncated sequence follow its kept part
+                else:
+                    out.append(enc); prev = d
         pd = self._padding
         if pd is not None and out:
             # utils/padding.rs:50-81 (the per-sequence padding of post_process step 3 is subsumed by the batch-level one)
