@@ -215,3 +215,31 @@ def test_gpu_decreasing_doc_off_is_rejected():
     res = ctypes.c_void_p()
     rc = _lib.lib().b2t_encode_batch(tok.handle, data.ctypes.data, off.ctypes.data, 3, _lib.WANT_OFFSETS, ctypes.byref(res))
     assert rc == _lib.B2T_ERR_INVALID and b"non-decreasing" in _lib.lib().b2t_last_error()
+
+
+@pytest.mark.parametrize("asset", ["gpt2_style", "wordpiece"])
+def test_pretokenized_input_vs_wheel(asset):
+    """is_pretokenized=True (tokenizer/mod.rs:762-805): words are encoded one by one, offsets stay relative to the word,
+    word ids are the word's index -- with added tokens, a template, truncation and padding on top"""
+    tk = wheel()
+    if tk is None:
+        pytest.skip("reference wheel not importable")
+    import random
+    from fuzzgen import rand_doc
+    rng = random.Random(3)
+    tj = with_added_tokens(_patched(asset, True if asset == "gpt2_style" else None), True)
+    ref, mine = tk.Tokenizer.from_str(tj), oracle_backed_tokenizer(tj)
+    pool = ["hello", "world", "don't", "<mask>", " x", "", "a<|endoftext|>b", "tok", "Zürich", "  ", "multi word item", "日本語", "1234567", "wörd"]
+    seqs = [[]] + [[rng.choice(pool) if rng.random() < 0.6 else rand_doc(rng, 5) for _ in range(rng.randint(0, 9))] for _ in range(300)]
+    for special in (False, True):
+        _compare(_flat(mine.encode_batch(seqs, is_pretokenized=True, add_special_tokens=special)),
+                 _flat(ref.encode_batch(seqs, is_pretokenized=True, add_special_tokens=special)), seqs, f"{asset} pretokenized special={special}")
+    for t in (ref, mine):
+        t.enable_truncation(max_length=6, stride=2)
+        t.enable_padding(pad_to_multiple_of=4)
+    _compare(_flat_full(mine.encode_batch(seqs, is_pretokenized=True)), _flat_full(ref.encode_batch(seqs, is_pretokenized=True)), seqs,
+             f"{asset} pretokenized + truncation + padding")
+    e = mine.encode(["hello", "world"], is_pretokenized=True)
+    assert e.ids == list(ref.encode(["hello", "world"], is_pretokenized=True).ids)
+    with pytest.raises(TypeError):
+        mine.encode_batch(["not a list of words"], is_pretokenized=True)

@@ -544,19 +544,36 @@ class Tokenizer:
         trail = next((k for k, c in enumerate(reversed(t)) if not ws(c)), len(t))
         return lead, trail
 
-    def _encode_list(self, docs, offsets, word_ids, add_special_tokens):
+    def _encode_list(self, docs, offsets, word_ids, add_special_tokens, is_pretokenized=False):
+        seq_rows = None
+        if is_pretokenized:
+            # tokenizer/mod.rs:762-805: every word of a pre-tokenized sequence is encoded on its own (added tokens,
+            # pre-tokenizer, model), its tokens keep offsets relative to the word and all get the word's index
+            if any(isinstance(d, str) for d in docs):
+                raise TypeError("is_pretokenized=True expects sequences of words (List[str]), not str")
+            seq_rows = np.zeros(len(docs) + 1, dtype=np.int64)
+            if docs:
+                np.cumsum(np.fromiter(map(len, docs), dtype=np.int64, count=len(docs)), out=seq_rows[1:])
+            docs = [w for d in docs for w in d]
         try:
             bs = [d.encode("utf-8") for d in docs]
         except AttributeError:
-            raise UnsupportedConfig("only raw single sequences (str) are supported; pairs and pre-tokenized input are not") from None
+            raise UnsupportedConfig("only raw sequences (str), or lists of words with is_pretokenized=True, are supported; pairs are not") from None
         joined = b"".join(bs)
         off = np.zeros(len(bs) + 1, dtype=np.uint64)
         if bs:
             np.cumsum(np.fromiter(map(len, bs), dtype=np.int64, count=len(bs)), out=off[1:])
         flags = (_lib.WANT_OFFSETS if offsets else 0) | (_lib.WANT_WORD_IDS if word_ids else 0)
         be, trim = self._encode_core(np.frombuffer(joined, dtype=np.uint8), off, flags, joined, True)
+        if seq_rows is not None:  # rows (words) -> sequences
+            wid = None
+            if be.word_ids is not None:
+                counts = np.diff(be.row_ptr).astype(np.int64)
+                word_in_seq = np.arange(len(docs), dtype=np.int64) - np.repeat(seq_rows[:-1], np.diff(seq_rows))
+                wid = np.repeat(word_in_seq, counts).astype(np.uint32)
+            be = BatchEncoding(be.ids, be.offsets, wid, be.row_ptr[seq_rows])
         # TokenizerImpl::post_process (tokenizer/mod.rs:1265-1317): 1. truncate, 2. post-processor, 3. pad
-        part_doc = np.arange(len(docs), dtype=np.int64)
+        part_doc = np.arange(len(be.row_ptr) - 1, dtype=np.int64)
         tr = self._truncation
         if tr is not None:
             if tr["strategy"] == "only_second":
@@ -592,20 +609,16 @@ class Tokenizer:
 
     def encode_batch(self, input, is_pretokenized=False, add_special_tokens=True):
         """tokenizer.rs:1312-1340 -> TokenizerImpl::encode_batch_char_offsets (tokenizer/mod.rs:1360-1379)."""
-        if is_pretokenized:
-            raise UnsupportedConfig("is_pretokenized=True is not on the accelerated path")
-        return self._encode_list(list(input), True, True, add_special_tokens)
+        return self._encode_list(list(input), True, True, add_special_tokens, is_pretokenized)
 
     def encode_batch_fast(self, input, is_pretokenized=False, add_special_tokens=True):
         """tokenizer.rs:1433-1461 -> encode_batch_fast (tokenizer/mod.rs:1382-1401): ids only."""
-        if is_pretokenized:
-            raise UnsupportedConfig("is_pretokenized=True is not on the accelerated path")
-        return self._encode_list(list(input), False, False, add_special_tokens)
+        return self._encode_list(list(input), False, False, add_special_tokens, is_pretokenized)
 
     def encode(self, sequence, pair=None, is_pretokenized=False, add_special_tokens=True):
-        if pair is not None or is_pretokenized:
-            raise UnsupportedConfig("pairs / pre-tokenized input are not on the accelerated path")
-        return self._encode_list([sequence], True, True, add_special_tokens)[0]
+        if pair is not None:
+            raise UnsupportedConfig("pairs of sequences are not on the accelerated path")
+        return self._encode_list([sequence], True, True, add_special_tokens, is_pretokenized)[0]
 
     def pre_tokenize_batch(self, docs):
         """PreTokenizer seam: per document the list of (start_byte, end_byte) of its splits."""
