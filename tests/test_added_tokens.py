@@ -170,7 +170,9 @@ def test_unsupported_post_processors():
         parse_tokenizer_json(js)  # offset trimming is defined on the byte-level alphabet
     js = json.loads(asset_json("gpt2_style"))
     js["post_processor"] = {"type": "RobertaProcessing", "sep": ["</s>", 2], "cls": ["<s>", 0], "trim_offsets": False, "add_prefix_space": False}
-    assert parse_tokenizer_json(js)["template"] == {"pre": [(0, 0)], "post": [(2, 0)], "type_id": 0, "trim": None}
+    t = parse_tokenizer_json(js)["template"]
+    assert (t["pre"], t["post"], t["type_id"], t["trim"]) == ([(0, 0)], [(2, 0)], 0, None)
+    assert t["pair"] == [("special", 0, 0), ("seq", 0, 0), ("special", 2, 0), ("special", 2, 0), ("seq", 1, 0), ("special", 2, 0)]
     js["post_processor"] = {"type": "Sequence", "processors": [{"type": "ByteLevel", "trim_offsets": False},
                                                                {"type": "BertProcessing", "sep": ["[SEP]", 102], "cls": ["[CLS]", 101]}]}
     assert parse_tokenizer_json(js)["template"]["pre"] == [(101, 0)]
@@ -243,3 +245,62 @@ def test_pretokenized_input_vs_wheel(asset):
     assert e.ids == list(ref.encode(["hello", "world"], is_pretokenized=True).ids)
     with pytest.raises(TypeError):
         mine.encode_batch(["not a list of words"], is_pretokenized=True)
+
+
+def _pair_processors(js):
+    by = {e["content"]: e["id"] for e in js["added_tokens"]}
+    cls, sep = ["<|endoftext|>", by["<|endoftext|>"]], ["<mask>", by["<mask>"]]
+    sp = {"<a>": {"id": "<a>", "ids": [by["<a>"]], "tokens": ["<a>"]}, "<b>": {"id": "<b>", "ids": [by["<a><b>"], by["<a>"]], "tokens": ["<a><b>", "<a>"]}}
+    tmpl = {"type": "TemplateProcessing",
+            "single": [{"SpecialToken": {"id": "<a>", "type_id": 0}}, {"Sequence": {"id": "A", "type_id": 0}}],
+            "pair": [{"SpecialToken": {"id": "<a>", "type_id": 0}}, {"Sequence": {"id": "A", "type_id": 0}}, {"SpecialToken": {"id": "<b>", "type_id": 1}},
+                     {"Sequence": {"id": "B", "type_id": 1}}, {"SpecialToken": {"id": "<a>", "type_id": 1}}],
+            "special_tokens": sp}
+    return [None, {"type": "ByteLevel", "add_prefix_space": True, "trim_offsets": True, "use_regex": True},
+            {"type": "BertProcessing", "sep": sep, "cls": cls}, {"type": "RobertaProcessing", "sep": sep, "cls": cls, "trim_offsets": True, "add_prefix_space": False},
+            tmpl, {"type": "Sequence", "processors": [{"type": "ByteLevel", "add_prefix_space": False, "trim_offsets": True, "use_regex": True}, tmpl]}]
+
+
+def test_pairs_vs_wheel():
+    """EncodeInput::Dual: both sequences through the engine, then truncation strategies, the pair templates and the merge
+    with every combination of overflowing parts (pairs.py), padding -- against the reference, mixed with single inputs"""
+    tk = wheel()
+    if tk is None:
+        pytest.skip("reference wheel not importable")
+    import random
+    rng = random.Random(8)
+    base = json.loads(with_added_tokens(_patched("gpt2_style", True)))
+    texts = added_token_docs(31, 120) + ["", "a", "a b c d e f g h i j k l m n o p", "  x  "]
+    inputs = [(rng.choice(texts), rng.choice(texts)) if rng.random() < 0.7 else rng.choice(texts) for _ in range(45)] + [("", ""), ("a", ""), ("", "b")]
+    truncs = [None, dict(max_length=12, stride=0), dict(max_length=9, stride=2, direction="left"), dict(max_length=11, stride=3, strategy="only_first"),
+              dict(max_length=14, stride=1, strategy="only_second"), dict(max_length=7, stride=1, strategy="longest_first")]
+    for pi, pp in enumerate(_pair_processors(base)):
+        tj = json.dumps(dict(base, post_processor=pp))
+        ref, mine = tk.Tokenizer.from_str(tj), oracle_backed_tokenizer(tj)
+        for ti, tc in enumerate(truncs):
+            for t in (ref, mine):
+                t.no_truncation() if tc is None else t.enable_truncation(**tc)
+                t.enable_padding(pad_to_multiple_of=4) if (ti + pi) % 3 == 0 else t.no_padding()
+            for special in (False, True):
+                # some (input, setting) combinations are errors in the reference (a strategy that cannot shorten the input
+                # enough, a stride that no longer fits once the special tokens are subtracted): they must be errors here too
+                batch = inputs
+                try:
+                    exp = _flat_full(ref.encode_batch(batch, add_special_tokens=special))
+                except BaseException:
+                    batch = []
+                    for x in inputs:
+                        args = (x,) if isinstance(x, str) else x
+                        try:
+                            ref.encode(*args, add_special_tokens=special)
+                            batch.append(x)
+                        except BaseException:
+                            with pytest.raises(ValueError):
+                                mine.encode(*args, add_special_tokens=special)
+                    exp = _flat_full(ref.encode_batch(batch, add_special_tokens=special))
+                got = _flat_full(mine.encode_batch(batch, add_special_tokens=special))
+                _compare(got, exp, batch, f"pairs pp={pp and pp['type']} trunc={tc} special={special}")
+        for t in (ref, mine):
+            t.no_truncation(); t.no_padding()
+        e_ref, e_mine = ref.encode("hello world", "x <mask> y"), mine.encode("hello world", "x <mask> y")
+        assert e_mine.sequence_ids == e_ref.sequence_ids and e_mine.n_sequences == e_ref.n_sequences and e_mine.type_ids == e_ref.type_ids

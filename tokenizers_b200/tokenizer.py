@@ -9,7 +9,7 @@ mirrored here: added-token extraction before it (`added.py`) and the special-tok
 """
 import ctypes, json
 import numpy as np
-from . import _lib, added
+from . import _lib, added, pairs
 from ._lib import B2TError
 
 LLAMA3_PATTERN = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*"
@@ -30,15 +30,27 @@ def _pack(strings):
 
 def parse_post_processor(pp):
     """post_processor of tokenizer.json -> None (nothing to do) or
-    {"pre": [(id, type_id)], "post": [...], "type_id": t, "trim": None | add_prefix_space} for SINGLE sequences
+    {"pre": [(id, type_id)], "post": [...], "type_id": t, "trim": None | add_prefix_space, "single": pieces, "pair": pieces}
     (processors/template.rs:646-, processors/bert.rs, processors/roberta.rs, processors/sequence.rs;
-    "trim": ByteLevel / Roberta `trim_offsets`, pre_tokenizers/byte_level.rs:174-234)."""
+    "trim": ByteLevel / Roberta `trim_offsets`, pre_tokenizers/byte_level.rs:174-234).  pre / post / type_id describe
+    the single-sequence template for the vectorised CSR path; `single` / `pair` are the same templates as piece lists
+    [("seq", 0 | 1, type_id) | ("special", token id, type_id)] for the per-input path that handles pairs."""
     if pp is None:
         return None
     ty = pp.get("type")
-    none = {"pre": [], "post": [], "type_id": 0, "trim": None}
+
+    def from_pieces(single, pair, trim):
+        pre, post, seen, seq_type = [], [], False, 0
+        for kind, v, t in single:
+            if kind == "seq":
+                seen, seq_type = True, t
+            else:
+                (post if seen else pre).append((v, t))
+        return {"pre": pre, "post": post, "type_id": seq_type, "trim": trim, "single": single, "pair": pair}
+
+    plain = ([("seq", 0, 0)], [("seq", 0, 0), ("seq", 1, 1)])
     if ty == "ByteLevel":
-        return dict(none, trim=bool(pp.get("add_prefix_space", True))) if pp.get("trim_offsets", True) else None
+        return from_pieces(plain[0], plain[1], bool(pp.get("add_prefix_space", True))) if pp.get("trim_offsets", True) else None
     if ty == "Sequence":
         out = None
         for sub in pp.get("processors", []):
@@ -53,22 +65,34 @@ def parse_post_processor(pp):
                 out = dict(t, trim=out["trim"] if t["trim"] is None else t["trim"])
         return out
     if ty in ("BertProcessing", "RobertaProcessing"):
-        trim = bool(pp.get("add_prefix_space", True)) if ty == "RobertaProcessing" and pp.get("trim_offsets", True) else None
-        return {"pre": [(int(pp["cls"][1]), 0)], "post": [(int(pp["sep"][1]), 0)], "type_id": 0, "trim": trim}
+        cls, sep = int(pp["cls"][1]), int(pp["sep"][1])
+        if ty == "BertProcessing":
+            single = [("special", cls, 0), ("seq", 0, 0), ("special", sep, 0)]
+            pair = single + [("seq", 1, 1), ("special", sep, 1)]
+            return from_pieces(single, pair, None)
+        trim = bool(pp.get("add_prefix_space", True)) if pp.get("trim_offsets", True) else None
+        single = [("special", cls, 0), ("seq", 0, 0), ("special", sep, 0)]
+        pair = single + [("special", sep, 0), ("seq", 1, 0), ("special", sep, 0)]
+        return dict(from_pieces(single, pair, trim), overflow_type=0)  # roberta.rs: type id 0 everywhere, overflowing parts too
     if ty == "TemplateProcessing":
-        pre, post, seen, seq_type = [], [], False, 0
-        for piece in pp.get("single", []):
-            if "Sequence" in piece:
-                if seen or piece["Sequence"].get("id") != "A":
-                    raise UnsupportedConfig("TemplateProcessing.single must contain sequence A exactly once")
-                seen, seq_type = True, int(piece["Sequence"].get("type_id", 0))
-            else:
-                sp = piece["SpecialToken"]
-                ids = pp["special_tokens"][sp["id"]]["ids"]
-                (post if seen else pre).extend((int(i), int(sp.get("type_id", 0))) for i in ids)
-        if not seen:
-            raise UnsupportedConfig("TemplateProcessing.single without a sequence")
-        return {"pre": pre, "post": post, "type_id": seq_type, "trim": None}
+        def pieces(tpl):
+            out, seen = [], set()
+            for piece in tpl:
+                if "Sequence" in piece:
+                    i = 0 if piece["Sequence"].get("id") == "A" else 1
+                    if i in seen:
+                        raise UnsupportedConfig("a template may use each sequence once")
+                    seen.add(i)
+                    out.append(("seq", i, int(piece["Sequence"].get("type_id", 0))))
+                else:
+                    sp = piece["SpecialToken"]
+                    out.extend(("special", int(i), int(sp.get("type_id", 0))) for i in pp["special_tokens"][sp["id"]]["ids"])
+            return out, seen
+        single, seen1 = pieces(pp.get("single", []))
+        pair, seen2 = pieces(pp.get("pair", []))
+        if seen1 != {0}:
+            raise UnsupportedConfig("TemplateProcessing.single must contain sequence A exactly once")
+        return from_pieces(single, pair if seen2 == {0, 1} else None, None)
     raise UnsupportedConfig(f"post-processor {ty} is not supported")
 
 
@@ -149,9 +173,10 @@ class BatchEncoding:
     `special_tokens_mask` and `attention_mask` are None unless a special-token template / padding was applied; tokens
     those added carry offsets (0, 0) and word id NO_WORD."""
 
-    def __init__(self, ids, offsets, word_ids, row_ptr, type_ids=None, special_tokens_mask=None, attention_mask=None):
+    def __init__(self, ids, offsets, word_ids, row_ptr, type_ids=None, special_tokens_mask=None, attention_mask=None, sequence_ids=None):
         self.ids, self.offsets, self.word_ids, self.row_ptr = ids, offsets, word_ids, row_ptr
         self.type_ids, self.special_tokens_mask, self.attention_mask = type_ids, special_tokens_mask, attention_mask
+        self.sequence_ids = sequence_ids  # int8, -1 = none (special / pad token); only set for pairs of sequences
 
     @property
     def n_tokens(self):
@@ -216,12 +241,16 @@ class Encoding:
 
     @property
     def sequence_ids(self):
+        q = self._col(self._be.sequence_ids)
+        if q is not None:
+            return [None if v < 0 else v for v in q.tolist()]
         m = self._col(self._be.special_tokens_mask)
         return [0] * len(self) if m is None else [None if sp else 0 for sp in m.tolist()]
 
     @property
     def n_sequences(self):
-        return 1
+        q = self._col(self._be.sequence_ids)
+        return 1 if q is None or q.size == 0 else max(int(q.max()) + 1, 1)
 
     def _pad(self, target, pad_id, pad_type_id, pad_token, left):
         """Encoding::pad (tokenizer/encoding.rs:465-560): this row gets arrays of its own"""
@@ -241,7 +270,8 @@ class Encoding:
             np.array([0, target], dtype=np.uint64),
             cat(np.full(k, pad_type_id, dtype=np.uint32), col(be.type_ids, np.zeros(n, dtype=np.uint32))),
             cat(np.ones(k, dtype=np.uint8), col(be.special_tokens_mask, np.zeros(n, dtype=np.uint8))),
-            cat(np.zeros(k, dtype=np.uint8), col(be.attention_mask, np.ones(n, dtype=np.uint8))))
+            cat(np.zeros(k, dtype=np.uint8), col(be.attention_mask, np.ones(n, dtype=np.uint8))),
+            None if be.sequence_ids is None else cat(np.full(k, -1, dtype=np.int8), col(be.sequence_ids, None)))
         self._a, self._b, self._pad_token = 0, target, pad_token
 
     def __repr__(self):
@@ -544,7 +574,72 @@ class Tokenizer:
         trail = next((k for k, c in enumerate(reversed(t)) if not ws(c)), len(t))
         return lead, trail
 
+    def _pad_all(self, out):
+        """pad_encodings (utils/padding.rs:50-81); the per-sequence padding of post_process step 3 is subsumed by it"""
+        pd = self._padding
+        if pd is not None and out:
+            target = pd["length"] if pd["length"] is not None else max(len(e) for e in out)
+            m = pd["pad_to_multiple_of"]
+            if m and target % m:
+                target += m - target % m
+            for e in out:
+                e._pad(target, pd["pad_id"], pd["pad_type_id"], pd["pad_token"], pd["direction"] == "left")
+        return out
+
+    def _encode_pairs(self, inputs, offsets, word_ids, add_special_tokens):
+        """Batches with pairs of sequences: the engine encodes every sequence as a row of its own; truncation, the
+        post-processor and the merge of the two halves (with all combinations of their overflowing parts) follow the
+        reference one input at a time (pairs.py)."""
+        seqs, first = [], []
+        for x in inputs:
+            first.append(len(seqs))
+            if isinstance(x, str):
+                seqs.append(x)
+            elif isinstance(x, (tuple, list)) and len(x) == 2 and all(isinstance(t, str) for t in x):
+                seqs.extend(x)
+            else:
+                raise UnsupportedConfig("inputs must be str or a pair (str, str)")
+        first.append(len(seqs))
+        bs = [d.encode("utf-8") for d in seqs]
+        joined = b"".join(bs)
+        off = np.zeros(len(bs) + 1, dtype=np.uint64)
+        if bs:
+            np.cumsum(np.fromiter(map(len, bs), dtype=np.int64, count=len(bs)), out=off[1:])
+        be, trim = self._encode_core(np.frombuffer(joined, dtype=np.uint8), off, _lib.WANT_OFFSETS | _lib.WANT_WORD_IDS, joined, True)
+        rp = be.row_ptr.tolist()
+        ids, offs, wid = be.ids.tolist(), [tuple(o) for o in be.offsets.tolist()], be.word_ids.tolist()
+        ld, tr = (trim[0].tolist(), trim[1].tolist()) if trim is not None else (None, None)
+
+        def pe(row, type_id):
+            a, b = rp[row], rp[row + 1]
+            n = b - a
+            return pairs.PE(ids[a:b], [type_id] * n, wid[a:b], offs[a:b], [0] * n, [1] * n, [type_id] * n,
+                            None if ld is None else ld[a:b], None if tr is None else tr[a:b])
+
+        def to_encoding(p):
+            n = len(p)
+            one = BatchEncoding(np.asarray(p.ids, dtype=np.uint32),
+                                np.asarray(p.offsets, dtype=np.uint32).reshape(-1, 2) if offsets else None,
+                                np.asarray([NO_WORD if w is None else w for w in p.words], dtype=np.uint32) if word_ids else None,
+                                np.array([0, n], dtype=np.uint64), np.asarray(p.type_ids, dtype=np.uint32),
+                                np.asarray(p.special, dtype=np.uint8), None,
+                                np.asarray([-1 if q is None else q for q in p.seq], dtype=np.int8))
+            e = Encoding(self, one, 0, n)
+            if p.overflowing:
+                e.overflowing = [to_encoding(o) for o in p.overflowing]
+            return e
+
+        out = []
+        for i in range(len(inputs)):
+            r = first[i]
+            a = pe(r, 0)
+            b = pe(r + 1, 1) if first[i + 1] - r == 2 else None
+            out.append(to_encoding(pairs.post_process(a, b, self._template, self._truncation, add_special_tokens)))
+        return self._pad_all(out)
+
     def _encode_list(self, docs, offsets, word_ids, add_special_tokens, is_pretokenized=False):
+        if not is_pretokenized and any(not isinstance(d, str) for d in docs):
+            return self._encode_pairs(docs, offsets, word_ids, add_special_tokens)
         seq_rows = None
         if is_pretokenized:
             # tokenizer/mod.rs:762-805: every word of a pre-tokenized sequence is encoded on its own (added tokens,
@@ -576,12 +671,12 @@ class Tokenizer:
         part_doc = np.arange(len(be.row_ptr) - 1, dtype=np.int64)
         tr = self._truncation
         if tr is not None:
-            if tr["strategy"] == "only_second":
-                raise ValueError("Truncation error: Second sequence not provided")
             tp = self._template
             n_added = len(tp["pre"]) + len(tp["post"]) if (add_special_tokens and tp is not None) else 0
             if tr["max_length"] < n_added:
                 raise ValueError("truncation max_length is smaller than the number of special tokens the post-processor adds")
+            if tr["strategy"] == "only_second" and np.any(np.diff(be.row_ptr).astype(np.int64) > tr["max_length"] - n_added):
+                raise ValueError("Truncation error: Second sequence not provided")
             be, cut, part_doc = truncate_csr(be, list(trim) if trim is not None else [], tr["max_length"] - n_added, tr["stride"], tr["direction"])
             trim = tuple(cut) if trim is not None else None
         be = self._finish(be, trim, add_special_tokens)
@@ -596,16 +691,7 @@ class Tokenizer:
                     out[-1].overflowing = list(out[-1].overflowing) + [enc]  # the parts of a truncated sequence follow its kept part
                 else:
                     out.append(enc); prev = d
-        pd = self._padding
-        if pd is not None and out:
-            # utils/padding.rs:50-81 (the per-sequence padding of post_process step 3 is subsumed by the batch-level one)
-            target = pd["length"] if pd["length"] is not None else max(len(e) for e in out)
-            m = pd["pad_to_multiple_of"]
-            if m and target % m:
-                target += m - target % m
-            for e in out:
-                e._pad(target, pd["pad_id"], pd["pad_type_id"], pd["pad_token"], pd["direction"] == "left")
-        return out
+        return self._pad_all(out)
 
     def encode_batch(self, input, is_pretokenized=False, add_special_tokens=True):
         """tokenizer.rs:1312-1340 -> TokenizerImpl::encode_batch_char_offsets (tokenizer/mod.rs:1360-1379)."""
@@ -617,7 +703,9 @@ class Tokenizer:
 
     def encode(self, sequence, pair=None, is_pretokenized=False, add_special_tokens=True):
         if pair is not None:
-            raise UnsupportedConfig("pairs of sequences are not on the accelerated path")
+            if is_pretokenized:
+                raise UnsupportedConfig("pre-tokenized pairs are not supported")
+            return self._encode_list([(sequence, pair)], True, True, add_special_tokens)[0]
         return self._encode_list([sequence], True, True, add_special_tokens, is_pretokenized)[0]
 
     def pre_tokenize_batch(self, docs):
