@@ -58,6 +58,7 @@ def test_byte_offsets_and_fast_vs_wheel():
     full = mine.encode_batch(docs, add_special_tokens=True)
     fast = mine.encode_batch_fast(docs, add_special_tokens=True)
     assert [e.ids for e in full] == [e.ids for e in fast]
+    _compare(_flat(fast), _flat(tk.Tokenizer.from_str(tj).encode_batch_fast(docs, add_special_tokens=True)), docs, "encode_batch_fast")
     # byte offsets of the CSR entry point == char offsets mapped through the document's UTF-8 encoding
     data = np.frombuffer("".join(docs).encode("utf-8"), dtype=np.uint8)
     off = np.zeros(len(docs) + 1, dtype=np.uint64)

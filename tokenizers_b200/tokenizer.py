@@ -205,14 +205,14 @@ class Encoding:
 
     @property
     def offsets(self):
-        if self._be.offsets is None:
-            raise ValueError("offsets were not requested (encode_batch_fast)")
+        if self._be.offsets is None:  # encode_batch_fast (OffsetType::None): the reference reports (0, 0) everywhere
+            return [(0, 0)] * len(self)
         return [tuple(x) for x in self._be.offsets[self._a:self._b].tolist()]
 
     @property
     def word_ids(self):
-        if self._be.word_ids is None:
-            return None
+        if self._be.word_ids is None:  # encode_batch_fast: no word indices either
+            return [None] * len(self)
         return [None if w == NO_WORD else w for w in self._be.word_ids[self._a:self._b].tolist()]
 
     words = word_ids
