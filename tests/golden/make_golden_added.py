@@ -10,7 +10,7 @@ import tokenizers  # noqa: E402
 
 def flat(encs):
     return [{"ids": list(e.ids), "offsets": [list(o) for o in e.offsets], "word_ids": list(e.word_ids),
-             "type_ids": list(e.type_ids), "special": list(e.special_tokens_mask)} for e in encs]
+             "type_ids": list(e.type_ids), "special": list(e.special_tokens_mask), "tokens": list(e.tokens)} for e in encs]
 
 
 configs = []

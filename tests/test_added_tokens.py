@@ -16,9 +16,9 @@ def _patched(asset, prefix_space=None):
     return json.dumps(js)
 
 
-def _flat(encs):
+def _flat(encs, tokens=True):
     return [{"ids": list(e.ids), "offsets": [list(o) for o in e.offsets], "word_ids": list(e.word_ids),
-             "type_ids": list(e.type_ids), "special": list(e.special_tokens_mask)} for e in encs]
+             "type_ids": list(e.type_ids), "special": list(e.special_tokens_mask), "tokens": list(e.tokens) if tokens else None} for e in encs]
 
 
 def _compare(got, exp, docs, what):
@@ -58,7 +58,8 @@ def test_byte_offsets_and_fast_vs_wheel():
     full = mine.encode_batch(docs, add_special_tokens=True)
     fast = mine.encode_batch_fast(docs, add_special_tokens=True)
     assert [e.ids for e in full] == [e.ids for e in fast]
-    _compare(_flat(fast), _flat(tk.Tokenizer.from_str(tj).encode_batch_fast(docs, add_special_tokens=True)), docs, "encode_batch_fast")
+    # (token texts are not compared: without offsets the reference reports '' for added tokens found in the text)
+    _compare(_flat(fast, False), _flat(tk.Tokenizer.from_str(tj).encode_batch_fast(docs, add_special_tokens=True), False), docs, "encode_batch_fast")
     # byte offsets of the CSR entry point == char offsets mapped through the document's UTF-8 encoding
     data = np.frombuffer("".join(docs).encode("utf-8"), dtype=np.uint8)
     off = np.zeros(len(docs) + 1, dtype=np.uint64)
@@ -123,7 +124,8 @@ def test_candidate_start_inside_a_run_across_documents():
 def _flat_full(encs):
     def one(e):
         return {"ids": list(e.ids), "offsets": [list(o) for o in e.offsets], "word_ids": list(e.word_ids), "type_ids": list(e.type_ids),
-                "special": list(e.special_tokens_mask), "attention": list(e.attention_mask), "overflowing": [one(o) for o in e.overflowing]}
+                "special": list(e.special_tokens_mask), "attention": list(e.attention_mask), "tokens": list(e.tokens),
+                "overflowing": [one(o) for o in e.overflowing]}
     return [one(e) for e in encs]
 
 
@@ -156,9 +158,9 @@ def test_truncation_and_padding_vs_wheel(asset, template):
     ref, mine = tk.Tokenizer.from_str(json.dumps(js)), oracle_backed_tokenizer(json.dumps(js))
     assert mine.truncation == ref.truncation and mine.padding["length"] == 14
     _compare(_flat_full(mine.encode_batch(docs)), _flat_full(ref.encode_batch(docs)), docs, "settings from tokenizer.json")
-    # (known difference: the text of an lstrip / rstrip token is its matched span in the reference, its content here)
-    plain = [d for d in docs if not any(t in d for t in ("<mask>", "[SEP2]", "<both>", "wörd"))][:80]
-    assert [e.tokens for e in mine.encode_batch(plain)] == [e.tokens for e in ref.encode_batch(plain)]
+    def toks(encs):  # the text of an lstrip / rstrip token is its matched span (Token::new(id, value, ..), added_vocabulary.rs:508)
+        return [(e.tokens, [o.tokens for o in e.overflowing]) for e in encs]
+    assert toks(mine.encode_batch(docs)) == toks(ref.encode_batch(docs))
     ref.no_truncation(); mine.no_truncation()
     _compare(_flat_full(mine.encode_batch(docs)), _flat_full(ref.encode_batch(docs)), docs, "padding only")
 

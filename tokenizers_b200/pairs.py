@@ -17,11 +17,12 @@ import copy
 class PE:
     """A plain-Python Encoding.  words: None for special tokens; seq: index of the sequence a token belongs to or None;
     ld / tr: leading / trailing space counts of the token's text (for offset trimming), or None."""
-    __slots__ = ("ids", "type_ids", "words", "offsets", "special", "attn", "seq", "ld", "tr", "overflowing")
+    __slots__ = ("ids", "type_ids", "words", "offsets", "special", "attn", "seq", "text", "ld", "tr", "overflowing")
 
     def __init__(self, ids=(), type_ids=(), words=(), offsets=(), special=(), attn=(), seq=(), ld=None, tr=None):
         self.ids, self.type_ids, self.words, self.offsets = list(ids), list(type_ids), list(words), list(offsets)
         self.special, self.attn, self.seq = list(special), list(attn), list(seq)
+        self.text = [None] * len(self.ids)  # token text where it is not the vocabulary string (lstrip / rstrip added tokens)
         self.ld, self.tr = (None if ld is None else list(ld)), (None if tr is None else list(tr))
         self.overflowing = []
 
@@ -29,8 +30,10 @@ class PE:
         return len(self.ids)
 
     def slice(self, a, b):
-        return PE(self.ids[a:b], self.type_ids[a:b], self.words[a:b], self.offsets[a:b], self.special[a:b], self.attn[a:b], self.seq[a:b],
-                  None if self.ld is None else self.ld[a:b], None if self.tr is None else self.tr[a:b])
+        p = PE(self.ids[a:b], self.type_ids[a:b], self.words[a:b], self.offsets[a:b], self.special[a:b], self.attn[a:b], self.seq[a:b],
+               None if self.ld is None else self.ld[a:b], None if self.tr is None else self.tr[a:b])
+        p.text = self.text[a:b]
+        return p
 
     def clone(self):
         return copy.deepcopy(self)
@@ -120,7 +123,7 @@ def merge_with(acc, pair):
             n = so.clone(); merge_with(n, oo.clone()); over.append(n)
     for oo in pair.overflowing:
         n = acc.clone(); merge_with(n, oo.clone()); over.append(n)
-    for f in ("ids", "type_ids", "words", "offsets", "special", "attn", "seq"):
+    for f in ("ids", "type_ids", "words", "offsets", "special", "attn", "seq", "text"):
         getattr(acc, f).extend(getattr(pair, f))
     if acc.ld is not None and pair.ld is not None:
         acc.ld.extend(pair.ld); acc.tr.extend(pair.tr)

@@ -177,6 +177,18 @@ class BatchEncoding:
         self.ids, self.offsets, self.word_ids, self.row_ptr = ids, offsets, word_ids, row_ptr
         self.type_ids, self.special_tokens_mask, self.attention_mask = type_ids, special_tokens_mask, attention_mask
         self.sequence_ids = sequence_ids  # int8, -1 = none (special / pad token); only set for pairs of sequences
+        self.token_text = None            # {token index: str}: added tokens whose text is a wider span than their content (lstrip / rstrip)
+
+    def _remap_text(self, src, new_to_old):
+        """carry src.token_text over to this CSR, whose token i is src's token new_to_old[i]"""
+        if src.token_text:
+            keys = np.fromiter(src.token_text, dtype=np.int64)
+            slot = np.full(len(src.ids), -1, dtype=np.int64)
+            slot[keys] = np.arange(len(keys))
+            hit = np.flatnonzero(slot[new_to_old] >= 0)
+            vals = list(src.token_text.values())
+            self.token_text = {int(i): vals[int(slot[new_to_old[i]])] for i in hit}
+        return self
 
     @property
     def n_tokens(self):
@@ -219,10 +231,15 @@ class Encoding:
 
     @property
     def tokens(self):
-        ids, attn = self.ids, self._col(self._be.attention_mask)
-        if attn is None:
-            return [self._tok.id_to_token(i) for i in ids]
-        return [self._tok.id_to_token(i) if m else self._pad_token for i, m in zip(ids, attn.tolist())]
+        ids, attn, text = self.ids, self._col(self._be.attention_mask), self._be.token_text
+        out = [self._tok.id_to_token(i) for i in ids]
+        if attn is not None:
+            out = [t if m else self._pad_token for t, m in zip(out, attn.tolist())]
+        if text:
+            for k in range(len(out)):
+                if self._a + k in text:
+                    out[k] = text[self._a + k]
+        return out
 
     @property
     def type_ids(self):
@@ -272,6 +289,9 @@ class Encoding:
             cat(np.ones(k, dtype=np.uint8), col(be.special_tokens_mask, np.zeros(n, dtype=np.uint8))),
             cat(np.zeros(k, dtype=np.uint8), col(be.attention_mask, np.ones(n, dtype=np.uint8))),
             None if be.sequence_ids is None else cat(np.full(k, -1, dtype=np.int8), col(be.sequence_ids, None)))
+        if be.token_text:
+            shift = (k if left else 0) - self._a
+            self._be.token_text = {i + shift: t for i, t in be.token_text.items() if self._a <= i < self._b}
         self._a, self._b, self._pad_token = 0, target, pad_token
 
     def __repr__(self):
@@ -292,7 +312,9 @@ def trim_offsets(be, ld, tr, add_prefix_space):
     n0 = np.where((ld > 0) & ~keep, np.minimum(o0 + ld, o1), o0)
     n1 = np.where((tr > 0) & (o1 >= tr), np.maximum(o1 - tr, n0), o1)
     offs = np.stack([n0, n1], axis=1).astype(np.uint32)
-    return BatchEncoding(be.ids, offs, be.word_ids, be.row_ptr, be.type_ids, be.special_tokens_mask)
+    out = BatchEncoding(be.ids, offs, be.word_ids, be.row_ptr, be.type_ids, be.special_tokens_mask)
+    out.token_text = be.token_text
+    return out
 
 
 def truncate_csr(be, extra, max_length, stride, direction):
@@ -339,7 +361,7 @@ def truncate_csr(be, extra, max_length, stride, direction):
     np.cumsum(lens, out=rp[1:])
     idx = np.repeat(seg_a - rp[:-1].astype(np.int64), lens) + np.arange(int(rp[-1]), dtype=np.int64)
     take = lambda x: None if x is None else x[idx]
-    return (BatchEncoding(be.ids[idx], take(be.offsets), take(be.word_ids), rp), [take(x) for x in extra],
+    return (BatchEncoding(be.ids[idx], take(be.offsets), take(be.word_ids), rp)._remap_text(be, idx), [take(x) for x in extra],
             np.asarray(seg_doc, dtype=np.int64))
 
 
@@ -367,7 +389,10 @@ def post_process(be, template):
         ids[starts + j] = tid; type_ids[starts + j] = ty
     for j, (tid, ty) in enumerate(post):
         ids[ends - len(post) + j] = tid; type_ids[ends - len(post) + j] = ty
-    return BatchEncoding(ids, offs, wid, new_rp, type_ids, special)
+    out = BatchEncoding(ids, offs, wid, new_rp, type_ids, special)
+    if be.token_text:
+        out.token_text = {int(pos[i]): t for i, t in be.token_text.items()}
+    return out
 
 
 def _view(ptr, count, dtype):
@@ -525,7 +550,14 @@ class Tokenizer:
             for i, a, b in added_at:
                 ld[i], tr[i] = self._span_spaces(raw, a, b)
             trim = (ld, tr)
-        return BatchEncoding(ids, offs, wid, rp), trim
+        be = BatchEncoding(ids, offs, wid, rp)
+        for i, a, b in added_at:  # Token::new(id, value = the matched span): differs from the content after lstrip / rstrip
+            tok = self._added.tokens[int(ids[i])]
+            if b - a != len(tok.content.encode("utf-8")):
+                if be.token_text is None:
+                    be.token_text = {}
+                be.token_text[i] = bytes(raw[a:b]).decode("utf-8", "replace")
+        return be, trim
 
     def _finish(self, be, trim, add_special_tokens):
         """the post-processor: offset trimming, then the special-token template"""
@@ -610,11 +642,15 @@ class Tokenizer:
         ids, offs, wid = be.ids.tolist(), [tuple(o) for o in be.offsets.tolist()], be.word_ids.tolist()
         ld, tr = (trim[0].tolist(), trim[1].tolist()) if trim is not None else (None, None)
 
+        text = be.token_text or {}
+
         def pe(row, type_id):
             a, b = rp[row], rp[row + 1]
             n = b - a
-            return pairs.PE(ids[a:b], [type_id] * n, wid[a:b], offs[a:b], [0] * n, [1] * n, [type_id] * n,
-                            None if ld is None else ld[a:b], None if tr is None else tr[a:b])
+            p = pairs.PE(ids[a:b], [type_id] * n, wid[a:b], offs[a:b], [0] * n, [1] * n, [type_id] * n,
+                         None if ld is None else ld[a:b], None if tr is None else tr[a:b])
+            p.text = [text.get(i) for i in range(a, b)]
+            return p
 
         def to_encoding(p):
             n = len(p)
@@ -624,6 +660,8 @@ class Tokenizer:
                                 np.array([0, n], dtype=np.uint64), np.asarray(p.type_ids, dtype=np.uint32),
                                 np.asarray(p.special, dtype=np.uint8), None,
                                 np.asarray([-1 if q is None else q for q in p.seq], dtype=np.int8))
+            if any(t is not None for t in p.text):
+                one.token_text = {i: t for i, t in enumerate(p.text) if t is not None}
             e = Encoding(self, one, 0, n)
             if p.overflowing:
                 e.overflowing = [to_encoding(o) for o in p.overflowing]
@@ -666,7 +704,9 @@ class Tokenizer:
                 counts = np.diff(be.row_ptr).astype(np.int64)
                 word_in_seq = np.arange(len(docs), dtype=np.int64) - np.repeat(seq_rows[:-1], np.diff(seq_rows))
                 wid = np.repeat(word_in_seq, counts).astype(np.uint32)
+            text = be.token_text
             be = BatchEncoding(be.ids, be.offsets, wid, be.row_ptr[seq_rows])
+            be.token_text = text
         # TokenizerImpl::post_process (tokenizer/mod.rs:1265-1317): 1. truncate, 2. post-processor, 3. pad
         part_doc = np.arange(len(be.row_ptr) - 1, dtype=np.int64)
         tr = self._truncation
