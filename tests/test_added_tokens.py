@@ -307,3 +307,20 @@ def test_pairs_vs_wheel():
             t.no_truncation(); t.no_padding()
         e_ref, e_mine = ref.encode("hello world", "x <mask> y"), mine.encode("hello world", "x <mask> y")
         assert e_mine.sequence_ids == e_ref.sequence_ids and e_mine.n_sequences == e_ref.n_sequences and e_mine.type_ids == e_ref.type_ids
+
+
+def test_decode_vs_wheel():
+    tk = wheel()
+    if tk is None:
+        pytest.skip("reference wheel not importable")
+    for asset, dec in (("gpt2_style", {"type": "ByteLevel", "add_prefix_space": True, "trim_offsets": True, "use_regex": True}),
+                       ("wordpiece", {"type": "WordPiece", "prefix": "##", "cleanup": True}), ("wordpiece", None)):
+        js = json.loads(with_added_tokens(asset_json(asset), True))
+        js["decoder"] = dec
+        tj = json.dumps(js)
+        ref, mine = tk.Tokenizer.from_str(tj), oracle_backed_tokenizer(tj)
+        docs = added_token_docs(5, 300) + ["I do not know , it 's fine . don't you ?"]
+        encs = ref.encode_batch(docs)
+        for skip in (True, False):
+            assert mine.decode_batch([e.ids for e in encs], skip_special_tokens=skip) == ref.decode_batch([e.ids for e in encs], skip_special_tokens=skip)
+        assert mine.decode([10 ** 9, 5]) == ref.decode([10 ** 9, 5])  # unknown ids are dropped

@@ -160,6 +160,7 @@ def parse_tokenizer_json(js):
     if template is not None and template["trim"] is not None and (cfg["model"] != _lib.MODEL_BPE or cfg["pretok"] == _lib.PRETOK_WHITESPACE):
         raise UnsupportedConfig("trim_offsets needs a byte-level BPE pipeline")
     cfg["template"] = template
+    cfg["decoder"] = js.get("decoder")
     cfg["truncation"] = parse_truncation(js.get("truncation"))
     cfg["padding"] = parse_padding(js.get("padding"))
     return cfg
@@ -395,6 +396,22 @@ def post_process(be, template):
     return out
 
 
+_CHAR_BYTES = None
+
+
+def _char_bytes():
+    """inverse of the byte-level alphabet (pre_tokenizers/byte_level.rs:15-39): character -> byte"""
+    global _CHAR_BYTES
+    if _CHAR_BYTES is None:
+        keep = list(range(0x21, 0x7F)) + list(range(0xA1, 0xAD)) + list(range(0xAE, 0x100))
+        cs, n = {b: chr(b) for b in keep}, 0
+        for b in range(256):
+            if b not in cs:
+                cs[b] = chr(256 + n); n += 1
+        _CHAR_BYTES = {c: b for b, c in cs.items()}
+    return _CHAR_BYTES
+
+
 def _view(ptr, count, dtype):
     if not ptr or count == 0:
         return np.zeros(0, dtype=dtype)
@@ -414,6 +431,7 @@ class Tokenizer:
         self._vocab_r = None
         self._template = cfg["template"]
         self._truncation, self._padding = cfg["truncation"], cfg["padding"]
+        self._decoder = cfg["decoder"]
         self._trim = None
         self._added = None
         if any(t.get("content") for t in cfg["added_tokens"]):
@@ -747,6 +765,44 @@ class Tokenizer:
                 raise UnsupportedConfig("pre-tokenized pairs are not supported")
             return self._encode_list([(sequence, pair)], True, True, add_special_tokens)[0]
         return self._encode_list([sequence], True, True, add_special_tokens, is_pretokenized)[0]
+
+    # ---- decode (tokenizer/mod.rs:935-953; host only: ids -> text is a table walk, nothing for the GPU to do)
+    def decode(self, ids, skip_special_tokens=True):
+        toks = []
+        for i in ids:
+            t = self.id_to_token(i)
+            if t is None:
+                continue
+            if skip_special_tokens and self._added is not None and t in self._added.by_content and self._added.by_content[t].special:
+                continue
+            toks.append(t)
+        d = self._decoder
+        if d is None:
+            return " ".join(toks)
+        if d.get("type") == "ByteLevel":  # pre_tokenizers/byte_level.rs:156-171
+            inv = _char_bytes()
+            out = bytearray()
+            for t in toks:
+                try:
+                    out.extend(inv[c] for c in t)
+                except KeyError:
+                    out.extend(t.encode("utf-8"))
+            return out.decode("utf-8", "replace")
+        if d.get("type") == "WordPiece":  # decoders/wordpiece.rs:31-61
+            prefix, clean, out = d.get("prefix", "##"), d.get("cleanup", True), []
+            for k, t in enumerate(toks):
+                if k != 0:
+                    t = t[len(prefix):] if t.startswith(prefix) else " " + t
+                if clean:
+                    for a, b in ((" .", "."), (" ?", "?"), (" !", "!"), (" ,", ","), (" ' ", "'"), (" n't", "n't"), (" 'm", "'m"),
+                                 (" do not", " don't"), (" 's", "'s"), (" 've", "'ve"), (" 're", "'re")):
+                        t = t.replace(a, b)
+                out.append(t)
+            return "".join(out)
+        raise UnsupportedConfig(f"decoder {d.get('type')} is not supported")
+
+    def decode_batch(self, sequences, skip_special_tokens=True):
+        return [self.decode(s, skip_special_tokens) for s in sequences]
 
     def pre_tokenize_batch(self, docs):
         """PreTokenizer seam: per document the list of (start_byte, end_byte) of its splits."""
