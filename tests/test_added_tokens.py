@@ -324,3 +324,21 @@ def test_decode_vs_wheel():
         for skip in (True, False):
             assert mine.decode_batch([e.ids for e in encs], skip_special_tokens=skip) == ref.decode_batch([e.ids for e in encs], skip_special_tokens=skip)
         assert mine.decode([10 ** 9, 5]) == ref.decode([10 ** 9, 5])  # unknown ids are dropped
+
+
+def test_add_tokens_vs_wheel():
+    """Tokenizer.add_tokens / add_special_tokens after loading: id assignment and extraction follow the reference"""
+    tk = wheel()
+    if tk is None:
+        pytest.skip("reference wheel not importable")
+    tj = asset_json("gpt2_style")
+    ref, mine = tk.Tokenizer.from_str(tj), oracle_backed_tokenizer(tj)
+    at = tk.AddedToken
+    for t in (ref, mine):
+        assert t.add_special_tokens(["<|endoftext|>", "<pad>"]) == 2
+        assert t.add_tokens(["hello", "newword", at("tok", single_word=True), at("<x>", lstrip=True, rstrip=True)]) == 4
+        assert t.add_tokens(["newword"]) == 0
+    assert mine.get_vocab_size() == ref.get_vocab_size() and mine.get_vocab() == ref.get_vocab()
+    assert mine.num_special_tokens_to_add(False) == ref.num_special_tokens_to_add(False) == 0
+    docs = ["hello newword <|endoftext|> x  <x>  y tok atok <pad>", "newwordnewword", ""] + added_token_docs(4, 200)
+    _compare(_flat(mine.encode_batch(docs)), _flat(ref.encode_batch(docs)), docs, "after add_tokens")

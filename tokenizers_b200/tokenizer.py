@@ -493,6 +493,61 @@ class Tokenizer:
             n += sum(1 for t in self._added.tokens.values() if self._vocab.get(t.content) != t.id)
         return n
 
+    def get_vocab(self, with_added_tokens=True):
+        v = dict(self._vocab)
+        if with_added_tokens and self._added is not None:
+            v.update({t.content: t.id for t in self._added.tokens.values()})
+        return v
+
+    def num_special_tokens_to_add(self, is_pair):
+        """PostProcessor::added_tokens (template.rs:647-653, bert.rs, roberta.rs)"""
+        tp = self._template
+        if tp is None:
+            return 0
+        pieces = tp["pair"] if is_pair else tp["single"]
+        return sum(1 for p in (pieces or []) if p[0] == "special")
+
+    def _add(self, tokens, special):
+        """AddedVocabulary::add_tokens (added_vocabulary.rs:270-340): a token keeps the model's id when its content is in the
+        vocabulary, otherwise it gets the next free id; returns how many were new"""
+        entries = [] if self._added is None else [
+            {"id": t.id, "content": t.content, "single_word": t.single_word, "lstrip": t.lstrip, "rstrip": t.rstrip,
+             "normalized": t.normalized, "special": t.special} for t in self._added.tokens.values()]
+        known = {e["content"]: e for e in entries}
+        top = max([e["id"] for e in entries] + [max(self._vocab.values())])
+        nxt = top + 1
+        added_n = 0
+        for t in tokens:
+            d = {"content": t} if isinstance(t, str) else {k: getattr(t, k) for k in ("content", "single_word", "lstrip", "rstrip", "normalized") if hasattr(t, k)}
+            if not d.get("content"):
+                continue
+            d.setdefault("single_word", False); d.setdefault("lstrip", False); d.setdefault("rstrip", False)
+            d["special"] = special
+            if isinstance(t, str) or "normalized" not in d:
+                d["normalized"] = not special
+            old = known.get(d["content"])
+            if old is not None and all(old[k] == d[k] for k in ("single_word", "lstrip", "rstrip", "normalized", "special")):
+                continue
+            if d["content"] in self._vocab:
+                d["id"] = self._vocab[d["content"]]
+            elif old is not None:
+                d["id"] = old["id"]
+            else:
+                d["id"], nxt = nxt, nxt + 1
+            if old is not None:
+                entries.remove(old)
+            entries.append(d); known[d["content"]] = d
+            added_n += 1
+        self._added = added.AddedVocabulary(entries, self._rust_class_table()) if entries else None
+        self._trim = None
+        return added_n
+
+    def add_tokens(self, tokens):
+        return self._add(tokens, False)
+
+    def add_special_tokens(self, tokens):
+        return self._add(tokens, True)
+
     def token_to_id(self, token):
         if self._added is not None and token in self._added.by_content:
             return self._added.by_content[token].id
