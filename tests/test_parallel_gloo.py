@@ -45,6 +45,19 @@ def test_shard_range_partitions():
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
 
 
+def test_shard_by_bytes_balances_skewed_lengths():
+    from tokenizers_b200.parallel import shard_by_bytes
+    rng = np.random.default_rng(5)
+    lens = np.minimum((rng.pareto(1.2, 20000) * 50 + 8).astype(np.int64), 65536)  # Zipf-like lengths, 64 KB outliers
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for w in (1, 2, 3, 8):
+        r = shard_by_bytes(off, w)
+        assert r[0][0] == 0 and r[-1][1] == len(lens) and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        by = [int(off[b] - off[a]) for a, b in r]
+        assert max(by) - min(by) <= 2 * int(lens.max()), by
+    assert shard_by_bytes(np.array([0]), 4) == [(0, 0)] * 4 and shard_by_bytes(np.array([0, 5]), 2) in ([(0, 0), (0, 1)], [(0, 1), (1, 1)])
+
+
 def test_two_rank_gather_equals_single_rank():
     mgr = mp.Manager(); ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)

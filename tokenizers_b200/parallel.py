@@ -16,6 +16,27 @@ def shard_range(n_docs, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_by_bytes(doc_off, world):
+    """Contiguous document ranges with (nearly) equal BYTES per rank: [(lo, hi)] * world.
+
+    Equal document counts are only balanced when documents have similar lengths; with the length-skewed corpus of
+    BASELINE config 5 (Zipf lengths, 64 KB outliers) the per-rank work follows the bytes.  Cut points
+    are the document boundaries closest to the multiples of total / world; ranges stay contiguous, so the gathered CSR
+    is in input order without a permutation."""
+    import numpy as np
+    off = np.asarray(doc_off, dtype=np.int64)
+    n, total = len(off) - 1, int(off[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r // world
+        k = int(np.searchsorted(off, target, side="left"))
+        if k > 0 and k <= n and abs(int(off[k - 1]) - target) <= abs(int(off[min(k, n)]) - target):
+            k -= 1
+        cuts.append(min(max(k, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def all_gather_v(local, group=None):
     """All-gather 1-D tensors of different lengths.  Returns (flat tensor of every rank's data in rank order, counts)."""
     world = dist.get_world_size(group)
