@@ -84,7 +84,8 @@ void b2t_engine_destroy(b2t_engine* e);
 
 /* Replaces TokenizerImpl::encode_batch / encode_batch_char_offsets / encode_batch_fast (tokenizer/mod.rs:1337-1401)
  * for raw (not pre-tokenized) single sequences with add_special_tokens=false.  HOST buffers: `bytes` holds the
- * documents back to back, document d = bytes[doc_off[d] .. doc_off[d+1]); doc_off[0] must be 0.  The call copies the
+ * documents back to back, document d = bytes[doc_off[d] .. doc_off[d+1]); doc_off[0] must be 0 and doc_off must be
+ * non-decreasing (checked: B2T_ERR_INVALID otherwise -- nothing unordered reaches a kernel).  The call copies the
  * input to the device in chunks, runs the kernels and copies the token CSR back into pinned host memory owned by
  * the result.  flags = 0 is the encode_batch_fast analogue (ids only). */
 int b2t_encode_batch(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, uint32_t flags,
