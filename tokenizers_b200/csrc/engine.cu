@@ -42,6 +42,11 @@ static int fail(int code, const char* fmt, ...) {
 extern "C" const char* b2t_last_error(void) { return g_err; }
 extern "C" const char* b2t_version(void) { return "tokenizers_b200 0.1 (sm_100a)"; }
 
+#ifdef B2T_K1_DEBUG
+extern "C" int b2t_debug_k1(uint32_t* out, size_t words) {
+  return (int)cudaMemcpyFromSymbol(out, b2t::g_k1_dbg, words * 4);
+}
+#endif
 extern "C" int b2t_unicode_class_table(int scheme, uint8_t* out) {
   if (!out || (scheme != 0 && scheme != 1)) return fail(B2T_ERR_INVALID, "b2t_unicode_class_table: bad arguments");
   unicode_class_table(scheme, out);
@@ -123,6 +128,7 @@ struct b2t_engine {
   int device = 0;
   int model = 0, pretok = 0, add_prefix_space = 0;
   int sm_count = 148;
+  int k1_tiled = 0;          // B2T_K1_TILED=1: the round-1 shared-memory-tiled scan (kept for A/B runs)
   DeviceTables dt;
   int monotone = 0;
   DevBuf d_cls, d_byte_to_id, d_merge, d_word, d_pool, d_edge;
@@ -185,6 +191,7 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
   b2t_engine* e = new b2t_engine();
   e->device = dev; e->model = cfg->model; e->pretok = cfg->pretok; e->add_prefix_space = cfg->add_prefix_space;
   cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (const char* kt = getenv("B2T_K1_TILED")) e->k1_tiled = atoi(kt) != 0;
   if (const char* cb = getenv("B2T_CHUNK_BYTES")) {  // host-path chunk size (tests use tiny chunks to exercise the pipeline)
     long long v = atoll(cb);
     if (v >= 1024 && v < (1ll << 31)) e->chunk_bytes = (size_t)v;
@@ -254,6 +261,19 @@ template <int KIND>
 static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Workspace& ws, cudaStream_t st) {
   constexpr int TC = B2T_K1_TC;
   const int64_t n_chunks = n / CHUNK + 1;
+  if (!e->k1_tiled) {
+    // streaming form: every warp owns a contiguous range of whole pages; ~4 waves of resident warps
+    const int64_t n_kb = (n_chunks + 31) / 32;
+    const int64_t resident = (int64_t)e->sm_count * B2T_K1S_MINBLOCKS * (B2T_K1S_THREADS / 32);
+    int64_t kb = (n_kb + resident * 4 - 1) / (resident * 4);
+    kb = std::min<int64_t>(128, std::max<int64_t>(2, (kb + 1) & ~1ll));
+    const int64_t n_warps = (n_kb + kb - 1) / kb;
+    const int64_t grid = (n_warps + (B2T_K1S_THREADS / 32) - 1) / (B2T_K1S_THREADS / 32);
+    pretok_stream_kernel<KIND><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
+                                                                         ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
+                                                                         ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb);
+    return;
+  }
   const int64_t n_tiles = (n_chunks + TC - 1) / TC;
   // contiguous tile ranges per block (the kernel pipelines consecutive tiles); ~8 blocks per SM
   int64_t tiles_per_block = std::max<int64_t>(1, (n_tiles + (int64_t)e->sm_count * 8 - 1) / ((int64_t)e->sm_count * 8));

@@ -372,3 +372,222 @@ __global__ void __launch_bounds__(SCAN_BLOCK) page_scan_top_kernel(const uint64_
 }
 
 }  // namespace b2t
+
+// ================================================================================================ K1, streaming form
+// pretok_stream_kernel: the production K1.  Every WARP streams through its own contiguous range of the batch, 1 KB
+// (32 chunks of 32 bytes, one per lane) per iteration, and is independent of all other warps: no shared memory, no
+// block barrier.  Iteration i+1 is classified (pretok_fast.cuh: bit planes -> classes) before the boundaries of
+// iteration i are evaluated, so a lane gets everything it needs from its neighbours with warp shuffles:
+//   the chunk before lane 0   = lane 31 of the previous iteration (still in that lane's registers),
+//   the chunk after lane 31   = lane 0 of the next iteration (already classified).
+// The range ends are handled by classifying one extra KB on either side.  Page summaries (2 KB = two iterations of the
+// same warp) are combined in registers.  Algorithmic traffic is unchanged: 1.25 B per input byte.
+#include "pretok_fast.cuh"
+
+namespace b2t {
+
+// Exact window code (pretok_logic.cuh) for one chunk, everything re-read from global memory.  Used by the rare
+// fallback of the fast GPT-2 algebra and as the Llama-3 slow path.
+template <int KIND>
+__device__ __noinline__ uint32_t exact_chunk_start(const uint8_t* __restrict__ bytes, int64_t n, int64_t c,
+                                                  const uint32_t* __restrict__ cls_tbl, const uint32_t* __restrict__ doc_bits) {
+  const int64_t n_chunks = n / CHUNK + 1;
+  ByteAtGlobal at{bytes, n};
+  DsAtGlobal dsat{doc_bits, n_chunks};
+  const ChunkMasks p = classify_global<KIND>(bytes, n, c - 1, cls_tbl), o = classify_global<KIND>(bytes, n, c, cls_tbl),
+                   x = classify_global<KIND>(bytes, n, c + 1, cls_tbl);
+  Window w;
+  w.lead = win(p.lead, o.lead, x.lead); w.L = win(p.L, o.L, x.L); w.N = win(p.N, o.N, x.N); w.S = win(p.S, o.S, x.S);
+  w.SP = win(p.SP, o.SP, x.SP); w.NL = KIND == PT_LLAMA3 ? win(p.NL, o.NL, x.NL) : 0ull; w.AP = win(p.AP, o.AP, x.AP);
+  w.DS = win(dsat(c - 1), dsat(c), dsat(c + 1));
+  const int64_t wb = c * CHUNK - 16;
+  if (KIND == PT_GPT2) return boundaries_gpt2(w, wb, at).start;
+  if (KIND == PT_LLAMA3) {
+    struct GlobalMaskAt {
+      const uint8_t* bytes; int64_t n; const uint32_t* cls;
+      __device__ __forceinline__ ChunkMasks operator()(int64_t k) const { return classify_global<KIND>(bytes, n, k, cls); }
+    } masks{bytes, n, cls_tbl};
+    const LlamaCarry cy = llama_carry(c, n_chunks, masks, dsat);
+    return boundaries_llama3(w, wb, at, cy).start;
+  }
+  return boundaries_whitespace(w).start;
+}
+
+#ifndef B2T_K1S_THREADS
+#define B2T_K1S_THREADS 128
+#endif
+#ifndef B2T_K1S_MINBLOCKS
+#define B2T_K1S_MINBLOCKS 4
+#endif
+
+#ifdef B2T_K1_DEBUG
+__device__ uint32_t g_k1_dbg[8192 * 8];
+#endif
+// byte access with 32-bit positions (batches are < 2^31 bytes; "negative" positions wrap to out-of-range)
+struct ByteAt32 {
+  const uint8_t* __restrict__ p;
+  uint32_t n;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i < n ? (uint32_t)__ldg(p + i) : 0u; }
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(B2T_K1S_THREADS, B2T_K1S_MINBLOCKS)
+pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_t* __restrict__ doc_bits,
+                     const uint32_t* __restrict__ cls_tbl, uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
+                     uint64_t* __restrict__ page_sum, int n_kb, int kb_per_warp) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int it_lo = gw * kb_per_warp;             // even: a page is two consecutive iterations of one warp
+  if (it_lo >= n_kb) return;
+  const int it_hi = it_lo + kb_per_warp < n_kb ? it_lo + kb_per_warp : n_kb;
+  const uint32_t n = (uint32_t)n64;
+  const uint32_t n_chunks = n / CHUNK + 1;
+  const ByteAt32 at{bytes, n};
+  const int up = (lane + 31) & 31, down = (lane + 1) & 31;
+
+  auto load = [&](int it, uint32_t w[8]) {       // it = -1: nothing there
+    const uint32_t base = ((uint32_t)it * 32u + lane) * CHUNK;
+    if (it >= 0 && base + CHUNK <= n) {
+      const uint4* q = reinterpret_cast<const uint4*>(bytes + base);
+      const uint4 a = __ldg(q), b = __ldg(q + 1);
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = 0u;
+      if (it >= 0 && base < n) load_chunk_words(bytes, base, n, w);   // the batch ends inside this chunk
+    }
+  };
+  // classes of iteration `it`; `prev` = this lane's classes of the iteration before (lane 31's chunk precedes lane 0's)
+  auto classify = [&](const uint32_t w[8], int it, const FastCls& prev, FastCls& m, FastCls& pm) {
+    const uint32_t base = ((uint32_t)it * 32u + lane) * CHUNK;
+    const uint32_t valid = it < 0 || base >= n ? 0u : (n - base >= CHUNK ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (32u - (n - base))));
+    uint32_t b[8];
+    bitslice32(w, b);
+    m = classify_planes<KIND>(b, valid);
+#ifdef B2T_K1_NOANY
+    {
+#else
+    if (__any_sync(FULL, m.hi != 0u)) {
+#endif
+      if (m.unc) resolve_uncertain(m, at, base, cls_tbl);
+      fill_own(m);
+    }
+    // the chunk before mine (only bit 31 of the class words matters to the fast algebra; Llama-3 uses the top halves)
+    pm.L = __shfl_sync(FULL, lane == 31 ? prev.L : m.L, up);
+    pm.N = KIND == PT_WHITESPACE ? 0u : __shfl_sync(FULL, lane == 31 ? prev.N : m.N, up);
+    pm.S = __shfl_sync(FULL, lane == 31 ? prev.S : m.S, up);
+    pm.SP = KIND == PT_WHITESPACE ? 0u : __shfl_sync(FULL, lane == 31 ? prev.SP : m.SP, up);
+    if (KIND == PT_LLAMA3) {
+      pm.lead = __shfl_sync(FULL, lane == 31 ? prev.lead : m.lead, up);
+      pm.NL = __shfl_sync(FULL, lane == 31 ? prev.NL : m.NL, up);
+      pm.AP = __shfl_sync(FULL, lane == 31 ? prev.AP : m.AP, up);
+    }
+    if (m.cont & 1u) spill_in(m, pm.L, pm.N, pm.S);
+  };
+
+  uint32_t ov_mine = 0u;            // contraction overflow of my chunk of the previous iteration (lane 31's feeds lane 0)
+  uint32_t h_tot = 0u, h_aft = 0u, h_flag = 0u;   // first half of the current page
+
+  // One iteration: classify it+1 (words in w) into nxt / pnxt, refill w with the words of it+3, then boundaries,
+  // stores and page summary of iteration `it` (classes in cur / pcur).
+  auto step = [&](int it, const FastCls& cur, const FastCls& pcur, FastCls& nxt, FastCls& pnxt, uint32_t w[8]) {
+    classify(w, it + 1, cur, nxt, pnxt);
+    load(it + 3 <= it_hi ? it + 3 : -1, w);      // prefetch (the KB after the range is classified too, for its first bytes)
+
+    const uint32_t c = (uint32_t)it * 32u + lane, base = c * CHUNK;
+    const uint32_t ds = c < n_chunks ? __ldg(doc_bits + c) : 0u;
+    const uint32_t ds_next = c + 1 < n_chunks ? __ldg(doc_bits + c + 1) : 0u;
+    uint32_t start, drop = 0u;
+    if (KIND == PT_GPT2) {
+      const uint32_t head = (cur.lead & 1u) | ((cur.S & 1u) << 1), nhead = (nxt.lead & 1u) | ((nxt.S & 1u) << 1);
+      const uint32_t xh = __shfl_sync(FULL, lane == 0 ? nhead : head, down);
+      PrevTop pt; pt.L = pcur.L; pt.N = pcur.N; pt.S = pcur.S; pt.SP = pcur.SP;
+      const FastOut o = fast_gpt2(cur, pt, xh & 1u, (xh >> 1) & 1u, ds, ds_next, base, at);
+      Overflow in; in.bits = __shfl_sync(FULL, lane == 31 ? ov_mine : o.ov.bits, up);
+      ov_mine = o.ov.bits;
+      start = apply_overflow(o.start, cur.lead, in);
+      if (o.fallback) start = exact_chunk_start<KIND>(bytes, n64, c, cls_tbl, doc_bits);
+    } else if (KIND == PT_WHITESPACE) {
+      PrevTop pt; pt.L = pcur.L; pt.N = 0u; pt.S = pcur.S; pt.SP = 0u;
+      const FastOut o = fast_whitespace(cur, pt, ds);
+      start = o.start; drop = o.drop;
+    } else if (KIND == PT_LLAMA3) {
+      // window algebra of pretok_logic.cuh on [16 B of the previous chunk | mine | 16 B of the next chunk]
+      Window wd;
+      auto nextw = [&](uint32_t mine, uint32_t theirs) { return __shfl_sync(FULL, lane == 0 ? theirs : mine, down); };
+      wd.lead = win(pcur.lead, cur.lead, nextw(cur.lead, nxt.lead)); wd.L = win(pcur.L, cur.L, nextw(cur.L, nxt.L));
+      wd.N = win(pcur.N, cur.N, nextw(cur.N, nxt.N)); wd.S = win(pcur.S, cur.S, nextw(cur.S, nxt.S));
+      wd.SP = win(pcur.SP, cur.SP, nextw(cur.SP, nxt.SP)); wd.NL = win(pcur.NL, cur.NL, nextw(cur.NL, nxt.NL));
+      wd.AP = win(pcur.AP, cur.AP, nextw(cur.AP, nxt.AP));
+      const uint32_t ds_prev = (c >= 1u && c - 1u < n_chunks) ? __ldg(doc_bits + c - 1) : 0u;
+      wd.DS = win(ds_prev, ds, ds_next);
+      LlamaCarry cy; cy.n_count_before_window = 0; cy.zone_before_window = false; cy.tail_after_window = false;
+      const ByteAtGlobal at64{bytes, n64};
+      const BoundaryOut r = boundaries_llama3(wd, (int64_t)base - 16, at64, cy);
+      start = r.start;
+      if (r.slow) start = exact_chunk_start<KIND>(bytes, n64, c, cls_tbl, doc_bits);
+    } else {
+      start = ds & cur.lead;
+    }
+    if (c < n_chunks) {
+      start_bits[c] = start;
+      if (KIND == PT_WHITESPACE) drop_bits[c] = drop;
+    }
+#ifdef B2T_K1_DEBUG
+    if (c < 8192u) { uint32_t* d = g_k1_dbg + c * 8; d[0] = cur.lead; d[1] = cur.cont; d[2] = cur.L; d[3] = cur.N; d[4] = cur.S; d[5] = cur.SP; d[6] = pcur.L; d[7] = start; }
+#endif
+    // ---- page summary (segmented: counts restart at the last doc start of the page); this iteration is half a page
+    const uint32_t kept = start & ~drop;
+    const uint32_t tot = (uint32_t)__popc(cur.lead) | ((uint32_t)__popc(kept) << 16);
+    const unsigned dsm = __ballot_sync(FULL, ds != 0u);
+    const uint32_t wtot = __reduce_add_sync(FULL, tot);
+    uint32_t waft = 0u;
+    if (dsm) {
+      const int last = 31 - __clz((int)dsm);
+      uint32_t mine = 0u;
+      if (lane > last) mine = tot;
+      else if (lane == last) {
+        const uint32_t from = ~bits_below(31 - __clz((int)ds));
+        mine = (uint32_t)__popc(cur.lead & from) | ((uint32_t)__popc(kept & from) << 16);
+      }
+      waft = __reduce_add_sync(FULL, mine);
+    }
+    const uint32_t wflag = dsm != 0u;
+    const uint32_t page = (uint32_t)it >> 1;
+    if (it & 1) {
+      const uint32_t a = wflag ? waft : h_aft + wtot, t = h_tot + wtot, f = h_flag | wflag;
+      if (lane == 0 && page * (uint32_t)PAGE <= n) page_sum[page] = pack_sum(t, a, f);
+    } else {
+      h_tot = wtot; h_aft = waft; h_flag = wflag;
+      if (it + 1 >= n_kb && lane == 0 && page * (uint32_t)PAGE <= n) page_sum[page] = pack_sum(h_tot, h_aft, h_flag);  // the batch ends in the first half
+    }
+  };
+
+  FastCls A, pA, B, pB;   // p*: the chunk before (as far as needed)
+  uint32_t w0[8], w1[8];
+  {
+    FastCls zero;
+    zero.lead = zero.cont = zero.hi = zero.L = zero.N = zero.S = zero.SP = zero.AP = zero.NL = zero.unc = 0u;
+    load(it_lo - 1, w0);
+    classify(w0, it_lo - 1, zero, B, pB);
+    if (KIND == PT_GPT2 && it_lo > 0) {
+      // a contraction that starts in the last chunk before the range reaches into the range's first chunk
+      const uint32_t c = (uint32_t)(it_lo - 1) * 32u + lane;
+      const uint32_t ds = c < n_chunks ? __ldg(doc_bits + c) : 0u, ds_next = c + 1 < n_chunks ? __ldg(doc_bits + c + 1) : 0u;
+      PrevTop pt; pt.L = pB.L; pt.N = pB.N; pt.S = pB.S; pt.SP = pB.SP;
+      ov_mine = fast_gpt2(B, pt, 1u, 0u, ds, ds_next, c * CHUNK, at).ov.bits;
+    }
+    load(it_lo, w0);
+    classify(w0, it_lo, B, A, pA);
+    load(it_lo + 1, w0);
+    load(it_lo + 2 <= it_hi ? it_lo + 2 : -1, w1);
+  }
+  // two iterations per trip, the class registers ping-pong (A holds the even iteration, B the odd one)
+  for (int it = it_lo; it < it_hi; it += 2) {
+    step(it, A, pA, B, pB, w0);
+    if (it + 1 < it_hi) step(it + 1, B, pB, A, pA, w1);
+  }
+}
+
+}  // namespace b2t

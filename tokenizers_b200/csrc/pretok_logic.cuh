@@ -265,8 +265,8 @@ struct BoundaryOut {
 
 // Contraction lengths for the apostrophe at window position a (needs raw bytes): 0 = none, 2 = 's etc, 3 = 're etc.
 // Returned length is in BYTES after... i.e. the match is [a, a+len).  icase also folds U+017F to 's' (2 bytes => len 3).
-template <class ByteAt>
-B2T_HD int contraction_len(const ByteAt& at, int64_t pos, int64_t doc_end_hint, bool icase) {
+template <class ByteAt, class Pos>
+B2T_HD int contraction_len(const ByteAt& at, Pos pos, Pos doc_end_hint, bool icase) {
   // bytes past the end of the buffer read as 0 through `at`
   (void)doc_end_hint;
   uint32_t a = at(pos + 1), b = at(pos + 2);
@@ -291,7 +291,7 @@ B2T_HD uint64_t apply_contractions(uint64_t start, uint64_t cand, const Window& 
   while (todo) {
     int a = ctz64(todo);
     todo &= todo - 1;
-    int len = contraction_len(at, win_base + a, 0, icase);
+    int len = contraction_len(at, win_base + a, (int64_t)0, icase);
     if (!len) continue;
     // the whole match must lie inside the document: no doc start in (a, a+len)
     uint64_t inside = ((1ull << len) - 2ull) << a;  // bits a+1 .. a+len-1
