@@ -63,6 +63,7 @@ static void emul_fast(const uint8_t* bytes, uint64_t n, const uint64_t* doc_off,
   std::vector<uint32_t> DS(n_chunks + 2, 0);
   for (uint32_t d = 0; d <= n_docs; ++d) DS[doc_off[d] / 32] |= 1u << (doc_off[d] % 32);
   auto at = [&](int64_t p) -> uint32_t { return (p >= 0 && (uint64_t)p < n) ? bytes[p] : 0u; };
+  auto at4 = [&](int64_t p) -> uint32_t { return at(p) | (at(p + 1) << 8) | (at(p + 2) << 16) | (at(p + 3) << 24); };
   std::vector<FastCls> M(n_chunks + 1);
   std::vector<PrevTop> PT(n_chunks + 1);
   FastCls prev;
@@ -78,7 +79,7 @@ static void emul_fast(const uint8_t* bytes, uint64_t n, const uint64_t* doc_off,
     const uint32_t valid = base + 32 <= (int64_t)n ? 0xFFFFFFFFu : (base >= (int64_t)n ? 0u : (0xFFFFFFFFu >> (32 - (int)((int64_t)n - base))));
     bitslice32(w, b);
     FastCls m = classify_planes<KIND>(b, valid);
-    if (m.unc) resolve_uncertain(m, at, base, cls_tbl);
+    if (m.unc) resolve_uncertain(m, at4, base, cls_tbl);
     fill_own(m);
     PrevTop pt; pt.L = prev.L; pt.N = prev.N; pt.S = prev.S; pt.SP = prev.SP;
     if (m.cont & 1u) spill_in(m, pt.L, pt.N, pt.S);
@@ -111,11 +112,16 @@ static void emul_fast(const uint8_t* bytes, uint64_t n, const uint64_t* doc_off,
     const FastCls& m = M[c];
     const FastCls& x = M[c + 1];
     FastOut o;
-    if (KIND == PT_GPT2) o = fast_gpt2(m, PT[c], x.lead & 1u, x.S & 1u, DS[c], DS[c + 1], c * 32, at);
+    if (KIND == PT_GPT2) o = fast_gpt2(m, PT[c], 1u, 1u, DS[c], DS[c + 1], c * 32, at4);
     else if (KIND == PT_WHITESPACE) o = fast_whitespace(m, PT[c], DS[c]);
     else { o.start = DS[c] & m.lead; o.drop = 0; o.fallback = 0; o.ov.bits = 0; }
     uint32_t start = apply_overflow(o.start, m.lead, ov_in), drop = o.drop;
-    if (o.fallback) { start = exact(c, &drop); ++nfb; }
+    if (KIND == PT_GPT2) {
+      const uint32_t before = start;
+      start = finalize_gpt2(start, m.lead, m.S >> 31, x.lead & 15u, x.S & 15u, DS[c + 1]);
+      if (start != before && (m.hi >> 31)) ++nfb;   // counts the straddling multi-byte spaces that were given back
+    }
+    (void)exact;
     start_bits[c] = start;
     if (drop_bits) drop_bits[c] = drop;
     if (planes_out) { uint32_t* d = planes_out + c * 8; d[0] = m.lead; d[1] = m.cont; d[2] = m.L; d[3] = m.N; d[4] = m.S; d[5] = m.SP; d[6] = PT[c].L; d[7] = start; }

@@ -264,14 +264,21 @@ static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Work
   if (!e->k1_tiled) {
     // streaming form: every warp owns a contiguous range of whole pages; ~4 waves of resident warps
     const int64_t n_kb = (n_chunks + 31) / 32;
-    const int64_t resident = (int64_t)e->sm_count * B2T_K1S_MINBLOCKS * (B2T_K1S_THREADS / 32);
+    const int64_t resident = (int64_t)e->sm_count * (KIND == PT_LLAMA3 ? B2T_K1W_MINBLOCKS : B2T_K1S_MINBLOCKS) * (B2T_K1S_THREADS / 32);
     int64_t kb = (n_kb + resident * 4 - 1) / (resident * 4);
     kb = std::min<int64_t>(128, std::max<int64_t>(2, (kb + 1) & ~1ll));
     const int64_t n_warps = (n_kb + kb - 1) / kb;
     const int64_t grid = (n_warps + (B2T_K1S_THREADS / 32) - 1) / (B2T_K1S_THREADS / 32);
-    pretok_stream_kernel<KIND><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
+    if constexpr (KIND == PT_LLAMA3) {
+      pretok_stream_kernel<KIND><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
+                                                                           ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
+                                                                           ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb);
+    } else {
+      const SwapMasks masks{0x55555555u, 0x33333333u, 0x0F0F0F0Fu};
+      pretok_lean_kernel<KIND><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
                                                                          ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
-                                                                         ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb);
+                                                                         ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb, masks);
+    }
     return;
   }
   const int64_t n_tiles = (n_chunks + TC - 1) / TC;

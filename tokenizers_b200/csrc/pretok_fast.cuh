@@ -70,15 +70,16 @@ B2T_HD uint32_t tt_eval(const uint32_t* x) {
 
 // ---------------------------------------------------------------------------------------------- bit slicing
 // w[0..7]: the chunk's 32 bytes as little-endian words.  b[j] bit p = bit j of byte p.
-template <uint32_t D, uint32_t M>
-B2T_HD void plane_swap(uint32_t& a, uint32_t& b) {
-  // (x & M) | (y & ~M), written with ONE constant so that it folds into a single 3-input look-up
-  const uint32_t bs = b << D, as = a >> D;
-  const uint32_t na = bs ^ ((a ^ bs) & M);
-  const uint32_t nb = b ^ ((as ^ b) & M);
+// The three exchange masks are passed at RUN TIME (kernel parameters): with a compile-time mask nvcc splits
+// (x & M) | (y & ~M) into two look-ups with two immediates; with M in a register / constant bank it is one LOP3.
+struct SwapMasks { uint32_t m1, m2, m4; };   // 0x55555555, 0x33333333, 0x0F0F0F0F
+template <uint32_t D>
+B2T_HD void plane_swap(uint32_t& a, uint32_t& b, uint32_t M) {
+  const uint32_t na = (a & M) | ((b << D) & ~M);
+  const uint32_t nb = ((a >> D) & M) | (b & ~M);
   a = na; b = nb;
 }
-B2T_HD void bitslice32(const uint32_t w[8], uint32_t b[8]) {
+B2T_HD void bitslice32(const uint32_t w[8], uint32_t b[8], SwapMasks k = SwapMasks{0x55555555u, 0x33333333u, 0x0F0F0F0Fu}) {
   // byte permutation: b[k] <- [byte k, byte k+8, byte k+16, byte k+24]
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -88,12 +89,9 @@ B2T_HD void bitslice32(const uint32_t w[8], uint32_t b[8]) {
     b[4 * h + 2] = bperm(t2, t3, 0x5410u); b[4 * h + 3] = bperm(t2, t3, 0x7632u);
   }
   // exchange register-index bit i with bit-index bit i (i = 0, 1, 2)
-  plane_swap<1, 0x55555555u>(b[0], b[1]); plane_swap<1, 0x55555555u>(b[2], b[3]);
-  plane_swap<1, 0x55555555u>(b[4], b[5]); plane_swap<1, 0x55555555u>(b[6], b[7]);
-  plane_swap<2, 0x33333333u>(b[0], b[2]); plane_swap<2, 0x33333333u>(b[1], b[3]);
-  plane_swap<2, 0x33333333u>(b[4], b[6]); plane_swap<2, 0x33333333u>(b[5], b[7]);
-  plane_swap<4, 0x0F0F0F0Fu>(b[0], b[4]); plane_swap<4, 0x0F0F0F0Fu>(b[1], b[5]);
-  plane_swap<4, 0x0F0F0F0Fu>(b[2], b[6]); plane_swap<4, 0x0F0F0F0Fu>(b[3], b[7]);
+  plane_swap<1>(b[0], b[1], k.m1); plane_swap<1>(b[2], b[3], k.m1); plane_swap<1>(b[4], b[5], k.m1); plane_swap<1>(b[6], b[7], k.m1);
+  plane_swap<2>(b[0], b[2], k.m2); plane_swap<2>(b[1], b[3], k.m2); plane_swap<2>(b[4], b[6], k.m2); plane_swap<2>(b[5], b[7], k.m2);
+  plane_swap<4>(b[0], b[4], k.m4); plane_swap<4>(b[1], b[5], k.m4); plane_swap<4>(b[2], b[6], k.m4); plane_swap<4>(b[3], b[7], k.m4);
 }
 
 // ---------------------------------------------------------------------------------------------- classification
@@ -164,25 +162,34 @@ B2T_HD FastCls classify_planes(const uint32_t b[8], uint32_t valid) {
     const uint32_t row5 = (c2 & k_ea) | (c5 & k_ed);                        // EA, ED
     uint32_t cl = tt_eval<LEAD_ALL_L, 6>(x) | (r0 & row0) | (r1 & row1) | (r4 & row4) | (r5 & row5);
     uint32_t co = tt_eval<LEAD_ALL_O, 6>(x) | (r4 & c2 & k_e2) | (r6 & c0 & k_f0);   // E2, F0
-    cl &= nlead; co &= nlead;
-    m.L |= cl;
-    m.unc = nlead & ~(cl | co);
+    // the two multi-byte spaces of everyday text: U+00A0 (C2 A0) and U+3000 (E3 80 80)
+    uint32_t cs = (r0 & c2 & ((b5 & ~(b4 | b3 | b2 | b1 | b0)) >> 1)) | (r4 & c3 & (z6 >> 1) & (z6 >> 2));
+    cl &= nlead; co &= nlead; cs &= nlead;
+    m.L |= cl; m.S |= cs;
+    m.unc = nlead & ~(cl | co | cs);
   }
   return m;
 }
 
-// Table look-up for the characters classify_planes left open (one per set bit of m.unc).
-template <class ByteAt, class Pos>
-B2T_HD void resolve_uncertain(FastCls& m, const ByteAt& at, Pos base, const uint32_t* __restrict__ cls_tbl) {
+// Table look-up for the characters classify_planes left open (one per set bit of m.unc).  at4(q) = the four bytes at
+// q..q+3 as a little-endian word (bytes past the end of the character are ignored; the text is valid UTF-8).
+template <class At4, class Pos>
+B2T_HD void resolve_uncertain(FastCls& m, const At4& at4, Pos base, const uint32_t* __restrict__ cls_tbl) {
   uint32_t todo = m.unc;
   while (todo) {
     const int p = ctz32(todo);
     todo &= todo - 1u;
-    int len;
-    const Pos q = base + (Pos)p;
-    const uint32_t c = decode_class(at(q), at(q + 1), at(q + 2), at(q + 3), cls_tbl, &len);
+    const uint32_t v = at4(base + (Pos)p);
+    const uint32_t b0 = v & 0xFFu;
+    const int len = 2 + (b0 >= 0xE0u) + (b0 >= 0xF0u);
+    // branch-free decode: the low 6 bits of all four bytes as if the character had 4 bytes, shifted down by the bytes
+    // it does not have, lead-byte marker bits masked off
+    const uint32_t t24 = ((v & 0x3Fu) << 18) | ((v << 4) & 0x3F000u) | ((v >> 10) & 0xFC0u) | ((v >> 24) & 0x3Fu);
+    uint32_t cp = (t24 >> (6 * (4 - len))) & ((2u << (5 * len)) - 1u);
+    cp = cp < 0x110000u ? cp : 0x10FFFFu;
+    const uint32_t c = class_of(cls_tbl, cp);
     const uint32_t bit = 1u << p;
-    if (c == CLS_L) m.L |= bit; else if (c == CLS_N) m.N |= bit; else if (c == CLS_S) m.S |= bit;
+    m.L |= c == CLS_L ? bit : 0u; m.N |= c == CLS_N ? bit : 0u; m.S |= c == CLS_S ? bit : 0u;
   }
   m.unc = 0u;
 }
@@ -222,9 +229,30 @@ B2T_HD uint32_t apply_overflow(uint32_t start, uint32_t lead, Overflow in) {
 // byte_level.rs:44   's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+
 // next_lead0 / next_S0: bit 0 of the next chunk's lead / S masks; ds / ds_next: doc-start words of this and the next chunk.
 // The result does not contain the previous chunk's overflow yet (apply_overflow).
-template <class ByteAt, class Pos>
+// Contraction length for the apostrophe whose following two bytes are b1, b2 (GPT-2: case-sensitive): 0 / 2 / 3.
+B2T_HD int contraction_len2(uint32_t a, uint32_t b) {
+  if (a == 's' || a == 't' || a == 'm' || a == 'd') return 2;
+  if ((a == 'r' || a == 'v') && b == 'e') return 3;
+  if (a == 'l' && b == 'l') return 3;
+  return 0;
+}
+
+// The bit the whitespace rule leaves open in fast_gpt2 when it is called with next_lead0 = next_S0 = 1: whether the
+// whitespace character that ends the chunk (or straddles its end) is the last one of its run and followed by a
+// non-space of the same document -- then \s+(?!\S) gives it back and it starts a split of its own.
+//   s31: bit 31 of the chunk's S mask; lead: its lead mask; nlead / nS: bits 0..3 of the NEXT chunk's lead / S masks
+//   (after fill and spill-in); ds_next: the next chunk's doc-start word.
+B2T_HD uint32_t finalize_gpt2(uint32_t start, uint32_t lead, uint32_t s31, uint32_t nlead, uint32_t nS, uint32_t ds_next) {
+  if (s31) {
+    const int k = ctz32((nlead & 7u) | 8u);   // bytes of my last character that lie in the next chunk (3: nothing follows)
+    if (k < 3 && lead && !((nS >> k) & 1u) && !((ds_next >> k) & 1u)) start |= 0x80000000u >> clz32(lead);
+  }
+  return start;
+}
+
+template <class At4, class Pos>
 B2T_HD FastOut fast_gpt2(const FastCls& m, const PrevTop& p, uint32_t next_lead0, uint32_t next_S0, uint32_t ds, uint32_t ds_next,
-                         Pos base, const ByteAt& at) {
+                         Pos base, const At4& at4) {
   FastOut o;
   o.drop = 0u; o.fallback = 0u; o.ov.bits = 0u;
   const uint32_t O = ~(m.L | m.N | m.S);
@@ -253,7 +281,8 @@ B2T_HD FastOut fast_gpt2(const FastCls& m, const PrevTop& p, uint32_t next_lead0
     while (cand) {
       const int a = ctz32(cand);
       cand &= cand - 1u;
-      const int len = contraction_len(at, base + (Pos)a, (Pos)0, false);
+      const uint32_t v = at4(base + (Pos)a);
+      const int len = contraction_len2((v >> 8) & 0xFFu, (v >> 16) & 0xFFu);
       if (!len) continue;
       if (ds64 & (((1ull << len) - 2ull) << a)) continue;          // the match must lie inside the document
       clr |= 1ull << (a + 1);

@@ -417,7 +417,10 @@ __device__ __noinline__ uint32_t exact_chunk_start(const uint8_t* __restrict__ b
 #define B2T_K1S_THREADS 128
 #endif
 #ifndef B2T_K1S_MINBLOCKS
-#define B2T_K1S_MINBLOCKS 4
+#define B2T_K1S_MINBLOCKS 8
+#endif
+#ifndef B2T_K1W_MINBLOCKS
+#define B2T_K1W_MINBLOCKS 4   // window (Llama-3) form: more live state
 #endif
 
 #ifdef B2T_K1_DEBUG
@@ -429,12 +432,41 @@ struct ByteAt32 {
   uint32_t n;
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i < n ? (uint32_t)__ldg(p + i) : 0u; }
 };
+// the four bytes at q..q+3 (q < n) as one word: two aligned loads and a funnel shift
+struct At4Global {
+  const uint32_t* __restrict__ words;
+  uint32_t n;
+  __device__ __forceinline__ uint32_t operator()(uint32_t q) const {
+    const uint32_t a0 = __ldg(words + (q >> 2)), a1 = ((q | 3u) + 1u < n) ? __ldg(words + (q >> 2) + 1) : 0u;
+    return __funnelshift_r(a0, a1, (q & 3u) * 8u);
+  }
+};
 
+// the chunk that holds the end of the batch: aligned word loads, bytes at or past n masked off (stays in registers)
+__device__ __forceinline__ void load_tail_words(const uint8_t* __restrict__ bytes, uint32_t base, uint32_t n, uint32_t w[8]) {
+  const uint32_t* __restrict__ words = reinterpret_cast<const uint32_t*>(bytes + base);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t p = base + 4u * j;
+    uint32_t x = 0u;
+    if (p < n) {
+      x = __ldg(words + j);
+      if (n - p < 4u) x &= (1u << (8u * (n - p))) - 1u;
+    }
+    w[j] = x;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- lean form (GPT-2, Whitespace, no regex)
+// Stage A (iteration j): bit planes, classes, and all of the boundary algebra that looks backwards.  Stage B
+// (iteration j - 1): the one bit that looks forwards (finalize_gpt2), the store and the page summary.  Between the two
+// a lane keeps six words, so the kernel runs at 64 registers.  There is one copy of the code: the loop starts one
+// iteration before the warp's range (its output is discarded, only the carries are kept).
 template <int KIND>
 __global__ void __launch_bounds__(B2T_K1S_THREADS, B2T_K1S_MINBLOCKS)
-pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_t* __restrict__ doc_bits,
-                     const uint32_t* __restrict__ cls_tbl, uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
-                     uint64_t* __restrict__ page_sum, int n_kb, int kb_per_warp) {
+pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_t* __restrict__ doc_bits,
+                   const uint32_t* __restrict__ cls_tbl, uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
+                   uint64_t* __restrict__ page_sum, int n_kb, int kb_per_warp, SwapMasks masks) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -443,7 +475,7 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
   const int it_hi = it_lo + kb_per_warp < n_kb ? it_lo + kb_per_warp : n_kb;
   const uint32_t n = (uint32_t)n64;
   const uint32_t n_chunks = n / CHUNK + 1;
-  const ByteAt32 at{bytes, n};
+  const At4Global at4{reinterpret_cast<const uint32_t*>(bytes), n};
   const int up = (lane + 31) & 31, down = (lane + 1) & 31;
 
   auto load = [&](int it, uint32_t w[8]) {       // it = -1: nothing there
@@ -455,7 +487,130 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) w[j] = 0u;
-      if (it >= 0 && base < n) load_chunk_words(bytes, base, n, w);   // the batch ends inside this chunk
+      if (it >= 0 && base < n) load_tail_words(bytes, base, n, w);
+    }
+  };
+
+  // carries of my chunk of the previous iteration (lane 31's chunk precedes lane 0's)
+  uint32_t kL = 0u, kN = 0u, kS = 0u, kSP = 0u, k_ov = 0u;
+  // stage A results of iteration j - 1, waiting for stage B
+  uint32_t p_start = 0u, p_drop = 0u, p_lead = 0u, p_head = 0u, p_ds = 0u, p_dsn = 0u, p_s31 = 0u;
+  uint32_t h_tot = 0u, h_aft = 0u, h_flag = 0u;   // first half of the current page
+
+  uint32_t w[8];
+  load(it_lo > 0 ? it_lo - 1 : -1, w);
+#pragma unroll 1
+  for (int j = it_lo - 1; j <= it_hi; ++j) {
+    // ================= stage A: iteration j
+    const uint32_t c = (uint32_t)j * 32u + lane, base = c * CHUNK;
+    const uint32_t valid = j < 0 || base >= n ? 0u : (n - base >= CHUNK ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (32u - (n - base))));
+    uint32_t b[8];
+    bitslice32(w, b, masks);
+    load(j + 1 <= it_hi ? j + 1 : -1, w);        // prefetch (the KB after the range is classified too, for its first bytes)
+    FastCls m = classify_planes<KIND>(b, valid);
+    if (__any_sync(FULL, m.hi != 0u)) {
+      if (m.unc) resolve_uncertain(m, at4, base, cls_tbl);
+      fill_own(m);
+    }
+    PrevTop pt;
+    pt.L = __shfl_sync(FULL, lane == 31 ? kL : m.L, up);
+    pt.S = __shfl_sync(FULL, lane == 31 ? kS : m.S, up);
+    if (KIND == PT_GPT2) {
+      pt.N = __shfl_sync(FULL, lane == 31 ? kN : m.N, up);
+      pt.SP = __shfl_sync(FULL, lane == 31 ? kSP : m.SP, up);
+    } else { pt.N = 0u; pt.SP = 0u; }
+    if (m.cont & 1u) spill_in(m, pt.L, pt.N, pt.S);
+    kL = m.L; kN = m.N; kS = m.S; kSP = m.SP;
+    const uint32_t ds = (j >= 0 && c < n_chunks) ? __ldg(doc_bits + c) : 0u;
+    const uint32_t ds_next = (j >= 0 && c + 1 < n_chunks) ? __ldg(doc_bits + c + 1) : 0u;
+    uint32_t start, drop = 0u;
+    if (KIND == PT_GPT2) {
+      const FastOut o = fast_gpt2(m, pt, 1u, 1u, ds, ds_next, base, at4);
+      Overflow in; in.bits = __shfl_sync(FULL, lane == 31 ? k_ov : o.ov.bits, up);
+      k_ov = o.ov.bits;
+      start = apply_overflow(o.start, m.lead, in);
+    } else if (KIND == PT_WHITESPACE) {
+      const FastOut o = fast_whitespace(m, pt, ds);
+      start = o.start; drop = o.drop;
+    } else {
+      start = ds & m.lead;
+    }
+    const uint32_t head = (m.lead & 15u) | ((m.S & 15u) << 4);
+    // ================= stage B: iteration j - 1
+    if (j > it_lo) {
+      const int it = j - 1;
+      const uint32_t pc = (uint32_t)it * 32u + lane;
+      uint32_t fin = p_start;
+      if (KIND == PT_GPT2) {
+        const uint32_t xh = __shfl_sync(FULL, lane == 0 ? head : p_head, down);
+        fin = finalize_gpt2(fin, p_lead, p_s31, xh & 15u, xh >> 4, p_dsn);
+      }
+      if (pc < n_chunks) {
+        start_bits[pc] = fin;
+        if (KIND == PT_WHITESPACE) drop_bits[pc] = p_drop;
+      }
+#ifdef B2T_K1_DEBUG
+      if (pc < 8192u) { uint32_t* d = g_k1_dbg + pc * 8; d[0] = p_lead; d[7] = fin; }
+#endif
+      // ---- page summary (segmented: counts restart at the last doc start of the page); one iteration is half a page
+      const uint32_t kept = fin & ~p_drop;
+      const uint32_t tot = (uint32_t)__popc(p_lead) | ((uint32_t)__popc(kept) << 16);
+      const unsigned dsm = __ballot_sync(FULL, p_ds != 0u);
+      const uint32_t wtot = __reduce_add_sync(FULL, tot);
+      uint32_t waft = 0u;
+      if (dsm) {
+        const int last = 31 - __clz((int)dsm);
+        uint32_t mine = 0u;
+        if (lane > last) mine = tot;
+        else if (lane == last) {
+          const uint32_t from = ~bits_below(31 - __clz((int)p_ds));
+          mine = (uint32_t)__popc(p_lead & from) | ((uint32_t)__popc(kept & from) << 16);
+        }
+        waft = __reduce_add_sync(FULL, mine);
+      }
+      const uint32_t wflag = dsm != 0u;
+      const uint32_t page = (uint32_t)it >> 1;
+      if (it & 1) {
+        const uint32_t a = wflag ? waft : h_aft + wtot, t = h_tot + wtot, f = h_flag | wflag;
+        if (lane == 0 && page * (uint32_t)PAGE <= n) page_sum[page] = pack_sum(t, a, f);
+      } else {
+        h_tot = wtot; h_aft = waft; h_flag = wflag;
+        if (it + 1 >= n_kb && lane == 0 && page * (uint32_t)PAGE <= n) page_sum[page] = pack_sum(h_tot, h_aft, h_flag);  // the batch ends in the first half
+      }
+    }
+    p_start = start; p_drop = drop; p_lead = m.lead; p_head = head; p_ds = ds; p_dsn = ds_next; p_s31 = m.S >> 31;
+  }
+}
+
+template <int KIND>
+// ---------------------------------------------------------------------------------------------- window form (Llama-3)
+// Same streaming structure with the 64-bit window algebra of pretok_logic.cuh (two iterations per trip).
+__global__ void __launch_bounds__(B2T_K1S_THREADS, B2T_K1W_MINBLOCKS)
+pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_t* __restrict__ doc_bits,
+                     const uint32_t* __restrict__ cls_tbl, uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
+                     uint64_t* __restrict__ page_sum, int n_kb, int kb_per_warp) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int it_lo = gw * kb_per_warp;             // even: a page is two consecutive iterations of one warp
+  if (it_lo >= n_kb) return;
+  const int it_hi = it_lo + kb_per_warp < n_kb ? it_lo + kb_per_warp : n_kb;
+  const uint32_t n = (uint32_t)n64;
+  const uint32_t n_chunks = n / CHUNK + 1;
+  static_assert(KIND == PT_LLAMA3, "the window form is the Llama-3 kernel");
+  const At4Global at4{reinterpret_cast<const uint32_t*>(bytes), n};
+  const int up = (lane + 31) & 31, down = (lane + 1) & 31;
+
+  auto load = [&](int it, uint32_t w[8]) {       // it = -1: nothing there
+    const uint32_t base = ((uint32_t)it * 32u + lane) * CHUNK;
+    if (it >= 0 && base + CHUNK <= n) {
+      const uint4* q = reinterpret_cast<const uint4*>(bytes + base);
+      const uint4 a = __ldg(q), b = __ldg(q + 1);
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = 0u;
+      if (it >= 0 && base < n) load_tail_words(bytes, base, n, w);   // the batch ends inside this chunk
     }
   };
   // classes of iteration `it`; `prev` = this lane's classes of the iteration before (lane 31's chunk precedes lane 0's)
@@ -470,7 +625,7 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
 #else
     if (__any_sync(FULL, m.hi != 0u)) {
 #endif
-      if (m.unc) resolve_uncertain(m, at, base, cls_tbl);
+      if (m.unc) resolve_uncertain(m, at4, base, cls_tbl);
       fill_own(m);
     }
     // the chunk before mine (only bit 31 of the class words matters to the fast algebra; Llama-3 uses the top halves)
@@ -486,7 +641,6 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
     if (m.cont & 1u) spill_in(m, pm.L, pm.N, pm.S);
   };
 
-  uint32_t ov_mine = 0u;            // contraction overflow of my chunk of the previous iteration (lane 31's feeds lane 0)
   uint32_t h_tot = 0u, h_aft = 0u, h_flag = 0u;   // first half of the current page
 
   // One iteration: classify it+1 (words in w) into nxt / pnxt, refill w with the words of it+3, then boundaries,
@@ -499,20 +653,7 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
     const uint32_t ds = c < n_chunks ? __ldg(doc_bits + c) : 0u;
     const uint32_t ds_next = c + 1 < n_chunks ? __ldg(doc_bits + c + 1) : 0u;
     uint32_t start, drop = 0u;
-    if (KIND == PT_GPT2) {
-      const uint32_t head = (cur.lead & 1u) | ((cur.S & 1u) << 1), nhead = (nxt.lead & 1u) | ((nxt.S & 1u) << 1);
-      const uint32_t xh = __shfl_sync(FULL, lane == 0 ? nhead : head, down);
-      PrevTop pt; pt.L = pcur.L; pt.N = pcur.N; pt.S = pcur.S; pt.SP = pcur.SP;
-      const FastOut o = fast_gpt2(cur, pt, xh & 1u, (xh >> 1) & 1u, ds, ds_next, base, at);
-      Overflow in; in.bits = __shfl_sync(FULL, lane == 31 ? ov_mine : o.ov.bits, up);
-      ov_mine = o.ov.bits;
-      start = apply_overflow(o.start, cur.lead, in);
-      if (o.fallback) start = exact_chunk_start<KIND>(bytes, n64, c, cls_tbl, doc_bits);
-    } else if (KIND == PT_WHITESPACE) {
-      PrevTop pt; pt.L = pcur.L; pt.N = 0u; pt.S = pcur.S; pt.SP = 0u;
-      const FastOut o = fast_whitespace(cur, pt, ds);
-      start = o.start; drop = o.drop;
-    } else if (KIND == PT_LLAMA3) {
+    {
       // window algebra of pretok_logic.cuh on [16 B of the previous chunk | mine | 16 B of the next chunk]
       Window wd;
       auto nextw = [&](uint32_t mine, uint32_t theirs) { return __shfl_sync(FULL, lane == 0 ? theirs : mine, down); };
@@ -527,8 +668,6 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
       const BoundaryOut r = boundaries_llama3(wd, (int64_t)base - 16, at64, cy);
       start = r.start;
       if (r.slow) start = exact_chunk_start<KIND>(bytes, n64, c, cls_tbl, doc_bits);
-    } else {
-      start = ds & cur.lead;
     }
     if (c < n_chunks) {
       start_bits[c] = start;
@@ -571,13 +710,6 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
     zero.lead = zero.cont = zero.hi = zero.L = zero.N = zero.S = zero.SP = zero.AP = zero.NL = zero.unc = 0u;
     load(it_lo - 1, w0);
     classify(w0, it_lo - 1, zero, B, pB);
-    if (KIND == PT_GPT2 && it_lo > 0) {
-      // a contraction that starts in the last chunk before the range reaches into the range's first chunk
-      const uint32_t c = (uint32_t)(it_lo - 1) * 32u + lane;
-      const uint32_t ds = c < n_chunks ? __ldg(doc_bits + c) : 0u, ds_next = c + 1 < n_chunks ? __ldg(doc_bits + c + 1) : 0u;
-      PrevTop pt; pt.L = pB.L; pt.N = pB.N; pt.S = pB.S; pt.SP = pB.SP;
-      ov_mine = fast_gpt2(B, pt, 1u, 0u, ds, ds_next, c * CHUNK, at).ov.bits;
-    }
     load(it_lo, w0);
     classify(w0, it_lo, B, A, pA);
     load(it_lo + 1, w0);
