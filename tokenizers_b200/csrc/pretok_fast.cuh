@@ -35,6 +35,19 @@ B2T_HD uint32_t bperm(uint32_t x, uint32_t y, uint32_t s) {
 B2T_HD uint32_t fsl(uint32_t lo, uint32_t hi, int k) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << k) >> 32); }
 B2T_HD uint32_t fsr(uint32_t lo, uint32_t hi, int k) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> k); }
 #endif
+// x >> K for a constant K.  On the device as a multiply-high: the shift units share the integer pipe with the logic
+// ops that bound this kernel, the multiplier sits on the other pipe (measured on B200: no gain, the multiply-high is no cheaper than the shift -- kept switchable, off by default).
+#ifndef B2T_SHR_MULHI
+#define B2T_SHR_MULHI 0
+#endif
+template <int K>
+B2T_HD uint32_t shr(uint32_t x) {
+#if defined(__CUDA_ARCH__) && B2T_SHR_MULHI
+  return __umulhi(x, 1u << (32 - K));
+#else
+  return x >> K;
+#endif
+}
 // 3-input look-up: bit (a b c) of TB.  Written as a sum of minterms over three variables, which nvcc folds into ONE LOP3.
 // (An inline-asm lop3 here produced wrong class masks on sm_100a when the call sat next to a warp vote -- measured on
 // the GPU against the CPU run of this very file, profiles/k1_experiments_r02.md -- so the compiler does the folding.)
@@ -76,7 +89,7 @@ struct SwapMasks { uint32_t m1, m2, m4; };   // 0x55555555, 0x33333333, 0x0F0F0F
 template <uint32_t D>
 B2T_HD void plane_swap(uint32_t& a, uint32_t& b, uint32_t M) {
   const uint32_t na = (a & M) | ((b << D) & ~M);
-  const uint32_t nb = ((a >> D) & M) | (b & ~M);
+  const uint32_t nb = (shr<D>(a) & M) | (b & ~M);
   a = na; b = nb;
 }
 B2T_HD void bitslice32(const uint32_t w[8], uint32_t b[8], SwapMasks k = SwapMasks{0x55555555u, 0x33333333u, 0x0F0F0F0Fu}) {
@@ -98,6 +111,8 @@ B2T_HD void bitslice32(const uint32_t w[8], uint32_t b[8], SwapMasks k = SwapMas
 struct FastCls {
   uint32_t lead, cont, hi;        // byte starts a character / is a continuation byte / is not ASCII
   uint32_t L, N, S, SP, AP, NL;   // class masks; after fill_own + spill_in every byte carries its character's class
+  uint32_t A2, A3;                // GPT-2: apostrophes followed by s|t|m|d / by re|ve|ll inside the chunk (AP keeps only the
+                                  // apostrophes whose letters lie past the chunk end: they take the per-apostrophe path)
   uint32_t unc;                   // non-ASCII lead bytes whose class still needs the table (resolve_uncertain)
 };
 
@@ -124,12 +139,26 @@ B2T_HD FastCls classify_planes(const uint32_t b[8], uint32_t valid) {
   const uint32_t wsctl = c00 & b3 & (b2 | b1 | b0) & ~(b2 & b1);   // 0x09..0x0D
   m.SP = sp;
   m.S = sp | wsctl;
+  m.A2 = 0u; m.A3 = 0u;
   if (KIND == PT_WHITESPACE) {
     m.L = alpha | digit | (~b7 & b6 & ~b5 & b4 & b3 & b2 & b1 & b0);   // \w on ASCII: letters, digits, '_' (0x5F)
     m.N = 0u; m.AP = 0u; m.NL = 0u;
   } else {
     m.L = alpha; m.N = digit;
     m.AP = c20 & ~b3 & b2 & b1 & b0;                         // 0x27
+    if (KIND == PT_GPT2) {
+      // 's 't 'm 'd / 're 've 'll (case-sensitive): letter tests on the low 5 bits of 0x60..0x7F
+      const uint32_t lower = ~b7 & b6 & b5;
+      const uint32_t x5[5] = {b0, b1, b2, b3, b4};
+      const uint32_t stmd = lower & tt_eval<(1ull << 19) | (1ull << 20) | (1ull << 13) | (1ull << 4), 5>(x5);
+      const uint32_t rv = lower & tt_eval<(1ull << 18) | (1ull << 22), 5>(x5);
+      const uint32_t le = lower & tt_eval<(1ull << 5), 5>(x5), ll = lower & tt_eval<(1ull << 12), 5>(x5);
+      const uint32_t f3 = (rv & shr<1>(le)) | (ll & shr<1>(ll));    // first letter of re / ve / ll (both letters inside the chunk)
+      m.A2 = m.AP & shr<1>(stmd);
+      m.A3 = m.AP & shr<1>(f3);
+      // undecidable here: the apostrophe at bit 31, and the one at bit 30 when its letter is r / v / l
+      m.AP &= 0x80000000u | (0x40000000u & shr<1>(rv | ll));
+    }
     m.NL = KIND == PT_LLAMA3 ? (c00 & b3 & ~(b2 ^ b0) & (b1 ^ b0)) : 0u;   // 0x0A, 0x0D
   }
   // ---- non-ASCII: characters whose class follows from their first bytes
@@ -139,17 +168,18 @@ B2T_HD FastCls classify_planes(const uint32_t b[8], uint32_t valid) {
     // conditions on a continuation byte (its low 6 bits), moved to the position of the byte before it; a lead byte at
     // position 31 sees zeros and stays uncertain
     const uint32_t x54 = b5 & b4, o54 = b5 | b4;
-    const uint32_t k_c3 = (~(b4 & ~b3 & b2 & b1 & b0)) >> 1;             // != 0x97, 0xB7     (U+00D7, U+00F7)
-    const uint32_t k_ce = (b5 & (b4 | b3 | lo3)) >> 1;                   // >= 0xA3           (U+03A3..)
-    const uint32_t k_cf = (~(x54 & ~b3 & b2 & b1 & ~b0)) >> 1;           // != 0xB6           (U+03F6)
-    const uint32_t k_e4 = (~(x54 & ~b3 & b2 & b1 & b0)) >> 1;            // != 0xB7           (U+4DC0..U+4DFF)
-    const uint32_t k_e3 = o54 >> 1;                                      // >= 0x90           (U+3400..)
-    const uint32_t k_ea = x54 >> 1;                                      // >= 0xB0           (U+AC00..)
-    const uint32_t k_ed = (~b5 & ~(b4 & b3 & b2 & b1)) >> 1;             // <= 0x9D           (..U+D77F)
+    const uint32_t k_c3 = shr<1>(~(b4 & ~b3 & b2 & b1 & b0));            // != 0x97, 0xB7     (U+00D7, U+00F7)
+    const uint32_t k_ce = shr<1>(b5 & (b4 | b3 | lo3));                  // >= 0xA3           (U+03A3..)
+    const uint32_t k_cf = shr<1>(~(x54 & ~b3 & b2 & b1 & ~b0));          // != 0xB6           (U+03F6)
+    const uint32_t k_e4 = shr<1>(~(x54 & ~b3 & b2 & b1 & b0));           // != 0xB7           (U+4DC0..U+4DFF)
+    const uint32_t k_e3 = shr<1>(o54);                                   // >= 0x90           (U+3400..)
+    const uint32_t k_ea = shr<1>(x54);                                   // >= 0xB0           (U+AC00..)
+    const uint32_t k_ed = shr<1>(~b5 & ~(b4 & b3 & b2 & b1));            // <= 0x9D           (..U+D77F)
     const uint32_t z6 = ~(b5 | b4 | b3 | b2 | b1 | b0);                  // == 0x80
-    const uint32_t k_e2 = (z6 >> 1) & (((~b5 & b4) | (b5 & ~b4 & ~b3)) >> 2);   // E2 80 90..A7  (U+2010..U+2027)
+    const uint32_t z6s = shr<1>(z6);
+    const uint32_t k_e2 = z6s & shr<2>((~b5 & b4) | (b5 & ~b4 & ~b3));   // E2 80 90..A7      (U+2010..U+2027)
     const uint32_t f9f = ~b5 & b4 & b3 & b2 & b1 & b0;                   // == 0x9F
-    const uint32_t k_f0 = (f9f >> 1) & ((~((~(b5 | b4 | b3) & b2) | (b5 & ~b4 & b3 & b2 & b1 & b0))) >> 2);  // F0 9F, third byte not 84..87, AF
+    const uint32_t k_f0 = shr<1>(f9f) & shr<2>(~((~(b5 | b4 | b3) & b2) | (b5 & ~b4 & b3 & b2 & b1 & b0)));  // F0 9F, third byte not 84..87, AF
     const uint32_t x[6] = {b0, b1, b2, b3, b4, b5};
     // lead byte & 63 = 8 * row + col: one look-up per row (b5 b4 b3) and per column (b2 b1 b0) that a rule names
     const uint32_t r0 = lop3<0x01>(b5, b4, b3), r1 = lop3<0x02>(b5, b4, b3), r4 = lop3<0x10>(b5, b4, b3),
@@ -163,7 +193,7 @@ B2T_HD FastCls classify_planes(const uint32_t b[8], uint32_t valid) {
     uint32_t cl = tt_eval<LEAD_ALL_L, 6>(x) | (r0 & row0) | (r1 & row1) | (r4 & row4) | (r5 & row5);
     uint32_t co = tt_eval<LEAD_ALL_O, 6>(x) | (r4 & c2 & k_e2) | (r6 & c0 & k_f0);   // E2, F0
     // the two multi-byte spaces of everyday text: U+00A0 (C2 A0) and U+3000 (E3 80 80)
-    uint32_t cs = (r0 & c2 & ((b5 & ~(b4 | b3 | b2 | b1 | b0)) >> 1)) | (r4 & c3 & (z6 >> 1) & (z6 >> 2));
+    uint32_t cs = (r0 & c2 & shr<1>(b5 & ~(b4 | b3 | b2 | b1 | b0))) | (r4 & c3 & z6s & shr<2>(z6));
     cl &= nlead; co &= nlead; cs &= nlead;
     m.L |= cl; m.S |= cs;
     m.unc = nlead & ~(cl | co | cs);
@@ -273,8 +303,15 @@ B2T_HD FastOut fast_gpt2(const FastCls& m, const PrevTop& p, uint32_t next_lead0
   if (((m.S & m.hi) >> 31) & (next_lead0 ^ 1u)) o.fallback = 1u;  // its bytes continue in the next chunk
   start |= m.S & (~pS | lastchar);
   start |= ds;
-  // contractions: the apostrophe must sit at a match start
-  uint32_t cand = m.AP & (pL | pN | (pS & ~pSP) | ds);
+  // contractions: the apostrophe must sit at a match start, the whole match inside the document
+  const uint32_t at_start = pL | pN | (pS & ~pSP) | ds;
+  {
+    const uint32_t nDS2 = fsr(ds, ds_next, 2);
+    const uint32_t c2 = m.A2 & at_start & ~nDS, c3 = m.A3 & at_start & ~nDS & ~nDS2, cc = c2 | c3;
+    start = (start & ~(cc << 1)) | (c2 << 2) | (c3 << 3);       // the letter after the apostrophe does not start a split, the character after the match does
+    o.ov.bits = ((c2 >> 30) | (c3 >> 29)) & 1u;                  // 's at bit 30 / 're at bit 29: that character is the next chunk's first
+  }
+  uint32_t cand = m.AP & at_start;                                // letters in the next chunk: one at a time, from the bytes
   if (cand) {
     const uint64_t ds64 = (uint64_t)ds | ((uint64_t)ds_next << 32);
     uint64_t set = 0, clr = 0;
@@ -289,7 +326,7 @@ B2T_HD FastOut fast_gpt2(const FastCls& m, const PrevTop& p, uint32_t next_lead0
       set |= 1ull << (a + len);
     }
     start = (start & ~(uint32_t)clr) | (uint32_t)set;
-    o.ov.bits = (uint32_t)(set >> 32) | ((uint32_t)(clr >> 32) << 8);
+    o.ov.bits |= (uint32_t)(set >> 32) | ((uint32_t)(clr >> 32) << 8);
   }
   o.start = start & m.lead;
   return o;

@@ -503,10 +503,19 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
   for (int j = it_lo - 1; j <= it_hi; ++j) {
     // ================= stage A: iteration j
     const uint32_t c = (uint32_t)j * 32u + lane, base = c * CHUNK;
-    const uint32_t valid = j < 0 || base >= n ? 0u : (n - base >= CHUNK ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (32u - (n - base))));
+    // interior iteration (warp-uniform): this KB and the first chunk of the next one lie inside the batch
+    const bool interior = j >= 0 && ((uint32_t)j * 32u + 33u) * CHUNK <= n;
+    uint32_t valid = 0xFFFFFFFFu;
+    if (!interior) valid = j < 0 || base >= n ? 0u : (n - base >= CHUNK ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (32u - (n - base))));
     uint32_t b[8];
     bitslice32(w, b, masks);
-    load(j + 1 <= it_hi ? j + 1 : -1, w);        // prefetch (the KB after the range is classified too, for its first bytes)
+    if (j + 1 < it_hi && ((uint32_t)j * 32u + 64u) * CHUNK <= n) {   // prefetch; the common case first: a whole KB inside the batch
+      const uint4* q = reinterpret_cast<const uint4*>(bytes + (uint32_t)(base + 32u * CHUNK));   // (j = -1: the sum wraps to lane * 32)
+      const uint4 a = __ldg(q), bq = __ldg(q + 1);
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = bq.x; w[5] = bq.y; w[6] = bq.z; w[7] = bq.w;
+    } else {
+      load(j + 1 <= it_hi ? j + 1 : -1, w);      // range / batch ends (the KB after the range is classified too, for its first bytes)
+    }
     FastCls m = classify_planes<KIND>(b, valid);
     if (__any_sync(FULL, m.hi != 0u)) {
       if (m.unc) resolve_uncertain(m, at4, base, cls_tbl);
@@ -521,8 +530,9 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
     } else { pt.N = 0u; pt.SP = 0u; }
     if (m.cont & 1u) spill_in(m, pt.L, pt.N, pt.S);
     kL = m.L; kN = m.N; kS = m.S; kSP = m.SP;
-    const uint32_t ds = (j >= 0 && c < n_chunks) ? __ldg(doc_bits + c) : 0u;
-    const uint32_t ds_next = (j >= 0 && c + 1 < n_chunks) ? __ldg(doc_bits + c + 1) : 0u;
+    uint32_t ds, ds_next;
+    if (interior) { ds = __ldg(doc_bits + c); ds_next = __ldg(doc_bits + c + 1); }
+    else { ds = (j >= 0 && c < n_chunks) ? __ldg(doc_bits + c) : 0u; ds_next = (j >= 0 && c + 1 < n_chunks) ? __ldg(doc_bits + c + 1) : 0u; }
     uint32_t start, drop = 0u;
     if (KIND == PT_GPT2) {
       const FastOut o = fast_gpt2(m, pt, 1u, 1u, ds, ds_next, base, at4);
@@ -549,9 +559,6 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
         start_bits[pc] = fin;
         if (KIND == PT_WHITESPACE) drop_bits[pc] = p_drop;
       }
-#ifdef B2T_K1_DEBUG
-      if (pc < 8192u) { uint32_t* d = g_k1_dbg + pc * 8; d[0] = p_lead; d[7] = fin; }
-#endif
       // ---- page summary (segmented: counts restart at the last doc start of the page); one iteration is half a page
       const uint32_t kept = fin & ~p_drop;
       const uint32_t tot = (uint32_t)__popc(p_lead) | ((uint32_t)__popc(kept) << 16);
