@@ -216,6 +216,10 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
   e->dt.edge_mask = ht.edge_tbl.empty() ? 0 : (uint32_t)ht.edge_tbl.size() - 1;
   e->dt.unk_id = ht.unk_id;
   e->dt.max_chars = ht.max_chars;
+  // the page kernels use ~23 KB of shared memory per block, 8 blocks per SM: leave the rest of the 228 KB pool to L1
+  // (the merge-table probes of the merge rounds are read-only loads and hit there)
+  cudaFuncSetAttribute(model_tile_kernel<MODEL_BPE>, cudaFuncAttributePreferredSharedMemoryCarveout, 86);
+  cudaFuncSetAttribute(model_tile_kernel<MODEL_WORDPIECE>, cudaFuncAttributePreferredSharedMemoryCarveout, 86);
   cudaError_t se = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) { b2t_engine_destroy(e); return fail(B2T_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(se)); }
   *out = e;

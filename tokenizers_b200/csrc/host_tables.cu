@@ -61,8 +61,11 @@ std::string build_host_tables(int model, int pretok, int ignore_merges, uint32_t
   }
   std::unordered_map<std::string, uint32_t> vocab;
   vocab.reserve((size_t)n_vocab * 2);
-  for (uint32_t i = 0; i < n_vocab; ++i)
+  for (uint32_t i = 0; i < n_vocab; ++i) {
+    // the page kernels keep (id, length) of a token in one 32-bit word: 20 bits of id (model_kernels.cuh tok_pack)
+    if (vocab_ids[i] >= (1u << 20)) return "token ids of 2^20 and above are not supported";
     vocab[std::string((const char*)vocab_bytes + vocab_off[i], vocab_off[i + 1] - vocab_off[i])] = vocab_ids[i];
+  }
   out->max_chars = max_chars;
 
   if (model == 0) {
@@ -155,6 +158,9 @@ std::string build_host_tables(int model, int pretok, int ignore_merges, uint32_t
   } else {
     // ---- WordPiece: byte trie with two roots
     if (!unk_token) return "WordPiece needs unk_token";
+    // the WordPiece page kernel keeps a 416-byte halo: a word of max_input_chars_per_word 4-byte characters must fit it
+    // (a longer limit would silently turn long multi-byte words into [UNK])
+    if ((uint64_t)max_chars * 4 > 416) return "max_input_chars_per_word above 104 is not supported";
     auto iu = vocab.find(unk_token);
     if (iu == vocab.end()) {
       *vocab_err = true;

@@ -86,6 +86,14 @@ __device__ __forceinline__ int warp_prefix_words(const uint32_t* bits, uint16_t*
 
 __device__ __forceinline__ uint32_t mask_le(int b) { return b >= 31 ? 0xFFFFFFFFu : ((2u << b) - 1u); }
 
+// One word per byte position of the page: token id (low 20 bits) and token length in bytes (high 12 bits); length 0 =
+// no token starts here.  (Ids and lengths used to be two arrays; one array leaves 4.5 KB of the SM's shared memory /
+// L1 pool to L1, where the merge-table probes of the merge rounds then hit.)  b2t_engine_create refuses ids >= 2^20.
+constexpr int TOK_ID_BITS = 20;
+__device__ __forceinline__ uint32_t tok_pack(uint32_t id, int len) { return id | ((uint32_t)len << TOK_ID_BITS); }
+__device__ __forceinline__ int tok_len(uint32_t x) { return (int)(x >> TOK_ID_BITS); }
+__device__ __forceinline__ uint32_t tok_id(uint32_t x) { return x & ((1u << TOK_ID_BITS) - 1u); }
+
 
 // ------------------------------------------------------------------------------------------------ word cache
 // The reference keeps a per-thread word cache in front of merge_word (models/bpe/model.rs:24-90, 568-586) because
@@ -135,8 +143,8 @@ __device__ __forceinline__ void wc_make_key(const uint8_t* s_byte, int s, int le
   if (key.fp == 0) key.fp = 1;
 }
 
-// Returns true on a hit (tokens written to s_id / s_len).
-__device__ __forceinline__ bool wc_lookup(uint4* cache, uint32_t mask, const WordKey& key, int s, uint32_t* s_id, uint16_t* s_len) {
+// Returns true on a hit (tokens written to s_tok).
+__device__ __forceinline__ bool wc_lookup(uint4* cache, uint32_t mask, const WordKey& key, int s, uint32_t* s_tok) {
   uint32_t slot = key.slot & mask;
 #pragma unroll 1
   for (int pr = 0; pr < WC_PROBES; ++pr, slot = (slot + 1) & mask) {
@@ -158,22 +166,22 @@ __device__ __forceinline__ bool wc_lookup(uint4* cache, uint32_t mask, const Wor
     int pos = s;
 #pragma unroll
     for (int t = 0; t < WC_MAX_TOK; ++t)
-      if (t < ntok) { s_id[pos] = ids[t]; s_len[pos] = (uint16_t)lens[t]; pos += (int)lens[t]; }
+      if (t < ntok) { s_tok[pos] = tok_pack(ids[t], (int)lens[t]); pos += (int)lens[t]; }
     return true;
   }
   return false;
 }
 
-// Publish the merged pre-token [s, e) (symbols chained by s_len) into the first free slot of its probe sequence.
-__device__ __forceinline__ void wc_publish(uint4* cache, uint32_t mask, const WordKey& key, int s, int e, const uint32_t* s_id,
-                                           const uint16_t* s_len) {
+// Publish the merged pre-token [s, e) (symbols chained by their lengths) into the first free slot of its probe sequence.
+__device__ __forceinline__ void wc_publish(uint4* cache, uint32_t mask, const WordKey& key, int s, int e, const uint32_t* s_tok) {
   uint32_t ids[6] = {0, 0, 0, 0, 0, 0}, lens[6] = {0, 0, 0, 0, 0, 0};
   int nt = 0, p = s;
   while (p < e) {
     if (nt == WC_MAX_TOK) return;  // too many tokens for a slot
-    const int l = s_len[p];
+    const uint32_t tk = s_tok[p];
+    const int l = tok_len(tk);
 #pragma unroll
-    for (int t = 0; t < WC_MAX_TOK; ++t) if (t == nt) { ids[t] = s_id[p]; lens[t] = (uint32_t)l; }
+    for (int t = 0; t < WC_MAX_TOK; ++t) if (t == nt) { ids[t] = tok_id(tk); lens[t] = (uint32_t)l; }
     ++nt; p += l;
   }
   uint32_t slot = key.slot & mask;
@@ -196,8 +204,8 @@ __device__ __forceinline__ void wc_publish(uint4* cache, uint32_t mask, const Wo
   }
 }
 
-// models/bpe/model.rs:558-567 (ignore_merges): is the whole pre-token a vocabulary entry?  Writes its id to s_id[s].
-__device__ __forceinline__ bool vocab_whole_word(const DeviceTables& t, const uint8_t* s_byte, int s, int len, uint32_t* s_id) {
+// models/bpe/model.rs:558-567 (ignore_merges): is the whole pre-token a vocabulary entry?  Writes it (one token) to s_tok[s].
+__device__ __forceinline__ bool vocab_whole_word(const DeviceTables& t, const uint8_t* s_byte, int s, int len, uint32_t* s_tok) {
   StrHash h; strhash_init(h);
   for (int p = s; p < s + len; ++p) strhash_byte(h, s_byte[p]);
   strhash_fin(h);
@@ -209,7 +217,7 @@ __device__ __forceinline__ bool vocab_whole_word(const DeviceTables& t, const ui
       const uint8_t* q = t.word_pool + en.w;
       bool same = true;
       for (int i = 0; i < len; ++i) if (__ldg(q + i) != s_byte[s + i]) { same = false; break; }
-      if (same) { s_id[s] = en.z; return true; }
+      if (same) { s_tok[s] = tok_pack(en.z, len); return true; }
     }
     slot = (slot + 1) & t.word_mask;
   }
@@ -222,20 +230,20 @@ __device__ __forceinline__ bool vocab_whole_word(const DeviceTables& t, const ui
 // merges, and the (at most two) pairs that changed are looked up again.  All groups of a warp step together; the
 // control flow is warp-uniform, so nothing diverges -- idle groups are predicated off.
 template <int G, int J>
-__device__ __forceinline__ void coop_bpe(const DeviceTables& t, const uint8_t* s_byte, uint32_t* s_id, uint16_t* s_len, int s, int e,
+__device__ __forceinline__ void coop_bpe(const DeviceTables& t, const uint8_t* s_byte, uint32_t* s_tok, int s, int e,
                                          bool active, int gl) {
   uint32_t rk[J], ni[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int p = s + gl + G * j;
     rk[j] = 0xFFFFFFFFu; ni[j] = 0u;
-    if (active && p < e) { s_id[p] = __ldg(t.byte_to_id + s_byte[p]); s_len[p] = 1; }
+    if (active && p < e) s_tok[p] = tok_pack(__ldg(t.byte_to_id + s_byte[p]), 1);
   }
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int p = s + gl + G * j;
-    if (active && p + 1 < e) { const uint64_t v = merge_lookup(t, s_id[p], s_id[p + 1]); rk[j] = (uint32_t)(v >> 32); ni[j] = (uint32_t)v; }
+    if (active && p + 1 < e) { const uint64_t v = merge_lookup(t, tok_id(s_tok[p]), tok_id(s_tok[p + 1])); rk[j] = (uint32_t)(v >> 32); ni[j] = (uint32_t)v; }
   }
   while (true) {
     // leftmost minimum over my positions (they grow with j), then over the group
@@ -254,11 +262,11 @@ __device__ __forceinline__ void coop_bpe(const DeviceTables& t, const uint8_t* s
     uint32_t nid = 0;
     if (have) {
       // everybody in the group derives the same facts from shared memory (read before the owner writes)
-      const int ql = s_len[bp];
+      const int ql = tok_len(s_tok[bp]);
       const int q = bp + ql;
-      nx = q + s_len[q];
+      nx = q + tok_len(s_tok[q]);
       pv = bp - 1;
-      while (pv >= s && s_len[pv] == 0) --pv;
+      while (pv >= s && tok_len(s_tok[pv]) == 0) --pv;
     }
     __syncwarp();
     if (have) {
@@ -267,23 +275,23 @@ __device__ __forceinline__ void coop_bpe(const DeviceTables& t, const uint8_t* s
         const int p = s + gl + G * j;
         if (p == bp) {  // owner of the winning pair: merge right into left
           nid = ni[j];
-          const int q = bp + s_len[bp];
-          s_id[bp] = nid; s_len[bp] = (uint16_t)(nx - bp); s_len[q] = 0;
+          const int q = bp + tok_len(s_tok[bp]);
+          s_tok[bp] = tok_pack(nid, nx - bp); s_tok[q] = 0u;
         }
         if (p > bp && p < nx) rk[j] = 0xFFFFFFFFu;  // the swallowed symbol no longer starts a pair
       }
     }
     __syncwarp();
     if (have) {
-      const uint32_t newid = s_id[bp];
+      const uint32_t newid = tok_id(s_tok[bp]);
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const int p = s + gl + G * j;
         if (p == bp) {
           rk[j] = 0xFFFFFFFFu;
-          if (nx < e) { const uint64_t v = merge_lookup(t, newid, s_id[nx]); rk[j] = (uint32_t)(v >> 32); ni[j] = (uint32_t)v; }
+          if (nx < e) { const uint64_t v = merge_lookup(t, newid, tok_id(s_tok[nx])); rk[j] = (uint32_t)(v >> 32); ni[j] = (uint32_t)v; }
         } else if (p == pv) {
-          const uint64_t v = merge_lookup(t, s_id[pv], newid); rk[j] = (uint32_t)(v >> 32); ni[j] = (uint32_t)v;
+          const uint64_t v = merge_lookup(t, tok_id(s_tok[pv]), newid); rk[j] = (uint32_t)(v >> 32); ni[j] = (uint32_t)v;
         }
       }
     }
@@ -302,8 +310,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   constexpr int TW = TILE / 32;
   static_assert(NW <= 96, "warp_prefix_words handles <= 96 words");
   __shared__ __align__(16) uint8_t s_byte[SPAN];
-  __shared__ uint16_t s_len[SPAN];
-  __shared__ uint32_t s_id[SPAN];
+  __shared__ __align__(16) uint32_t s_tok[SPAN];   // tok_pack(id, length) of the token that starts at each position
   __shared__ uint32_t s_startb[NW + 1], s_keptb[NW + 1], s_leadb[NW + 1], s_tokb[NW + 1], s_dsb[TW + 1];
   __shared__ uint16_t s_apref[NW + 1], s_spref[NW + 1], s_lpref[NW + 1], s_tpref[NW + 1];
   __shared__ int16_t s_dlast[TW + 1];
@@ -356,14 +363,24 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
     if (w <= TW) s_dsb[w] = (w < TW && gw < n_chunks) ? __ldg(P.doc_bits + gw) : 0u;
   }
   __syncthreads();
-  // lead bits + symbol init, one 32-byte row per warp iteration
-  for (int row = warp; row < NW; row += NWARPS) {
-    int pos = row * 32 + lane;
-    uint32_t b = s_byte[pos];
-    bool lead = ((b & 0xC0u) != 0x80u) && (base + pos < n);
-    uint32_t lb = __ballot_sync(0xFFFFFFFFu, lead);
-    if (lane == 0) s_leadb[row] = lb;
-    s_len[pos] = 0;  // token starts are written by whoever resolves the pre-token
+  // lead bits (16 bytes per thread: continuation-byte flags by SWAR, two threads make one bitmap word) + symbol init
+  static_assert(SPAN / 16 <= MODEL_THREADS && (SPAN / 16) % 2 == 0, "one pass, thread pairs inside a warp");
+  {
+    const int i = tid;
+    const bool act = i < SPAN / 16;
+    const uint4 v = act ? reinterpret_cast<const uint4*>(s_byte)[i] : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t c0 = v.x & ~(v.x << 1) & 0x80808080u, c1 = v.y & ~(v.y << 1) & 0x80808080u,
+                   c2 = v.z & ~(v.z << 1) & 0x80808080u, c3 = v.w & ~(v.w << 1) & 0x80808080u;   // 10xxxxxx
+    const uint32_t cont = movemask2(c0, c1) | (movemask2(c2, c3) << 8);
+    const int64_t lim = n - base - (int64_t)i * 16;          // valid bytes from this thread's first position on
+    const uint32_t valid = lim >= 16 ? 0xFFFFu : (lim <= 0 ? 0u : ((1u << (int)lim) - 1u));
+    const uint32_t lead16 = ~cont & valid;
+    const uint32_t other = __shfl_down_sync(0xFFFFFFFFu, lead16, 1);
+    if (act && !(i & 1)) s_leadb[i >> 1] = lead16 | (other << 16);
+    if (act) {   // token starts are written by whoever resolves the pre-token
+      uint4* z = reinterpret_cast<uint4*>(s_tok) + 4 * i;
+      z[0] = make_uint4(0u, 0u, 0u, 0u); z[1] = make_uint4(0u, 0u, 0u, 0u); z[2] = make_uint4(0u, 0u, 0u, 0u); z[3] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   if (tid == 0) s_leadb[NW] = 0u;
   __syncthreads();
@@ -472,7 +489,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
     __syncthreads();
     for (int a = 0; a < s_nl; ++a) {
       const int ls = s_pt[s_lk[a]], le = min((int)s_pt[s_lk[a] + 1], SPAN);
-      for (int pos = ls + tid; pos < le; pos += MODEL_THREADS) s_len[pos] = 0;
+      for (int pos = ls + tid; pos < le; pos += MODEL_THREADS) s_tok[pos] = 0u;
     }
     __syncthreads();
   }
@@ -499,7 +516,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
           if (len <= WC_MAX_BYTES) {
             WordKey key;
             wc_make_key(s_byte, s, len, key);
-            hit = wc_lookup(P.wcache, P.wcache_mask, key, s, s_id, s_len);
+            hit = wc_lookup(P.wcache, P.wcache_mask, key, s, s_tok);
           }
           kind = hit ? 0 : 1;
         }
@@ -537,18 +554,18 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
           bool active = active0;
           if (P.t.ignore_merges) {  // models/bpe/model.rs:558-567: the whole pre-token is a vocabulary entry -> one token
             int whole = 0;
-            if (active0 && gl == 0) { whole = vocab_whole_word(P.t, s_byte, s, e - s, s_id) ? 1 : 0; if (whole) s_len[s] = (uint16_t)(e - s); }
+            if (active0 && gl == 0) whole = vocab_whole_word(P.t, s_byte, s, e - s, s_tok) ? 1 : 0;
             whole = __shfl_sync(0xFFFFFFFFu, whole, lane & ~(G - 1));
             active = active0 && !whole;
           }
-          coop_bpe<G, J>(P.t, s_byte, s_id, s_len, s, e, active, gl);
+          coop_bpe<G, J>(P.t, s_byte, s_tok, s, e, active, gl);
           __syncwarp();
           // long numbers rarely repeat: publishing them only fills the table (measured: -5 % kernel time without them)
           const bool numeric = active0 && (e - s) >= 5 && (unsigned)(s_byte[s + 1] - '0') < 10u && (unsigned)(s_byte[e - 1] - '0') < 10u;
           if (active0 && gl == 0 && e - s <= WC_MAX_BYTES && !numeric) {
             WordKey key;
             wc_make_key(s_byte, s, e - s, key);
-            wc_publish(P.wcache, P.wcache_mask, key, s, e, s_id, s_len);
+            wc_publish(P.wcache, P.wcache_mask, key, s, e, s_tok);
           }
         }
       };
@@ -564,11 +581,11 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
         bool active = true;
         if (P.t.ignore_merges) {
           int whole = 0;
-          if (lane == 0) { whole = vocab_whole_word(P.t, s_byte, s, e - s, s_id) ? 1 : 0; if (whole) s_len[s] = (uint16_t)(e - s); }
+          if (lane == 0) whole = vocab_whole_word(P.t, s_byte, s, e - s, s_tok) ? 1 : 0;
           whole = __shfl_sync(0xFFFFFFFFu, whole, 0);
           active = !whole;
         }
-        coop_bpe<32, LONG_PRETOK_MIN / 32>(P.t, s_byte, s_id, s_len, s, e, active, lane);
+        coop_bpe<32, LONG_PRETOK_MIN / 32>(P.t, s_byte, s_tok, s, e, active, lane);
       }
     }
   } else {
@@ -583,7 +600,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
           if (len <= WC_MAX_BYTES) {
             WordKey key;
             wc_make_key(s_byte, s, len, key);
-            hit = wc_lookup(P.wcache, P.wcache_mask, key, s, s_id, s_len);
+            hit = wc_lookup(P.wcache, P.wcache_mask, key, s, s_tok);
           }
           miss = !hit;
         }
@@ -625,18 +642,18 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
             if (en.z != EMPTY_KEY) { best_id = en.z; best_end = p + 1; }
           }
           if (best_end < 0) { bad = true; break; }
-          s_id[start] = best_id; s_len[start] = (uint16_t)(best_end - start);
+          s_tok[start] = tok_pack(best_id, best_end - start);
           start = best_end;
         }
       }
       if (bad) {
-        for (int p = s; p < e; ++p) s_len[p] = 0;
-        s_id[s] = P.t.unk_id; s_len[s] = (uint16_t)len;
+        for (int p = s; p < e; ++p) s_tok[p] = 0u;
+        s_tok[s] = tok_pack(P.t.unk_id, len);
       }
       if (len <= WC_MAX_BYTES) {
         WordKey key;
         wc_make_key(s_byte, s, len, key);
-        wc_publish(P.wcache, P.wcache_mask, key, s, e, s_id, s_len);
+        wc_publish(P.wcache, P.wcache_mask, key, s, e, s_tok);
       }
     }
     // a LONG split (> 416 bytes) has more than max_input_chars_per_word (<= 100 * 4 bytes) characters: it is [UNK];
@@ -655,7 +672,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   // ---------------------------------------------------------------- P5: token bitmap and count
   for (int row = warp; row < NW; row += NWARPS) {
     int pos = row * 32 + lane;
-    bool tok = pos >= first && pos < Eproc && s_len[pos] != 0;
+    bool tok = pos >= first && pos < Eproc && tok_len(s_tok[pos]) != 0;
     uint32_t tb = __ballot_sync(0xFFFFFFFFu, tok);
     if (lane == 0) s_tokb[row] = tb;
   }
@@ -744,8 +761,9 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   for (int j = tid; j < n_normal; j += MODEL_THREADS) {
     const int pos = s_tokpos[j];
     const unsigned long long out = excl + (unsigned long long)(j + long_tokens_before(pos));
-    const int e = pos + s_len[pos];
-    emit(out, s_id[pos], pos, base + e, lc_incl(e - 1), true);
+    const uint32_t tk = s_tok[pos];
+    const int e = pos + tok_len(tk);
+    emit(out, tok_id(tk), pos, base + e, lc_incl(e - 1), true);
   }
   if (MODEL == MODEL_BPE) {
     // tokens of the long pre-tokens, produced by the pre-pass (relative to the pre-token start)
