@@ -53,6 +53,8 @@ struct DeviceTables {
   const uint8_t* word_pool;    // token strings as raw bytes (ByteLevel chars mapped back to bytes)
   int ignore_merges;
   int monotone;                // every merge ranks after all merges creating its parts (long_kernels.cuh)
+  const uint32_t* tok2_bits;   // bit (b0 | b1 << 8): the two bytes b0 b1 are a token
+  const uint32_t* tri_bits;    // bit (b0 | b1 << 8 | b2 << 16): the bytes b0 b1 b2 occur consecutively inside some token
   // WordPiece: byte trie, two roots (0 = word start, 1 = after the continuing-subword prefix)
   const uint4* edge_tbl;       // {node << 8 | byte, child node, token id of child or EMPTY_KEY, 0}; x == EMPTY_KEY free
   uint32_t edge_mask;

@@ -91,7 +91,7 @@ struct Workspace {
   DevBuf doc_bits, start_bits, drop_bits, page_sum, page_carry, block_sum, block_carry, page_first_doc, ctl;
   DevBuf ids, offsets, word_ids, row_ptr;
   DevBuf tmp_ids, tmp_offsets, tmp_word_ids, tile_count, tile_first, tile_lexcl, tile_bsum;  // pass-1 provisional slots + scan
-  DevBuf page_long, long_desc, lp_id, lp_val, lp_len, lp_plen, lp_aux, lp_out;  // long BPE pre-tokens (long_kernels.cuh)
+  DevBuf page_long, long_desc, long_desc1, soft_bits, page_soft, lp_id, lp_val, lp_len, lp_plen, lp_aux, lp_out;  // long BPE pre-tokens (long_kernels.cuh)
   unsigned long long pool_cap = 0;
   DevBuf wcache;                      // per-batch word cache (model_kernels.cuh)
   DevBuf pfx_bytes, pfx_doc_off, pfx_local, pfx_block, prefix_bits, pfx_total;  // add_prefix_space re-pack (prefix_kernels.cuh)
@@ -105,7 +105,7 @@ struct Workspace {
     word_ids.release(); row_ptr.release(); h_ctl.release();
     tmp_ids.release(); tmp_offsets.release(); tmp_word_ids.release(); tile_count.release(); tile_first.release(); tile_lexcl.release(); tile_bsum.release();
     pfx_bytes.release(); pfx_doc_off.release(); pfx_local.release(); pfx_block.release(); prefix_bits.release(); pfx_total.release();
-    wcache.release(); page_long.release(); long_desc.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
+    wcache.release(); page_long.release(); long_desc.release(); long_desc1.release(); soft_bits.release(); page_soft.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
     stream = nullptr; done = nullptr;
@@ -131,7 +131,7 @@ struct b2t_engine {
   int k1_tiled = 0;          // B2T_K1_TILED=1: the round-1 shared-memory-tiled scan (kept for A/B runs)
   DeviceTables dt;
   int monotone = 0;
-  DevBuf d_cls, d_byte_to_id, d_merge, d_word, d_pool, d_edge;
+  DevBuf d_cls, d_byte_to_id, d_merge, d_word, d_pool, d_edge, d_tok2, d_tri;
   std::mutex mu;
   Workspace dev_ws;          // b2t_encode_batch_device
   Workspace slot[NSLOT];     // b2t_encode_batch chunks
@@ -198,7 +198,8 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
   }
   int rc = B2T_OK;
   if ((rc = upload(e->d_cls, ht.cls_packed)) || (rc = upload(e->d_byte_to_id, ht.byte_to_id)) || (rc = upload(e->d_merge, ht.merge_tbl)) ||
-      (rc = upload(e->d_word, ht.word_tbl)) || (rc = upload(e->d_pool, ht.word_pool)) || (rc = upload(e->d_edge, ht.edge_tbl))) {
+      (rc = upload(e->d_word, ht.word_tbl)) || (rc = upload(e->d_pool, ht.word_pool)) || (rc = upload(e->d_edge, ht.edge_tbl)) ||
+      (rc = upload(e->d_tok2, ht.tok2_bits)) || (rc = upload(e->d_tri, ht.tri_bits))) {
     b2t_engine_destroy(e);
     return rc;
   }
@@ -211,6 +212,7 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
   e->dt.word_pool = e->d_pool.as<uint8_t>();
   e->dt.ignore_merges = cfg->ignore_merges ? 1 : 0;
   e->dt.monotone = ht.monotone ? 1 : 0;
+  e->dt.tok2_bits = e->d_tok2.as<uint32_t>(); e->dt.tri_bits = e->d_tri.as<uint32_t>();
   e->monotone = e->dt.monotone;
   e->dt.edge_tbl = e->d_edge.as<uint4>();
   e->dt.edge_mask = ht.edge_tbl.empty() ? 0 : (uint32_t)ht.edge_tbl.size() - 1;
@@ -232,7 +234,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
   cudaDeviceSynchronize();
   e->dev_ws.release();
   for (auto& s : e->slot) s.release();
-  e->d_cls.release(); e->d_byte_to_id.release(); e->d_merge.release(); e->d_word.release(); e->d_pool.release(); e->d_edge.release();
+  e->d_cls.release(); e->d_byte_to_id.release(); e->d_merge.release(); e->d_word.release(); e->d_pool.release(); e->d_edge.release(); e->d_tok2.release(); e->d_tri.release();
   for (b2t_result* r : e->pool) { r->h_ids.release(); r->h_offsets.release(); r->h_word_ids.release(); r->h_row_ptr.release(); delete r; }
   if (e->rec_ev_made) for (auto& ev : e->rec_ev) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -344,7 +346,8 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   if (model_pass && (rc = ws.wcache.ensure((size_t)WCACHE_SLOTS * 64))) return rc;
   if (model_pass && bpe) {
     if ((rc = ws.page_long.ensure(n_pages * 4)) || (rc = ws.long_desc.ensure((size_t)(n / (LONG_PRETOK_MIN + 1) + 2) * sizeof(LongDesc))) ||
-        (rc = ensure_long_pool(ws, 1u << 20)))
+        (rc = ws.long_desc1.ensure((size_t)(n / (LONG_PRETOK_MIN + 1) + 2) * sizeof(LongDesc))) || (rc = ws.soft_bits.ensure(n_words * 4)) ||
+        (rc = ws.page_soft.ensure(n_pages)) || (rc = ensure_long_pool(ws, 1u << 20)))
       return rc;
   }
   if (model_pass) {
@@ -358,6 +361,10 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   CU(cudaMemsetAsync(ws.doc_bits.p, 0, n_words * 4, st));
   CU(cudaMemsetAsync(ws.ctl.p, 0, sizeof(ctl_block), st));
   if (model_pass) CU(cudaMemsetAsync(ws.wcache.p, 0, (size_t)WCACHE_SLOTS * 64, st));
+  if (model_pass && bpe) {
+    CU(cudaMemsetAsync(ws.soft_bits.p, 0, n_words * 4, st));
+    CU(cudaMemsetAsync(ws.page_soft.p, 0, n_pages, st));
+  }
   e->last_launches = 0;
   rec(e, st, nullptr);
   doc_mark_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.doc_bits.as<uint32_t>(), ws.page_first_doc.as<uint32_t>());
@@ -379,9 +386,14 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     LongPool pool;
     pool.id = ws.lp_id.as<uint32_t>(); pool.val = ws.lp_val.as<uint64_t>(); pool.len = ws.lp_len.as<uint32_t>(); pool.plen = ws.lp_plen.as<uint32_t>();
     pool.aux = ws.lp_aux.as<uint32_t>(); pool.out = ws.lp_out.as<uint4>(); pool.cap = ws.pool_cap;
-    long_find_kernel<<<(unsigned)((n_pages + 7) / 8), 256, 0, st>>>(ws.start_bits.as<uint32_t>(), n, n_pages, &ctl->lc, ws.long_desc.as<LongDesc>(),
-                                                                   ws.page_long.as<int32_t>(), ws.pool_cap);
-    rec(e, st, "long_find"); e->last_launches++;
+    // long pre-tokens: find them, cut them where no token can span, find the pieces that are still long
+    long_find_kernel<0><<<(unsigned)((n_pages + 7) / 8), 256, 0, st>>>(ws.start_bits.as<uint32_t>(), nullptr, nullptr, n, n_pages, &ctl->lc,
+                                                                      ws.long_desc1.as<LongDesc>(), nullptr, 0ull);
+    soft_cut_kernel<<<(unsigned)(e->sm_count * 4), 256, 0, st>>>(d_bytes, &ctl->lc, ws.long_desc1.as<LongDesc>(), ws.soft_bits.as<uint32_t>(),
+                                                               ws.page_soft.as<uint8_t>(), e->dt);
+    long_find_kernel<1><<<(unsigned)((n_pages + 7) / 8), 256, 0, st>>>(ws.start_bits.as<uint32_t>(), ws.soft_bits.as<uint32_t>(), ws.page_soft.as<uint8_t>(),
+                                                                      n, n_pages, &ctl->lc, ws.long_desc.as<LongDesc>(), ws.page_long.as<int32_t>(), ws.pool_cap);
+    rec(e, st, "long_find"); e->last_launches += 3;
     bpe_long_kernel<<<(unsigned)(e->sm_count * 2), LONG_THREADS, 0, st>>>(d_bytes, &ctl->lc, ws.long_desc.as<LongDesc>(), pool, e->dt, e->monotone);
     rec(e, st, "bpe_long"); e->last_launches++;
   }
@@ -389,6 +401,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     ModelParams P;
     P.bytes = d_bytes; P.n = n;
     P.start_bits = ws.start_bits.as<uint32_t>(); P.drop_bits = ws.drop_bits.as<uint32_t>(); P.doc_bits = ws.doc_bits.as<uint32_t>();
+    P.soft_bits = ws.soft_bits.as<uint32_t>(); P.page_soft = ws.page_soft.as<uint8_t>();
     P.page_carry = ws.page_carry.as<uint64_t>(); P.block_carry = ws.block_carry.as<uint64_t>(); P.page_first_doc = ws.page_first_doc.as<uint32_t>();
     P.doc_off = d_doc_off; P.n_docs = n_docs;
     P.flags = ((flags & B2T_WANT_OFFSETS) ? F_OFFSETS : 0u) | ((flags & B2T_WANT_WORD_IDS) ? F_WORD_IDS : 0u) |

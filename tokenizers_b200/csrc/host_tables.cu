@@ -124,6 +124,33 @@ std::string build_host_tables(int model, int pretok, int ignore_merges, uint32_t
       }
       out->monotone = mono;
     }
+    // ---- byte pairs that are tokens, byte triples inside tokens (soft cuts of long pre-tokens, long_kernels.cuh)
+    {
+      out->tok2_bits.assign((1u << 16) / 32, 0u);
+      out->tri_bits.assign((1u << 24) / 32, 0u);
+      for (uint32_t i = 0; i < n_vocab; ++i) {
+        const uint8_t* s = vocab_bytes + vocab_off[i];
+        const uint32_t len = vocab_off[i + 1] - vocab_off[i];
+        std::vector<uint8_t> raw;
+        bool ok = len > 0;
+        for (uint32_t p = 0; p < len && ok;) {  // byte-level chars back to bytes
+          uint32_t b0 = s[p], cp, l;
+          if (b0 < 0x80) { cp = b0; l = 1; }
+          else if (b0 < 0xE0 && p + 1 < len) { cp = ((b0 & 31u) << 6) | (s[p + 1] & 63u); l = 2; }
+          else { ok = false; break; }
+          auto it = byte_of_cp.find(cp);
+          if (it == byte_of_cp.end()) { ok = false; break; }
+          raw.push_back((uint8_t)it->second);
+          p += l;
+        }
+        if (!ok) continue;  // not a string of ByteLevel characters: no merge can produce it from text
+        if (raw.size() == 2) { const uint32_t k = raw[0] | ((uint32_t)raw[1] << 8); out->tok2_bits[k >> 5] |= 1u << (k & 31); }
+        for (size_t p = 0; p + 2 < raw.size(); ++p) {
+          const uint32_t k = raw[p] | ((uint32_t)raw[p + 1] << 8) | ((uint32_t)raw[p + 2] << 16);
+          out->tri_bits[k >> 5] |= 1u << (k & 31);
+        }
+      }
+    }
     // ---- whole-word table for ignore_merges (models/bpe/model.rs:558-567)
     if (ignore_merges) {
       uint32_t wcap = pow2_at_least((uint64_t)n_vocab * 5 / 2 + 16);

@@ -20,6 +20,10 @@ struct HostTables {
   std::vector<uint4> word_tbl;
   std::vector<uint8_t> word_pool;
   std::vector<uint4> edge_tbl;
+  // BPE: which byte pairs are 2-byte tokens / which byte triples occur inside some token (raw bytes): a token can only
+  // span a byte boundary whose pair / triples pass these tests, everywhere else a long pre-token can be cut exactly
+  std::vector<uint32_t> tok2_bits;    // 2^16 bits
+  std::vector<uint32_t> tri_bits;     // 2^24 bits
   uint32_t unk_id = EMPTY_KEY;
   uint32_t max_chars = 100;
   bool monotone = false;

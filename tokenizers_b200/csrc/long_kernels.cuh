@@ -1,8 +1,14 @@
 // long_kernels.cuh -- the path for BPE pre-tokens longer than LONG_PRETOK_MIN bytes (URLs, base64 blobs, 64 KB letter / space
 // runs of the length-skew stress config).  They do not fit the per-page shared-memory scheme of model_kernels.cuh and
 // would stall their page for milliseconds, so they are resolved by a pre-pass:
-//   K1c long_find : one warp per page finds the pre-tokens that start in the page and are longer than LONG_PRETOK_MIN, gives
-//                   them consecutive slots (page_long[page] = first slot) and a region of the long pool;
+//   K1c long_find : one warp per page finds the pre-tokens that start in the page and are longer than LONG_PRETOK_MIN;
+//       soft_cut  : cuts them wherever no token of the vocabulary can span the byte boundary (the two bytes are not a
+//                   token and neither byte triple around the boundary occurs inside any token): merges never cross such a
+//                   boundary, so the pieces are merged independently -- by the page kernel like ordinary pre-tokens when
+//                   they are short (almost always), else by K2L.  The cuts live in a second bitmap (soft_bits): word ids and
+//                   the split list of the reference are untouched;
+//       long_find : (second pass, on start_bits | soft_bits) the pieces that are still longer than LONG_PRETOK_MIN get
+//                   consecutive slots (page_long[page] = first slot) and a region of the long pool;
 //   K2L bpe_long  : one block per long pre-token runs the merge loop of models/bpe/word.rs:162-250 on arrays in global
 //                   memory and leaves the token list (id, end byte, char offsets relative to the pre-token) in the pool;
 //   K2            : copies those tokens into the CSR at the right place (model_kernels.cuh).
@@ -24,9 +30,11 @@ constexpr int LONG_THREADS = 1024;  // one block per long pre-token; 256 -> 1024
 enum { ERR_POOL_OVERFLOW = 2u, ERR_INTERNAL = 4u };
 
 struct LongCtl {        // device-side counters, zeroed per batch
-  uint32_t n_long;      // number of long pre-tokens
+  uint32_t n_long;      // number of long pieces after the soft cuts (second pass)
   uint32_t err;
-  unsigned long long pool_used;  // bytes of long pre-tokens placed (or wanted, on overflow) in the pool
+  unsigned long long pool_used;  // bytes of long pieces placed (or wanted, on overflow) in the pool
+  uint32_t n_long1;     // number of long pre-tokens before the cuts (first pass)
+  uint32_t pad;
 };
 
 struct LongPool {
@@ -43,56 +51,58 @@ struct LongDesc {
   long long start, end;          // absolute byte range of the pre-token
   unsigned long long pool_off;   // its region of the pool
   uint32_t ntok;                 // filled by K2L
-  uint32_t pad;
+  uint32_t soft;                 // 1: a piece of a cut pre-token (the ignore_merges whole-word rule does not apply to it)
 };
 
 // ------------------------------------------------------------------------------------------------ K1c
 // One warp per page.  A start bit at p begins a long pre-token iff no start bit lies in (p, p + LONG_PRETOK_MIN].
-__global__ void long_find_kernel(const uint32_t* __restrict__ start_bits, int64_t n, int64_t n_pages, LongCtl* ctl,
+// PASS 0: on start_bits, fills desc (start, end) and ctl->n_long1.  PASS 1: on start_bits | soft_bits for the pages flagged
+// in page_soft (all others get page_long = -1), fills desc with pool regions, ctl->n_long and page_long.
+template <int PASS>
+__global__ void long_find_kernel(const uint32_t* __restrict__ start_bits, const uint32_t* __restrict__ soft_bits,
+                                 const uint8_t* __restrict__ page_soft, int64_t n, int64_t n_pages, LongCtl* ctl,
                                  LongDesc* desc, int32_t* __restrict__ page_long, unsigned long long pool_cap) {
   const int lane = threadIdx.x & 31;
   const int64_t page = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (page >= n_pages) return;
+  if (PASS == 1 && !__ldg(page_soft + page)) { if (lane == 0) page_long[page] = -1; return; }
   const int64_t n_words = n / 32 + 1;
   const int64_t w0 = page * (PAGE / 32);
   static_assert(PAGE / 32 == 64, "a lane handles words lane and lane + 32 of the page");
   constexpr int LW = LONG_PRETOK_MIN / 32;      // 8
+  auto bits_at = [&](int64_t w) -> uint32_t {
+    if (w >= n_words) return 0u;
+    uint32_t b = __ldg(start_bits + w);
+    if (PASS == 1) b |= __ldg(soft_bits + w);
+    return b;
+  };
   // lane handles words lane and lane + 32 of the page
-  int nlong_lane = 0;
   long long ps[2], qs[2];
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int64_t w = w0 + lane + half * 32;
-    uint32_t bits = w < n_words ? __ldg(start_bits + w) : 0u;
+    const uint32_t bits = bits_at(w);
     ps[half] = -1; qs[half] = -1;
     if (bits) {
       const int h = 31 - __clz((int)bits);
       bool is_long = true;
-      for (int k = 1; k < LW && is_long; ++k) {
-        const int64_t ww = w + k;
-        if (ww < n_words && __ldg(start_bits + ww)) is_long = false;
-      }
-      if (is_long) {
-        const int64_t ww = w + LW;
-        uint32_t b = ww < n_words ? __ldg(start_bits + ww) : 0u;
-        if (b & (h >= 31 ? 0xFFFFFFFFu : ((2u << h) - 1u))) is_long = false;
-      }
+      for (int k = 1; k < LW && is_long; ++k)
+        if (bits_at(w + k)) is_long = false;
+      if (is_long && (bits_at(w + LW) & (h >= 31 ? 0xFFFFFFFFu : ((2u << h) - 1u)))) is_long = false;
       const long long p = w * 32 + h;
       if (is_long && p + LONG_PRETOK_MIN < n) {
         // find the end: first start bit after p + LONG_PRETOK_MIN, or n
         long long q = -1;
         int64_t ww = w + LW;
-        uint32_t b = ww < n_words ? __ldg(start_bits + ww) : 0u;
-        b &= ~(h >= 31 ? 0xFFFFFFFFu : ((2u << h) - 1u));
+        uint32_t b = bits_at(ww) & ~(h >= 31 ? 0xFFFFFFFFu : ((2u << h) - 1u));
         while (true) {
           if (b) { q = ww * 32 + (__ffs((int)b) - 1); break; }
           ++ww;
           if (ww >= n_words) { q = n; break; }
-          b = __ldg(start_bits + ww);
+          b = bits_at(ww);
         }
         if (q > n) q = n;
         ps[half] = p; qs[half] = q;
-        ++nlong_lane;
       }
     }
   }
@@ -101,8 +111,11 @@ __global__ void long_find_kernel(const uint32_t* __restrict__ start_bits, int64_
   const int total = __popc(m0) + __popc(m1);
   int base = 0;
   if (lane == 0) {
-    page_long[page] = -1;
-    if (total) { base = (int)atomicAdd(&ctl->n_long, (uint32_t)total); page_long[page] = base; }
+    if (PASS == 1) page_long[page] = -1;
+    if (total) {
+      base = (int)atomicAdd(PASS == 0 ? &ctl->n_long1 : &ctl->n_long, (uint32_t)total);
+      if (PASS == 1) page_long[page] = base;
+    }
   }
   base = __shfl_sync(0xFFFFFFFFu, base, 0);
   if (!total) return;
@@ -110,12 +123,55 @@ __global__ void long_find_kernel(const uint32_t* __restrict__ start_bits, int64_
   for (int half = 0; half < 2; ++half) {
     if (ps[half] < 0) continue;
     const int slot = base + (half ? __popc(m0) + __popc(m1 & ((1u << lane) - 1u)) : __popc(m0 & ((1u << lane) - 1u)));
-    const unsigned long long L = (unsigned long long)(qs[half] - ps[half]);
-    const unsigned long long off = atomicAdd(&ctl->pool_used, L);
     LongDesc d;
-    d.start = ps[half]; d.end = qs[half]; d.pool_off = off; d.ntok = 0; d.pad = 0;
-    if (off + L > pool_cap) { atomicOr(&ctl->err, ERR_POOL_OVERFLOW); d.pool_off = ~0ull; }
+    d.start = ps[half]; d.end = qs[half]; d.pool_off = 0; d.ntok = 0; d.soft = 0;
+    if (PASS == 1) {
+      const unsigned long long L = (unsigned long long)(qs[half] - ps[half]);
+      const unsigned long long off = atomicAdd(&ctl->pool_used, L);
+      d.pool_off = off;
+      if (off + L > pool_cap) { atomicOr(&ctl->err, ERR_POOL_OVERFLOW); d.pool_off = ~0ull; }
+      // a piece of a cut pre-token starts or ends at a soft bit
+      const bool real_s = (__ldg(start_bits + (d.start >> 5)) >> (d.start & 31)) & 1u;
+      const bool real_e = d.end >= n || ((__ldg(start_bits + (d.end >> 5)) >> (d.end & 31)) & 1u);
+      d.soft = (real_s && real_e) ? 0u : 1u;
+    }
     desc[slot] = d;
+  }
+}
+
+// One block per long pre-token of the first pass: bit i of soft_bits is set iff a cut before byte i is exact, i.e. no
+// vocabulary token can contain bytes i-1 and i of this text next to each other:
+//   the two bytes are not a token, the triple (i-2, i-1, i) occurs in no token, the triple (i-1, i, i+1) occurs in no token
+// (a token of 2 bytes spanning the boundary IS that pair; a longer one contains one of the two triples; triples that
+// would reach outside the pre-token cannot occur).  Every page the pre-token touches is flagged in page_soft.
+__global__ void __launch_bounds__(256) soft_cut_kernel(const uint8_t* __restrict__ bytes, const LongCtl* __restrict__ ctl,
+                                                       const LongDesc* __restrict__ desc, uint32_t* __restrict__ soft_bits,
+                                                       uint8_t* __restrict__ page_soft, DeviceTables t) {
+  const uint32_t n_long = ctl->n_long1;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t j = blockIdx.x; j < n_long; j += gridDim.x) {
+    const long long s = desc[j].start, e = desc[j].end;
+    for (long long pg = s / PAGE + threadIdx.x; pg <= (e - 1) / PAGE; pg += blockDim.x) page_soft[pg] = 1;
+    // a warp takes 32 consecutive positions (aligned to the bitmap words)
+    for (long long w = (s >> 5) + (threadIdx.x >> 5); w * 32 < e; w += blockDim.x >> 5) {
+      const long long i = w * 32 + lane;
+      bool cut = false;
+      if (i > s && i < e) {
+        const uint32_t b1 = __ldg(bytes + i - 1), b2 = __ldg(bytes + i);
+        const uint32_t k2 = b1 | (b2 << 8);
+        cut = !((__ldg(t.tok2_bits + (k2 >> 5)) >> (k2 & 31)) & 1u);
+        if (cut && i - 2 >= s) {
+          const uint32_t k3 = __ldg(bytes + i - 2) | (b1 << 8) | (b2 << 16);
+          cut = !((__ldg(t.tri_bits + (k3 >> 5)) >> (k3 & 31)) & 1u);
+        }
+        if (cut && i + 1 < e) {
+          const uint32_t k3 = b1 | (b2 << 8) | (__ldg(bytes + i + 1) << 16);
+          cut = !((__ldg(t.tri_bits + (k3 >> 5)) >> (k3 & 31)) & 1u);
+        }
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, cut);
+      if (lane == 0 && m) atomicOr(soft_bits + w, m);
+    }
   }
 }
 
@@ -180,7 +236,7 @@ __global__ void __launch_bounds__(LONG_THREADS) bpe_long_kernel(const uint8_t* _
     // whole pre-token in the vocabulary (ignore_merges)?  Only tokens up to 255 bytes are in the table.
     if (tid == 0) s_hit = 0;
     __syncthreads();
-    if (t.ignore_merges && L < 65536 && tid == 0) {
+    if (t.ignore_merges && !d.soft && L < 65536 && tid == 0) {
       StrHash h; strhash_init(h);
       for (long long i = 0; i < L; ++i) strhash_byte(h, __ldg(src + i));
       strhash_fin(h);

@@ -36,6 +36,9 @@ constexpr int MAX_LONG_PER_PAGE = TILE / (LONG_PRETOK_MIN + 1) + 1;  // 8
 struct ModelParams {
   const uint8_t* bytes; int64_t n;
   const uint32_t* start_bits; const uint32_t* drop_bits; const uint32_t* doc_bits;
+  // BPE: exact cuts inside long pre-tokens (long_kernels.cuh soft_cut) and the pages that hold any; the page kernel merges
+  // the pieces like pre-tokens of their own, word ids and offsets keep following start_bits
+  const uint32_t* soft_bits; const uint8_t* page_soft;
   const uint64_t* page_carry; const uint64_t* block_carry; const uint32_t* page_first_doc;
   const uint64_t* doc_off; uint32_t n_docs;
   uint32_t flags;
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   uint16_t* const s_miss = s_list;
   uint16_t* const s_tokpos = s_list;
   __shared__ int s_nmiss, s_nmiss_hi;  // misses queued from the front (short) and from the back (longer) of s_miss
-  __shared__ int s_tile, s_next, s_nmq, s_P, s_Elast, s_long, s_ntok, s_ntot;
+  __shared__ int s_tile, s_next, s_nmq, s_P, s_Elast, s_long, s_ntok, s_ntot, s_anysoft;
   __shared__ unsigned long long s_excl;
   __shared__ long long s_long_end, s_span_doc_start;
   __shared__ int s_long_chars;
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   constexpr int NWARPS = MODEL_THREADS / 32;
   if (tid == 0) {
     s_tile = (int)blockIdx.x;
-    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0; s_nmiss_hi = 0;
+    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0; s_nmiss_hi = 0; s_anysoft = 0;
   }
   __syncthreads();
   const int64_t t = s_tile;
@@ -358,8 +361,10 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
     int64_t gw = base / 32 + w;
     uint32_t sb = (w < NW && gw < n_chunks) ? __ldg(P.start_bits + gw) : 0u;
     uint32_t db = (MODEL == MODEL_WORDPIECE && w < NW && gw < n_chunks) ? __ldg(P.drop_bits + gw) : 0u;
-    s_startb[w] = sb;
-    s_keptb[w] = sb & ~db;
+    uint32_t sf = 0u;
+    if (MODEL == MODEL_BPE && w < NW && gw < n_chunks && __ldg(P.page_soft + (gw >> 6))) { sf = __ldg(P.soft_bits + gw); if (sf) s_anysoft = 1; }
+    s_startb[w] = sb | sf;   // where a unit of merging starts: splits of the pre-tokenizer + exact cuts of long ones
+    s_keptb[w] = sb & ~db;   // splits of the pre-tokenizer that the reference keeps (word ids)
     if (w <= TW) s_dsb[w] = (w < TW && gw < n_chunks) ? __ldg(P.doc_bits + gw) : 0u;
   }
   __syncthreads();
@@ -494,6 +499,15 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
     __syncthreads();
   }
   const int n_longs = MODEL == MODEL_BPE ? s_nl : 0;
+  // [s, e) is a piece of a cut pre-token (not a whole split of the pre-tokenizer): with ignore_merges the whole-word rule
+  // and the word cache (whose entries follow that rule) do not apply to it
+  const bool any_soft = MODEL == MODEL_BPE && s_anysoft != 0;
+  auto is_piece = [&](int s, int e) -> bool {
+    if (!any_soft) return false;
+    const bool real_s = (s_keptb[s >> 5] >> (s & 31)) & 1u;
+    const bool real_e = base + e >= n || (e < SPAN && ((s_keptb[e >> 5] >> (e & 31)) & 1u));
+    return !(real_s && real_e);
+  };
   // number of long-path tokens that precede page position x
   auto long_tokens_before = [&](int x) -> int {
     int c = 0;
@@ -513,7 +527,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
         else if (len > THREAD_PATH_MAX) kind = 2;
         else {
           bool hit = false;
-          if (len <= WC_MAX_BYTES) {
+          if (len <= WC_MAX_BYTES && !(P.t.ignore_merges && is_piece(s, e))) {
             WordKey key;
             wc_make_key(s_byte, s, len, key);
             hit = wc_lookup(P.wcache, P.wcache_mask, key, s, s_tok);
@@ -554,7 +568,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
           bool active = active0;
           if (P.t.ignore_merges) {  // models/bpe/model.rs:558-567: the whole pre-token is a vocabulary entry -> one token
             int whole = 0;
-            if (active0 && gl == 0) whole = vocab_whole_word(P.t, s_byte, s, e - s, s_tok) ? 1 : 0;
+            if (active0 && gl == 0 && !is_piece(s, e)) whole = vocab_whole_word(P.t, s_byte, s, e - s, s_tok) ? 1 : 0;
             whole = __shfl_sync(0xFFFFFFFFu, whole, lane & ~(G - 1));
             active = active0 && !whole;
           }
@@ -562,7 +576,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
           __syncwarp();
           // long numbers rarely repeat: publishing them only fills the table (measured: -5 % kernel time without them)
           const bool numeric = active0 && (e - s) >= 5 && (unsigned)(s_byte[s + 1] - '0') < 10u && (unsigned)(s_byte[e - 1] - '0') < 10u;
-          if (active0 && gl == 0 && e - s <= WC_MAX_BYTES && !numeric) {
+          if (active0 && gl == 0 && e - s <= WC_MAX_BYTES && !numeric && !(P.t.ignore_merges && is_piece(s, e))) {
             WordKey key;
             wc_make_key(s_byte, s, e - s, key);
             wc_publish(P.wcache, P.wcache_mask, key, s, e, s_tok);
@@ -581,7 +595,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
         bool active = true;
         if (P.t.ignore_merges) {
           int whole = 0;
-          if (lane == 0) whole = vocab_whole_word(P.t, s_byte, s, e - s, s_tok) ? 1 : 0;
+          if (lane == 0 && !is_piece(s, e)) whole = vocab_whole_word(P.t, s_byte, s, e - s, s_tok) ? 1 : 0;
           whole = __shfl_sync(0xFFFFFFFFu, whole, 0);
           active = !whole;
         }
