@@ -3,17 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mb 1024] [--config gpt2|llama3|wordpiece]
 
-One step = one pass of the whole hot path (doc_mark -> pretok_scan -> page_scan -> bpe_tile) over one batch of the
-synthetic corpus of SURVEY.md §8(d) config 2 ("GPT-2 ByteLevel BPE, 1 GB synthetic UTF-8 docs avg 512 B").  Prints ONE
-JSON line (rank 0).  `value` is device-resident (input already in HBM, CUDA events); `e2e` goes through the C-ABI call
-b2t_encode_batch with pinned HOST buffers, copies inside the timed region; `roofline` is the pre-tokenization scan
-kernel (the HBM-bound one) from CUDA events recorded on its launch stream; `cpu_baseline` is the reference's own Rust
-implementation (the `tokenizers` wheel) on this box's host cores over a bounded sample.
+One step = one pass of the whole hot path (doc_mark -> pretok_scan -> page_scan -> long_find -> bpe_tile -> compaction)
+over one batch of the synthetic corpus of SURVEY.md 8(d) config 2 ("GPT-2 ByteLevel BPE, 1 GB synthetic UTF-8 docs avg
+512 B").  Prints ONE JSON line (rank 0):
+  value         device-resident: input already in HBM, CUDA events (N > 1: see below)
+  e2e           the C-ABI call b2t_encode_batch with pinned HOST buffers, H2D + kernels + D2H inside the timed region
+                (ids + char offsets); e2e_ids_only = the encode_batch_fast analogue (4 B per token back instead of 12)
+  roofline      the pre-tokenization scan kernel, CUDA events on its launch stream, against MEASURED_PEAKS.json
+  configs       the other BASELINE configs (Llama-3 style, Whitespace + WordPiece, length-skew corpus) at 512 MB, fewer steps
+  cpu_baseline  the reference's own Rust encode_batch (the `tokenizers` wheel) on this box's host cores, >= 256 MB sample
 
-With N > 1 (torchrun) every rank encodes its own shard of N x the corpus (weak scaling, no data-path collective: the
-path shards by documents); `value` = all ranks' bytes / max-over-ranks device time.  The NCCL all-gather-v of the token
-CSR that BASELINE.json's north_star mentions is timed in a second loop and reported under `allgather`;
-`per_rank_ms_per_step`, `per_rank_kernel_ms_per_step` and the per-GPU clocks show where a straggler comes from.
+N > 1 (torchrun, one rank per GPU): every rank encodes its own byte-balanced shard of an N x 1 GB batch (weak scaling)
+through tokenizers_b200.parallel.encode_batch_sharded -- counts exchanged, every rank's compaction kernel writes at its
+displacement of the gathered CSR, one NCCL send / recv group completes it on every rank.  The exchange of step i overlaps
+the kernels of step i + 1 (it runs on its own stream), all exchanges complete inside the timed region; `value` = all
+ranks' bytes / max-over-ranks time of that loop.  `sharded_no_collective` is the same loop without the exchange.
 """
 import argparse, ctypes, gzip, json, os, subprocess, sys, threading, time
 
@@ -103,14 +107,14 @@ class ClockSampler:
                 "samples": min((len(v) for v in sm.values()), default=0), "per_gpu_sm_mhz": list(med.values())}
 
 
-def cpu_reference_worker(cfg, threads, budget_s):
+def cpu_reference_worker(cfg, threads, budget_s, min_mb):
     """Runs in a fresh process (rayon's pool size is fixed at first use): the reference's own Rust encode_batch
     (tokenizers wheel, bindings/python/src/tokenizer.rs:1312-1340) over a bounded sample of the bench corpus."""
     os.environ["TOKENIZERS_PARALLELISM"] = "true"
     os.environ["RAYON_NUM_THREADS"] = str(threads)
     import tokenizers
     tok = tokenizers.Tokenizer.from_str(tokenizer_json(cfg))
-    cap = 96 << 20
+    cap = max(int(min_mb) + 8, 40) << 20
     buf = np.empty(cap + (1 << 20), dtype=np.uint8)
     n, off = gen_corpus(KIND[cfg], SEED[cfg], 0, cap // 300, cap, buf)
     raw = buf[:n].tobytes()
@@ -123,99 +127,82 @@ def cpu_reference_worker(cfg, threads, budget_s):
     tok.encode_batch(d[:2048], add_special_tokens=False)  # warm-up (rayon pool)
     t0 = time.perf_counter(); tok.encode_batch(d, add_special_tokens=False); t1 = time.perf_counter()
     rate = int(off[probe_n]) / (t1 - t0)
-    k = int(min(n_avail, max(probe_n, np.searchsorted(off, rate * budget_s))))
+    want = max(rate * budget_s, float(min_mb) * (1 << 20))
+    k = int(min(n_avail, max(probe_n, np.searchsorted(off, want))))
     d = docs(k)
     best = None
-    for _ in range(2):
+    for _ in range(2 if min_mb <= 0 else 1):
         t0 = time.perf_counter(); enc = tok.encode_batch(d, add_special_tokens=False); dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     nbytes = int(off[k]); ntok = sum(len(e.ids) for e in enc)
     return {"value": nbytes / best / 1e9, "unit": "GB/s", "tokens_per_s": ntok / best, "cores": threads, "kind": "reference",
             "sample": f"tokenizers wheel {tokenizers.__version__} Tokenizer.encode_batch (char offsets), RAYON_NUM_THREADS={threads}, "
-                      f"first {k} docs / {nbytes / 1e6:.1f} MB of the bench corpus, best of 2",
-            "seconds": best}
+                      f"first {k} docs / {nbytes / 1e6:.1f} MB of the bench corpus",
+            "seconds": best, "sample_bytes": nbytes}
 
 
-def cpu_reference(cfg, budget_s=12.0):
-    """Best of a small thread sweep (all visible cores, 32, 16, 8, 4), each in its own process."""
+def host_facts():
+    """What explains the reference's thread scaling on this box: cgroup CPU quota, affinity, NUMA layout."""
+    f = {"affinity_cpus": len(os.sched_getaffinity(0))}
+    for path, key in (("/sys/fs/cgroup/cpu.max", "cgroup_cpu_max"), ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "cgroup_cfs_quota_us")):
+        try:
+            f[key] = open(path).read().strip()
+        except Exception:
+            pass
+    try:
+        nodes = sorted(d for d in os.listdir("/sys/devices/system/node") if d.startswith("node"))
+        f["numa_nodes"] = {d: open(f"/sys/devices/system/node/{d}/cpulist").read().strip() for d in nodes}
+    except Exception:
+        pass
+    return f
+
+
+def cpu_reference(cfg, budget_s=4.0, min_mb=256):
+    """Thread sweep (all visible cores, 32, 16, 8, 4) on a few-second sample, each in its own process; then the best
+    thread count once more on >= min_mb MB of the corpus."""
     cores = len(os.sched_getaffinity(0))
     tried = []
+
+    def run(th, bud, mb):
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-worker", cfg, str(th), str(bud), str(mb)],
+                             capture_output=True, text=True, timeout=900)
+        return json.loads(out.stdout.strip().splitlines()[-1])
     for th in sorted({cores, min(cores, 32), min(cores, 16), min(cores, 8), min(cores, 4)}, reverse=True):
         try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-worker", cfg, str(th), str(budget_s)],
-                                 capture_output=True, text=True, timeout=600)
-            r = json.loads(out.stdout.strip().splitlines()[-1])
-            tried.append(r)
+            tried.append(run(th, budget_s, 0))
         except Exception as ex:
             tried.append({"value": 0.0, "cores": th, "error": str(ex)[:200]})
-    best = max(tried, key=lambda r: r.get("value") or 0.0)
-    best = dict(best)
+    best = dict(max(tried, key=lambda r: r.get("value") or 0.0))
+    if min_mb > 0 and best.get("value"):
+        try:
+            big = run(best["cores"], 1.0, min_mb)
+            big["sweep_value"] = best["value"]
+            best = big
+        except Exception as ex:
+            best["big_sample_error"] = str(ex)[:200]
     best["host_cores"] = cores
     best["sweep"] = {str(r["cores"]): round(r.get("value") or 0.0, 5) for r in tried}
+    best["host"] = host_facts()
     return best
 
 
-def main():
-    if len(sys.argv) >= 5 and sys.argv[1] == "--cpu-worker":
-        print(json.dumps(cpu_reference_worker(sys.argv[2], int(sys.argv[3]), float(sys.argv[4]))))
-        return
-    # Only the JSON line may reach stdout (NCCL and others print there): park the real stdout, send fd 1 to stderr.
-    real_stdout = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--mb", type=int, default=1024, help="corpus size per GPU in MiB")
-    ap.add_argument("--config", default="gpt2", choices=list(ASSET))
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--kind", type=int, default=0, help="corpus kind override (5 = length-skew stress of BASELINE configs[4])")
-    a = ap.parse_args()
-    a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = a.config
-    workload_kind = {5: " [length-skew corpus: Zipf doc lengths 8 B-64 KB, 0.1 % docs hold a 4-64 KB letter/space run]"}.get(a.kind, "")
-    workload = {"gpt2": "GPT-2 ByteLevel BPE (50257 vocab trained offline by the reference trainer), synthetic UTF-8 docs avg ~480 B",
-                "llama3": "Llama-3-style BPE (tiktoken regex, 128k vocab, ignore_merges)", "wordpiece": "Whitespace + WordPiece 30522"}[cfg]
-    max_bytes = a.mb << 20
-    n_docs_target = max_bytes // 300
+class DevArr:  # zero-copy torch view of an engine-owned device buffer
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
 
-    if a.impl == "reference":
-        # the reference's CPU implementation, all host threads, bounded sample per step; rank 0 only
-        if rank != 0:
-            return
-        per_step = []
-        for s_i in range(a.warmup + a.steps):
-            r = cpu_reference(cfg, budget_s=max(2.0, 45.0 / (3 * (a.warmup + a.steps))))
-            if s_i >= a.warmup:
-                per_step.append(r)
-        r = max(per_step, key=lambda x: x["value"])
-        out = {"impl": "reference", "metric": "encode_batch input throughput", "value": r["value"], "unit": "GB/s", "tokens_per_s": r["tokens_per_s"],
-               "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": workload, "bytes_per_step": None, "sample": r["sample"]},
-               "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores", "sweep")},
-               "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        real_stdout.write(json.dumps(out) + "\n"); real_stdout.flush()
-        return
 
+def measure(ctx, cfg, kind, mb, steps, warmup, sharded=False):
+    """Device-resident and end-to-end numbers of one configuration on this rank.  Returns a dict of raw measurements."""
     import torch
     from tokenizers_b200 import Tokenizer, _lib
-    from tokenizers_b200.parallel import all_gather_csr
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    L = _lib.lib()
+    L, rank, world, local = ctx["L"], ctx["rank"], ctx["world"], ctx["local"]
+    dist = ctx.get("dist")
     tok = Tokenizer.from_str(tokenizer_json(cfg), device=local)
-
-    # ---- corpus: this rank's shard, generated straight into pinned host memory
+    max_bytes = mb << 20
+    n_docs_target = max_bytes // (200 if kind == 5 else 300)
     hptr = ctypes.c_void_p()
     _lib.check(L.b2t_host_alloc(max_bytes + (1 << 20), ctypes.byref(hptr)))
     hbuf = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint8)), shape=(max_bytes + (1 << 20),))
-    kind = a.kind or KIND[cfg]
-    if kind == 5:
-        n_docs_target = max_bytes // 200
     n, off = gen_corpus(kind, 5 if kind == 5 else SEED[cfg], rank * n_docs_target, n_docs_target, max_bytes, hbuf)
     n_docs = len(off) - 1
     hoff_ptr = ctypes.c_void_p()
@@ -230,41 +217,26 @@ def main():
     stream = torch.cuda.current_stream()
     _lib.check(L.b2t_engine_set_profiling(tok.handle, 1))
 
-    class DevArr:  # zero-copy torch view of an engine-owned device buffer
-        def __init__(self, ptr, count, typestr):
-            self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
-
-    gathered = {}
-
-    def step_device(gather=False):
+    def step_device():
         res = ctypes.c_void_p()
         _lib.check(L.b2t_encode_batch_device(tok.handle, d_bytes.data_ptr(), n, d_off.data_ptr(), n_docs, flags, ctypes.c_void_p(stream.cuda_stream), ctypes.byref(res)))
         T = L.b2t_result_n_tokens(res)
-        if gather:  # one all-gather-v of the token CSR over NCCL (tokenizers_b200/parallel.py)
-            ids = torch.as_tensor(DevArr(L.b2t_result_ids(res), T, "<i4"), device="cuda")
-            offs = torch.as_tensor(DevArr(L.b2t_result_offsets(res), 2 * T, "<i4"), device="cuda")
-            rp = torch.as_tensor(DevArr(L.b2t_result_row_ptr(res), n_docs + 1, "<i8"), device="cuda")
-            gathered["csr"] = all_gather_csr(ids, offs.reshape(-1, 2), rp)
         L.b2t_result_free(res)
         return T
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
     names = (ctypes.c_char_p * 16)(); ms = (ctypes.c_float * 16)()
-    # one node: local rank r runs on the r-th visible GPU (nvidia-smi does not honour CUDA_VISIBLE_DEVICES, so map it)
-    vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
-    sampler = ClockSampler(vis[:world] if len(vis) >= world else range(world))
-    if rank == 0:
-        sampler.start()  # samples every 50 ms from the warm-up through the timed device and e2e regions
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         T = step_device()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    kern_ms = {}
+    barrier()
+    kern_ms, launches = {}, 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     ev0.record(stream)
-    launches = 0
-    for _ in range(a.steps):
+    for _ in range(steps):
         T = step_device()
         launches += L.b2t_engine_last_kernels(tok.handle, names, ms, 16)
         for i in range(16):
@@ -274,110 +246,211 @@ def main():
         for i in range(16):
             names[i] = None
     ev1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    gather_ms = None
-    if world > 1:
-        # the same steps followed by the all-gather-v of ids / offsets / row_ptr that BASELINE.json's north_star names.
-        # Reported separately (key "allgather"): the path itself has no exchange step -- every rank's slice of the CSR
-        # is complete on its own -- and a replicate-everything collective necessarily grows with N.
-        for _ in range(2):
-            step_device(True)
-        torch.cuda.synchronize(); dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        for _ in range(a.steps):
-            step_device(True)
-        g1.record(stream)
-        torch.cuda.synchronize(); dist.barrier()
-        gather_ms = g0.elapsed_time(g1)
-        gathered.clear()
-
-    # ---- end to end through the C ABI with pinned host buffers (H2D + kernels + D2H inside the call)
     _lib.check(L.b2t_engine_set_profiling(tok.handle, 0))
 
-    def step_e2e():
+    # ---- N > 1: the sharded product path, exchange of step i overlapping the kernels of step i + 1
+    shard_ms = None
+    if sharded and world > 1:
+        from tokenizers_b200.parallel import encode_batch_sharded
+        gs = torch.cuda.Stream()
+        out = None
+        for _ in range(2):
+            r = encode_batch_sharded(tok, d_bytes, n, d_off, n_docs, True, out=out, stream=stream, gather_stream=gs)
+            out = (r.ids, r.offsets, r.row_ptr)
+        stream.wait_stream(gs); barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(steps):
+            r = encode_batch_sharded(tok, d_bytes, n, d_off, n_docs, True, out=out, stream=stream, gather_stream=gs)
+        stream.wait_stream(gs)     # every exchange has completed inside the timed region
+        g1.record(stream)
+        barrier()
+        shard_ms = g0.elapsed_time(g1)
+        del r, out
+
+    # ---- end to end through the C ABI with pinned host buffers (H2D + kernels + D2H inside the call)
+    def step_e2e(fl):
         res = ctypes.c_void_p()
-        _lib.check(L.b2t_encode_batch(tok.handle, hptr, hoff_ptr, n_docs, flags, ctypes.byref(res)))
-        T = L.b2t_result_n_tokens(res)
+        _lib.check(L.b2t_encode_batch(tok.handle, hptr, hoff_ptr, n_docs, fl, ctypes.byref(res)))
+        Tt = L.b2t_result_n_tokens(res)
         L.b2t_result_free(res)
-        return T
-    for _ in range(a.warmup):
-        step_e2e()
-    torch.cuda.synchronize()
+        return Tt
+    e2e = {}
+    for key, fl in (("e2e", flags), ("e2e_ids_only", 0)):
+        for _ in range(warmup):
+            step_e2e(fl)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            Te = step_e2e(fl)
+        torch.cuda.synchronize()
+        e2e[key] = (time.perf_counter() - t0) * 1e3
+        assert Te == T
+    L.b2t_host_free(hptr); L.b2t_host_free(hoff_ptr)
+    del d_bytes, d_off, tok
+    torch.cuda.empty_cache()
+    return {"n": n, "n_docs": n_docs, "T": int(T), "dev_ms": dev_ms, "shard_ms": shard_ms, "e2e_ms": e2e["e2e"], "e2e_ids_ms": e2e["e2e_ids_only"],
+            "kern_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()}, "launches": int(launches), "steps": steps}
+
+
+def roofline_of(m, peaks, cfg):
+    peak = peaks.get("hbm_gbs", 6650.0)
+    k1 = m["kern_ms"].get("pretok_scan", float("nan"))
+    n = m["n"]
+    k1_bytes = n * 1.25 + (n / 2048) * 8  # bytes + doc_bits in, start_bits + page summaries out (DESIGN.md)
+    traffic, src = None, None
+    try:  # dram bytes of one launch from the committed ncu --set full capture (profiles/), scaled by input size
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        if tj.get("config") == cfg:
+            traffic, src = tj["dram_bytes_per_input_byte"] * n, tj.get("source", "profiles/k1_traffic.json")
+    except Exception:
+        pass
+    return {"kernel": "pretok_lean_kernel" if cfg != "llama3" else "pretok_stream_kernel", "bound": "hbm", "achieved": k1_bytes / (k1 * 1e-3) / 1e9, "peak": peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback (of fallback)",
+            "unit": "GB/s", "frac": k1_bytes / (k1 * 1e-3) / 1e9 / peak, "traffic": traffic,
+            "traffic_source": (f"ncu capture {src}, dram bytes per input byte x this launch's input bytes (not re-measured in this run)" if traffic else None),
+            "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1, "input_GBps": n / (k1 * 1e-3) / 1e9,
+            "frac_survey_8d_accounting": (n * 1.75) / (k1 * 1e-3) / 1e9 / peak,
+            "note": "achieved uses THIS kernel's layout (bytes + doc bitmap in, split bitmap + page summaries out = 1.25 B per input byte); "
+                    "frac_survey_8d_accounting is the same time with SURVEY.md 8(d)'s u32-start-list accounting (N + 4*N_pretok ~ 1.75 B/B)"}
+
+
+def main():
+    if len(sys.argv) >= 6 and sys.argv[1] == "--cpu-worker":
+        print(json.dumps(cpu_reference_worker(sys.argv[2], int(sys.argv[3]), float(sys.argv[4]), float(sys.argv[5]))))
+        return
+    # Only the JSON line may reach stdout (NCCL and others print there): park the real stdout, send fd 1 to stderr.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mb", type=int, default=1024, help="corpus size per GPU in MiB")
+    ap.add_argument("--config", default="gpt2", choices=list(ASSET))
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary configs (llama3 / wordpiece / skew)")
+    ap.add_argument("--kind", type=int, default=0, help="corpus kind override (5 = length-skew stress of BASELINE configs[4])")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = a.config
+    WORK = {"gpt2": "GPT-2 ByteLevel BPE (50257 vocab trained offline by the reference trainer), synthetic UTF-8 docs avg ~480 B",
+            "llama3": "Llama-3-style BPE (tiktoken regex, 128k vocab, ignore_merges)", "wordpiece": "Whitespace + WordPiece 30522"}
+    SKEW = " [length-skew corpus: Zipf doc lengths 8 B-64 KB, 0.1 % docs hold a 4-64 KB letter/space run]"
+    workload = WORK[cfg] + (SKEW if a.kind == 5 else "")
+
+    if a.impl == "reference":
+        # the reference's CPU implementation, all host threads, bounded sample per step; rank 0 only
+        if rank != 0:
+            return
+        per_step = []
+        for s_i in range(a.warmup + a.steps):
+            r = cpu_reference(cfg, budget_s=max(1.5, 30.0 / (3 * (a.warmup + a.steps))), min_mb=256 if s_i == a.warmup else 0)
+            if s_i >= a.warmup:
+                per_step.append(r)
+        r = max(per_step, key=lambda x: (x.get("sample_bytes", 0) >= (200 << 20), x["value"]))
+        out = {"impl": "reference", "metric": "encode_batch input throughput", "value": r["value"], "unit": "GB/s", "tokens_per_s": r["tokens_per_s"],
+               "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": workload, "bytes_per_step": r.get("sample_bytes"), "sample": r["sample"]},
+               "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores", "sweep", "host") if k in r},
+               "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        real_stdout.write(json.dumps(out) + "\n"); real_stdout.flush()
+        return
+
+    import torch
+    from tokenizers_b200 import _lib
+    from tokenizers_b200.parallel import bind_to_gpu_numa_node
+    torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)   # before any pinned allocation
+    dist = None
     if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        Te = step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert Te == T
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = {"L": _lib.lib(), "rank": rank, "world": world, "local": local, "dist": dist}
+    # one node: local rank r runs on the r-th visible GPU (nvidia-smi does not honour CUDA_VISIBLE_DEVICES, so map it)
+    vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    sampler = ClockSampler(vis[:world] if len(vis) >= world else range(world))
+    if rank == 0:
+        sampler.start()  # samples every 50 ms from the warm-up through the timed device and e2e regions
+    kind = a.kind or KIND[cfg]
+    m = measure(ctx, cfg, kind, a.mb, a.steps, a.warmup, sharded=True)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- reduce over ranks: time = max, work = sum
     if world > 1:
-        v = torch.tensor([dev_ms, e2e_s * 1e3, gather_ms], dtype=torch.float64, device="cuda")
+        v = torch.tensor([m["dev_ms"], m["e2e_ms"], m["e2e_ids_ms"], m["shard_ms"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        w = torch.tensor([float(n), float(T)], dtype=torch.float64, device="cuda")
+        w = torch.tensor([float(m["n"]), float(m["T"])], dtype=torch.float64, device="cuda")
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        mine = torch.tensor([dev_ms / a.steps, sum(float(np.mean(v)) for v in kern_ms.values())], dtype=torch.float64, device="cuda")
-        allr = torch.empty(2 * world, dtype=torch.float64, device="cuda")
+        mine = torch.tensor([m["dev_ms"] / a.steps, sum(m["kern_ms"].values()), m["e2e_ms"] / a.steps, float(numa if numa is not None else -1)], dtype=torch.float64, device="cuda")
+        allr = torch.empty(4 * world, dtype=torch.float64, device="cuda")
         dist.all_gather_into_tensor(allr, mine)
-        allr = allr.reshape(world, 2).tolist()
-        per_rank_ms = [round(x[0], 3) for x in allr]
-        per_rank_kern = [round(x[1], 3) for x in allr]  # kernels only: the rest of a rank's step is host launch / sync gaps
-        dev_ms, e2e_ms, gather_ms = v.tolist(); tot_bytes, tot_tok = w.tolist()
+        allr = allr.reshape(world, 4).tolist()
+        dev_ms, e2e_ms, e2e_ids_ms, shard_ms = v.tolist(); tot_bytes, tot_tok = w.tolist()
     else:
-        e2e_ms, tot_bytes, tot_tok = e2e_s * 1e3, float(n), float(T)
-        per_rank_ms = [round(dev_ms / a.steps, 3)]
-        per_rank_kern = [round(sum(float(np.mean(v)) for v in kern_ms.values()), 3)]
+        dev_ms, e2e_ms, e2e_ids_ms, shard_ms = m["dev_ms"], m["e2e_ms"], m["e2e_ids_ms"], None
+        tot_bytes, tot_tok = float(m["n"]), float(m["T"])
+        allr = [[m["dev_ms"] / a.steps, sum(m["kern_ms"].values()), m["e2e_ms"] / a.steps, float(numa if numa is not None else -1)]]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    ms_per_step = dev_ms / a.steps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = peaks.get("hbm_gbs", 6650.0)
-    k1 = float(np.mean(kern_ms.get("pretok_scan", [float("nan")])))
-    k1_bytes = n * 1.25 + (n / 2048) * 8  # bytes + doc_bits in, start_bits + page summaries out (DESIGN.md)
-    traffic = None
-    try:  # dram bytes of one launch from the committed ncu --set full capture (profiles/), scaled by input size
-        tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
-        if tj.get("config") == cfg:
-            traffic = tj["dram_bytes_per_input_byte"] * n
-    except Exception:
-        pass
-    roof = {"kernel": "pretok_scan_kernel", "bound": "hbm", "achieved": k1_bytes / (k1 * 1e-3) / 1e9, "peak": peak,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback (of fallback)",
-            "unit": "GB/s", "frac": k1_bytes / (k1 * 1e-3) / 1e9 / peak, "traffic": traffic, "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1,
-            "input_GBps": n / (k1 * 1e-3) / 1e9,
-            "note": "achieved uses THIS kernel's layout (bytes + doc bitmap in, split bitmap + page summaries out = 1.25 B per input byte); "
-                    "with SURVEY.md 8(d)'s u32-start-list accounting (N + 4*N_pretok ~ 1.75 B/B) the same time would read frac x 1.4"}
-    out = {"metric": "encode_batch input throughput", "value": tot_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
-           "tokens_per_s": tot_tok / (ms_per_step * 1e-3), "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+    n, n_docs, T = m["n"], m["n_docs"], m["T"]
+    dev_step = dev_ms / a.steps
+    head_step = (shard_ms / a.steps) if world > 1 else dev_step     # N > 1: the sharded path with its exchange is the headline
+    gbps = lambda ms_: tot_bytes / (ms_ * 1e-3) / 1e9
+    out = {"metric": "encode_batch input throughput", "value": gbps(head_step), "unit": "GB/s",
+           "tokens_per_s": tot_tok / (head_step * 1e-3), "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": head_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": workload + workload_kind + f", {n / 1e6:.0f} MB / {n_docs} docs per GPU, ids + char offsets", "bytes_per_gpu": n, "docs_per_gpu": n_docs,
+           "config": {"workload": workload + f", {n / 1e6:.0f} MB / {n_docs} docs per GPU, ids + char offsets", "bytes_per_gpu": n, "docs_per_gpu": n_docs,
                       "tokens_per_gpu": int(T), "l2": "inputs larger than L2 (no flush needed)",
-                      "parallelism": f"docs sharded over {world} rank(s), no data-path collective" + (" (all-gather-v variant under 'allgather')" if world > 1 else "")},
-           "kernels_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()}, "per_rank_ms_per_step": per_rank_ms,
-           "per_rank_kernel_ms_per_step": per_rank_kern,
-           "roofline": roof,
-           "e2e": {"value": tot_bytes / (e2e_ms / a.steps * 1e-3) / 1e9, "unit": "GB/s", "tokens_per_s": tot_tok / (e2e_ms / a.steps * 1e-3), "ms_per_step": e2e_ms / a.steps,
-                   "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(T * 12 + (n_docs + 1) * 8 + 16 * ((n >> 26) + 1))},
-           "gpu_launches": int(launches), "clocks": clocks}
-    if gather_ms is not None:
-        out["allgather"] = {"what": "same steps + NCCL all-gather-v of ids/offsets/row_ptr to every rank (tokenizers_b200/parallel.py)",
-                            "ms_per_step": gather_ms / a.steps, "value": tot_bytes / (gather_ms / a.steps * 1e-3) / 1e9, "unit": "GB/s"}
+                      "parallelism": ("one GPU" if world == 1 else
+                                      f"one batch of {world} shards (contiguous, one per rank); every rank ends with the whole CSR: counts exchanged, compaction "
+                                      f"writes at the rank's displacement, one NCCL send/recv group; the exchange of a step overlaps the next step's kernels")},
+           "kernels_ms": m["kern_ms"], "per_rank_ms_per_step": [round(x[0], 3) for x in allr], "per_rank_kernel_ms_per_step": [round(x[1], 3) for x in allr],
+           "roofline": roofline_of(m, peaks, cfg),
+           "e2e": {"value": gbps(e2e_ms / a.steps), "unit": "GB/s", "tokens_per_s": tot_tok / (e2e_ms / a.steps * 1e-3), "ms_per_step": e2e_ms / a.steps,
+                   "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(T * 12 + (n_docs + 1) * 8 + 16 * ((n >> 26) + 1)),
+                   "per_rank_ms_per_step": [round(x[2], 3) for x in allr], "numa_node_of_rank": [int(x[3]) for x in allr]},
+           "e2e_ids_only": {"value": gbps(e2e_ids_ms / a.steps), "unit": "GB/s", "ms_per_step": e2e_ids_ms / a.steps,
+                            "what": "b2t_encode_batch with flags = 0 (the encode_batch_fast analogue, tokenizer/mod.rs:1382): ids + row_ptr back, 4 B per token",
+                            "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(T * 4 + (n_docs + 1) * 8 + 16 * ((n >> 26) + 1))},
+           "gpu_launches": m["launches"], "clocks": clocks}
+    if world > 1:
+        out["sharded_no_collective"] = {"what": "the same shards, every rank keeps only its own slice of the CSR (no exchange)", "ms_per_step": dev_step,
+                                        "value": gbps(dev_step), "unit": "GB/s"}
+        out["exchange"] = {"what": "bytes of other ranks' CSR each rank receives per step", "bytes": int((tot_tok - T) * 12 + (world - 1) * (n_docs + 1) * 8)}
+    if world == 1 and not a.no_configs and a.kind == 0 and cfg == "gpt2":
+        # the other BASELINE configs on the same line: smaller corpora, fewer steps (stated), same measurement code
+        out["configs"] = {}
+        for name, c2, k2 in (("llama3", "llama3", 2), ("wordpiece", "wordpiece", 4), ("skew", "gpt2", 5)):
+            try:
+                mm = measure(ctx, c2, k2, 512, 3, 3)
+                st = mm["dev_ms"] / mm["steps"]
+                out["configs"][name] = {
+                    "workload": WORK[c2] + (SKEW if k2 == 5 else "") + f", {mm['n'] / 1e6:.0f} MB / {mm['n_docs']} docs, 3 timed steps",
+                    "value": mm["n"] / (st * 1e-3) / 1e9, "unit": "GB/s", "tokens_per_s": mm["T"] / (st * 1e-3), "ms_per_step": st, "kernels_ms": mm["kern_ms"],
+                    "roofline_frac": roofline_of(mm, peaks, c2)["frac"], "roofline_kernel_ms": mm["kern_ms"].get("pretok_scan"),
+                    "e2e": {"value": mm["n"] / (mm["e2e_ms"] / mm["steps"] * 1e-3) / 1e9, "unit": "GB/s"},
+                    "e2e_ids_only": {"value": mm["n"] / (mm["e2e_ids_ms"] / mm["steps"] * 1e-3) / 1e9, "unit": "GB/s"}}
+            except Exception as ex:
+                out["configs"][name] = {"error": str(ex)[:300]}
     if not a.no_cpu and world == 1:
         try:
-            out["cpu_baseline"] = {k: v for k, v in cpu_reference(cfg).items() if k != "seconds"}
+            cb = cpu_reference(cfg)
+            out["cpu_baseline"] = {k: v for k, v in cb.items() if k != "seconds"}
+            if cb.get("tokens_per_s"):
+                out["cpu_baseline"]["gpu_over_cpu_tokens_per_s"] = {"device_resident": out["tokens_per_s"] / cb["tokens_per_s"],
+                                                                    "e2e": out["e2e"]["tokens_per_s"] / cb["tokens_per_s"]}
         except Exception as ex:  # the wheel is part of the image; if it is missing say so instead of inventing a number
             out["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": len(os.sched_getaffinity(0)), "kind": "reference", "sample": f"unavailable: {ex}"}
     real_stdout.write(json.dumps(out) + "\n"); real_stdout.flush()

@@ -98,6 +98,19 @@ int b2t_encode_batch(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_of
 int b2t_encode_batch_device(b2t_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint64_t* d_doc_off,
                             uint32_t n_docs, uint32_t flags, void* stream, b2t_result** out);
 
+/* The same call in two halves, for callers that place the result themselves -- the multi-GPU path: the reference fans a
+ * batch out over rayon threads (tokenizer/mod.rs:1345-1348) and collects the encodings in input order; here every rank
+ * (one process per GPU) encodes its contiguous shard of the batch and writes its part of the token CSR straight at its
+ * displacement of the buffer that the all-gather then completes (tokenizers_b200/parallel.py encode_batch_sharded).
+ *   begin : everything up to the token counts; *n_tokens = tokens of this shard (one small device-to-host read).
+ *   finish: writes ids[0..n_tokens), offsets[0..2 n_tokens) (if requested at begin), word_ids (if requested) and
+ *           row_ptr[0..n_docs] = token_base + the shard's row_ptr to the DEVICE pointers given (already displaced by
+ *           the caller); asynchronous on `stream`.  No other call on this engine between begin and finish. */
+int b2t_encode_batch_device_begin(b2t_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint64_t* d_doc_off,
+                                  uint32_t n_docs, uint32_t flags, void* stream, uint64_t* n_tokens);
+int b2t_encode_batch_device_finish(b2t_engine* e, uint32_t* d_ids, uint32_t* d_offsets, uint32_t* d_word_ids,
+                                   uint64_t* d_row_ptr, uint64_t token_base, void* stream);
+
 /* Replaces PreTokenizer::pre_tokenize (tokenizer/mod.rs:65-67) for a batch: the splits of every document as
  * (start, end) BYTE offsets into the document (offsets[2k], offsets[2k+1]); row_ptr delimits documents.  ids and
  * word_ids are absent.  Host buffers in, pinned host buffers out.  (With add_prefix_space the split that contains the

@@ -244,3 +244,16 @@ def test_invalid_utf8_does_not_fault():
     be = tok.encode_batch_csr(data, off)
     assert be.row_ptr[0] == 0 and int(be.row_ptr[-1]) == len(be.ids) and np.all(np.diff(be.row_ptr.astype(np.int64)) >= 0)
     assert be.ids.max() < tok.get_vocab_size()
+
+
+def test_multi_gpu_sharded_equals_single():
+    """N ranks (one process per GPU, NCCL) encode byte-balanced shards of one batch and gather the CSR in place: the result
+    must equal what one GPU produces for the whole batch (tests/mgpu_check.py).  Needs >= 2 visible GPUs."""
+    import subprocess, sys, torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU visible")
+    n = min(n, 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1", "--nproc-per-node", str(n),
+                        os.path.join(helpers.ROOT, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]

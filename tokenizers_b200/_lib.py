@@ -10,7 +10,8 @@ PRETOK_BYTELEVEL, PRETOK_LLAMA3, PRETOK_WHITESPACE, PRETOK_BYTELEVEL_NOREGEX = 0
 WANT_OFFSETS, WANT_WORD_IDS, OFFSETS_BYTES = 1, 2, 4
 
 # every symbol include/b2t.h declares
-SYMBOLS = ["b2t_engine_create", "b2t_engine_destroy", "b2t_encode_batch", "b2t_encode_batch_device", "b2t_pre_tokenize_batch",
+SYMBOLS = ["b2t_engine_create", "b2t_engine_destroy", "b2t_encode_batch", "b2t_encode_batch_device", "b2t_encode_batch_device_begin",
+           "b2t_encode_batch_device_finish", "b2t_pre_tokenize_batch",
            "b2t_result_n_tokens", "b2t_result_n_docs", "b2t_result_on_device", "b2t_result_ids", "b2t_result_offsets",
            "b2t_result_word_ids", "b2t_result_row_ptr", "b2t_result_free", "b2t_host_alloc", "b2t_host_free",
            "b2t_engine_set_profiling", "b2t_engine_last_kernels", "b2t_unicode_class_table", "b2t_last_error", "b2t_version"]
@@ -49,6 +50,8 @@ def lib():
     L.b2t_engine_destroy.argtypes = [vp]; L.b2t_engine_destroy.restype = None
     L.b2t_encode_batch.argtypes = [vp, vp, vp, u32, u32, ctypes.POINTER(vp)]
     L.b2t_encode_batch_device.argtypes = [vp, vp, u64, vp, u32, u32, vp, ctypes.POINTER(vp)]
+    L.b2t_encode_batch_device_begin.argtypes = [vp, vp, u64, vp, u32, u32, vp, ctypes.POINTER(u64)]
+    L.b2t_encode_batch_device_finish.argtypes = [vp, vp, vp, vp, vp, u64, vp]
     L.b2t_pre_tokenize_batch.argtypes = [vp, vp, vp, u32, ctypes.POINTER(vp)]
     L.b2t_result_n_tokens.argtypes = [vp]; L.b2t_result_n_tokens.restype = u64
     L.b2t_result_n_docs.argtypes = [vp]; L.b2t_result_n_docs.restype = u32

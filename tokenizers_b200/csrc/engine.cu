@@ -89,7 +89,8 @@ struct PinBuf {
 struct Workspace {
   DevBuf bytes, doc_off;              // only used by the host path (inputs staged on the device)
   DevBuf doc_bits, start_bits, drop_bits, page_sum, page_carry, block_sum, block_carry, page_first_doc, ctl;
-  DevBuf ids, offsets, word_ids, row_ptr;
+  DevBuf ids, offsets, word_ids, row_ptr, row_ptr_local;
+  const uint64_t* last_doc_off = nullptr; uint32_t last_n_docs = 0, last_flags = 0; int64_t last_n_pages = 0; bool pending = false;  // begin / finish
   DevBuf tmp_ids, tmp_offsets, tmp_word_ids, tile_count, tile_first, tile_lexcl, tile_bsum;  // pass-1 provisional slots + scan
   DevBuf page_long, long_desc, long_desc1, soft_bits, page_soft, lp_id, lp_val, lp_len, lp_plen, lp_aux, lp_out;  // long BPE pre-tokens (long_kernels.cuh)
   unsigned long long pool_cap = 0;
@@ -102,7 +103,7 @@ struct Workspace {
   void release() {
     bytes.release(); doc_off.release(); doc_bits.release(); start_bits.release(); drop_bits.release(); page_sum.release();
     page_carry.release(); block_sum.release(); block_carry.release(); page_first_doc.release(); ctl.release(); ids.release(); offsets.release();
-    word_ids.release(); row_ptr.release(); h_ctl.release();
+    word_ids.release(); row_ptr.release(); row_ptr_local.release(); h_ctl.release();
     tmp_ids.release(); tmp_offsets.release(); tmp_word_ids.release(); tile_count.release(); tile_first.release(); tile_lexcl.release(); tile_bsum.release();
     pfx_bytes.release(); pfx_doc_off.release(); pfx_local.release(); pfx_block.release(); prefix_bits.release(); pfx_total.release();
     wcache.release(); page_long.release(); long_desc.release(); long_desc1.release(); soft_bits.release(); page_soft.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
@@ -307,8 +308,25 @@ static void rec(b2t_engine* e, cudaStream_t st, const char* name) {
 }
 
 // Runs K0..K2 for a batch resident on the device.  Does not synchronise.  model_pass=false stops after K1b.
+// pass 2 of the model pass: provisional slots -> CSR at the given destination, row_ptr = token_base + shard-local row_ptr
+static int finish_device(b2t_engine* e, Workspace& ws, uint32_t* d_ids, uint32_t* d_off, uint32_t* d_wid, uint64_t* d_rp,
+                         unsigned long long token_base, cudaStream_t st) {
+  const uint32_t flags = ws.last_flags, n_docs = ws.last_n_docs;
+  const int64_t n_pages = ws.last_n_pages;
+  compact_kernel<<<(unsigned)((n_pages * 32 + 255) / 256), 256, 0, st>>>(
+      ws.tile_count.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.tile_lexcl.as<unsigned long long>(), ws.tile_bsum.as<unsigned long long>(), n_pages,
+      ws.tmp_ids.as<uint32_t>(), (flags & B2T_WANT_OFFSETS) ? ws.tmp_offsets.as<uint2>() : nullptr,
+      (flags & B2T_WANT_WORD_IDS) ? ws.tmp_word_ids.as<uint32_t>() : nullptr, d_ids,
+      (flags & B2T_WANT_OFFSETS) ? reinterpret_cast<uint2*>(d_off) : nullptr, (flags & B2T_WANT_WORD_IDS) ? d_wid : nullptr);
+  row_ptr_fix_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(ws.last_doc_off, n_docs, ws.tile_lexcl.as<unsigned long long>(),
+                                                             ws.tile_bsum.as<unsigned long long>(), ws.row_ptr_local.as<uint64_t>(), d_rp, token_base);
+  e->last_launches += 2;
+  CU(cudaGetLastError());
+  return B2T_OK;
+}
+
 static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_bytes, int64_t n, const uint64_t* d_doc_off,
-                               uint32_t n_docs, uint32_t flags, cudaStream_t st, bool model_pass) {
+                               uint32_t n_docs, uint32_t flags, cudaStream_t st, bool model_pass, bool finish = true) {
   if (n + (int64_t)n_docs >= (1ll << 31)) return fail(B2T_ERR_TOO_LARGE, "batch of %lld bytes exceeds the per-call limit of 2^31-1; split it", (long long)n);
   int rc;
   const uint32_t* d_prefix_bits = nullptr;
@@ -351,7 +369,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
       return rc;
   }
   if (model_pass) {
-    if ((rc = ws.ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.tmp_ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.row_ptr.ensure(((size_t)n_docs + 1) * 8)) ||
+    if ((rc = ws.ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.tmp_ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.row_ptr.ensure(((size_t)n_docs + 1) * 8)) || (rc = ws.row_ptr_local.ensure(((size_t)n_docs + 1) * 8)) ||
         (rc = ws.tile_count.ensure(n_pages * 4)) || (rc = ws.tile_first.ensure(n_pages * 4)) || (rc = ws.tile_lexcl.ensure(n_pages * 8)) ||
         (rc = ws.tile_bsum.ensure((n_pages / TSCAN + 2) * 8)))
       return rc;
@@ -407,7 +425,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     P.flags = ((flags & B2T_WANT_OFFSETS) ? F_OFFSETS : 0u) | ((flags & B2T_WANT_WORD_IDS) ? F_WORD_IDS : 0u) |
               ((flags & B2T_OFFSETS_BYTES) ? F_BYTE_OFFSETS : 0u);
     P.ids = ws.tmp_ids.as<uint32_t>(); P.offsets = ws.tmp_offsets.as<uint32_t>(); P.word_ids = ws.tmp_word_ids.as<uint32_t>();
-    P.row_ptr = ws.row_ptr.as<uint64_t>();
+    P.row_ptr = ws.row_ptr_local.as<uint64_t>();
     P.tile_count = ws.tile_count.as<uint32_t>(); P.tile_first = ws.tile_first.as<uint32_t>();
     ctl_block* ctl = ws.ctl.as<ctl_block>();
     P.err_flag = &ctl->err;
@@ -424,14 +442,12 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     tile_scan_block_kernel<<<(unsigned)n_tblk, TSCAN, 0, st>>>(ws.tile_count.as<uint32_t>(), ws.tile_lexcl.as<unsigned long long>(),
                                                              ws.tile_bsum.as<unsigned long long>(), n_pages);
     tile_scan_top_kernel<<<1, TSCAN, 0, st>>>(ws.tile_bsum.as<unsigned long long>(), n_tblk, &ctl->total);
-    compact_kernel<<<(unsigned)((n_pages * 32 + 255) / 256), 256, 0, st>>>(
-        ws.tile_count.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.tile_lexcl.as<unsigned long long>(), ws.tile_bsum.as<unsigned long long>(), n_pages,
-        ws.tmp_ids.as<uint32_t>(), (flags & B2T_WANT_OFFSETS) ? ws.tmp_offsets.as<uint2>() : nullptr,
-        (flags & B2T_WANT_WORD_IDS) ? ws.tmp_word_ids.as<uint32_t>() : nullptr, ws.ids.as<uint32_t>(),
-        (flags & B2T_WANT_OFFSETS) ? ws.offsets.as<uint2>() : nullptr, (flags & B2T_WANT_WORD_IDS) ? ws.word_ids.as<uint32_t>() : nullptr);
-    row_ptr_fix_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.tile_lexcl.as<unsigned long long>(),
-                                                               ws.tile_bsum.as<unsigned long long>(), ws.row_ptr.as<uint64_t>());
-    rec(e, st, "scan_compact"); e->last_launches += 4;
+    e->last_launches += 2;
+    ws.last_doc_off = d_doc_off; ws.last_n_docs = n_docs; ws.last_flags = flags; ws.last_n_pages = n_pages;
+    if (finish) {
+      if ((rc = finish_device(e, ws, ws.ids.as<uint32_t>(), ws.offsets.as<uint32_t>(), ws.word_ids.as<uint32_t>(), ws.row_ptr.as<uint64_t>(), 0ull, st))) return rc;
+    }
+    rec(e, st, "scan_compact");
     CU(cudaMemcpyAsync(ws.h_ctl.p, ws.ctl.p, sizeof(ctl_block), cudaMemcpyDeviceToHost, st));
   }
   CU(cudaGetLastError());
@@ -502,6 +518,44 @@ extern "C" int b2t_encode_batch_device(b2t_engine* e, const uint8_t* d_bytes, ui
   r->row_ptr = ws.row_ptr.as<uint64_t>();
   *out = r;
   return B2T_OK;
+}
+
+extern "C" int b2t_encode_batch_device_begin(b2t_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint64_t* d_doc_off,
+                                             uint32_t n_docs, uint32_t flags, void* stream, uint64_t* n_tokens) {
+  if (!e || !n_tokens || !d_doc_off || (!d_bytes && n_bytes)) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device_begin: null argument");
+  if (((uintptr_t)d_bytes & 15u) != 0) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device_begin: d_bytes must be 16-byte aligned");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->own_stream;
+  Workspace& ws = e->dev_ws;
+  ws.pending = false;
+  int rc;
+  for (int attempt = 0;; ++attempt) {
+    if ((rc = run_device_pipeline(e, ws, d_bytes, (int64_t)n_bytes, d_doc_off, n_docs, flags, st, true, false))) return rc;
+    CU(cudaStreamSynchronize(st));
+    unsigned long long want = 0;
+    rc = check_ctl(ws, &want);
+    if (rc == B2T_OK) break;
+    if (rc != -1 || attempt >= 2) return rc == -1 ? fail(B2T_ERR_CUDA, "long pool did not converge") : rc;
+    if ((rc = ensure_long_pool(ws, want))) return rc;
+  }
+  *n_tokens = ws.h_ctl.as<ctl_block>()->total;
+  ws.pending = true;
+  return B2T_OK;
+}
+
+extern "C" int b2t_encode_batch_device_finish(b2t_engine* e, uint32_t* d_ids, uint32_t* d_offsets, uint32_t* d_word_ids,
+                                              uint64_t* d_row_ptr, uint64_t token_base, void* stream) {
+  if (!e || !d_ids || !d_row_ptr) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device_finish: null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  Workspace& ws = e->dev_ws;
+  if (!ws.pending) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device_finish without a matching begin");
+  if ((ws.last_flags & B2T_WANT_OFFSETS) && !d_offsets) return fail(B2T_ERR_INVALID, "offsets were requested at begin: d_offsets is null");
+  if ((ws.last_flags & B2T_WANT_WORD_IDS) && !d_word_ids) return fail(B2T_ERR_INVALID, "word ids were requested at begin: d_word_ids is null");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->own_stream;
+  ws.pending = false;
+  return finish_device(e, ws, d_ids, d_offsets, d_word_ids, d_row_ptr, token_base, st);
 }
 
 // ------------------------------------------------------------------------------------------------ host pipeline

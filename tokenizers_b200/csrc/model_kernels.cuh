@@ -918,11 +918,12 @@ __global__ void compact_kernel(const uint32_t* __restrict__ tile_count, const ui
 }
 
 __global__ void row_ptr_fix_kernel(const uint64_t* __restrict__ doc_off, uint32_t n_docs, const unsigned long long* __restrict__ local_excl,
-                                   const unsigned long long* __restrict__ block_excl, uint64_t* __restrict__ row_ptr) {
+                                   const unsigned long long* __restrict__ block_excl, const uint64_t* __restrict__ row_ptr_local,
+                                   uint64_t* __restrict__ row_ptr_out, unsigned long long token_base) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d > n_docs) return;
   const int64_t t = (int64_t)(doc_off[d] / TILE);
-  row_ptr[d] += local_excl[t] + block_excl[t / TSCAN];
+  row_ptr_out[d] = row_ptr_local[d] + local_excl[t] + block_excl[t / TSCAN] + token_base;
 }
 
 }  // namespace b2t

@@ -2,9 +2,16 @@
 contiguous ranges, one all-gather-v of the token CSR at the end (BASELINE.json north_star).
 
 The path has no exchange step other than that final gather: documents are independent units (the reference itself only
-parallelises over batch items, tokenizer/mod.rs:1345-1348).  The helpers work on any backend (NCCL on GPUs, gloo in the
-CPU tests) because they only use all_gather_into_tensor / all_gather on padded tensors.
+parallelises over batch items, tokenizer/mod.rs:1345-1348).
+
+`encode_batch_sharded` is the product entry point (one call per rank, every rank ends with the CSR of the whole batch):
+the engine stops at the token counts (b2t_encode_batch_device_begin), the ranks exchange them, every rank's compaction
+kernel then writes its tokens directly at its displacement of the gathered buffers (b2t_encode_batch_device_finish) and one
+group of NCCL send / recv pairs completes the other ranks' parts in place -- no padding, no concatenation, one small host
+sync for the counts.  `all_gather_csr` (padded all_gather_into_tensor + torch.cat) is the backend-neutral form the gloo
+tests use.
 """
+import ctypes
 import torch
 import torch.distributed as dist
 
@@ -74,3 +81,102 @@ def all_gather_csr(ids, offsets, row_ptr, group=None):
         base += counts[r]
         pos += c
     return g_ids, g_off, torch.cat(out)
+
+
+def bind_to_gpu_numa_node(device):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), BEFORE any pinned allocation: pinned
+    pages then land on that node and host<->device copies do not cross the socket link.  Returns the node or None."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device).pci_bus_id if hasattr(torch.cuda.get_device_properties(device), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device), "pci_device_id", 0)
+        if bus is None:
+            return None
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
+class ShardedResult:
+    """The token CSR of the whole batch on this rank's GPU: ids [T], offsets [T, 2] or None, row_ptr [n_docs_total + 1]."""
+    def __init__(self, ids, offsets, row_ptr, counts, doc_counts):
+        self.ids, self.offsets, self.row_ptr, self.token_counts, self.doc_counts = ids, offsets, row_ptr, counts, doc_counts
+
+
+def encode_batch_sharded(tok, d_bytes, n_bytes, d_doc_off, n_docs, want_offsets=True, group=None, out=None, stream=None, gather_stream=None):
+    """Encode this rank's shard (device tensors: packed bytes, shard-relative doc offsets) and return the CSR of the WHOLE
+    batch (all ranks' shards in rank order) on every rank.
+
+    out: optional (ids, offsets, row_ptr) tensors to reuse (capacity checked).  gather_stream: a torch.cuda.Stream for the
+    exchange -- the send / recv group then overlaps whatever the caller launches next on the current stream; the returned
+    tensors are ready once that stream is."""
+    from . import _lib
+    L = _lib.lib()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = d_bytes.device
+    st = stream or torch.cuda.current_stream(dev)
+    flags = _lib.WANT_OFFSETS if want_offsets else 0
+    nt = ctypes.c_uint64(0)
+    _lib.check(L.b2t_encode_batch_device_begin(tok.handle, d_bytes.data_ptr(), n_bytes, d_doc_off.data_ptr(), n_docs, flags,
+                                               ctypes.c_void_p(st.cuda_stream), ctypes.byref(nt)))
+    mine = torch.tensor([nt.value, n_docs], dtype=torch.int64, device=dev)
+    allc = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    allc = allc.reshape(world, 2).tolist()          # the one host sync of the call
+    tcnt = [int(x[0]) for x in allc]; dcnt = [int(x[1]) for x in allc]
+    tdisp = [0]; ddisp = [0]
+    for r in range(world):
+        tdisp.append(tdisp[-1] + tcnt[r]); ddisp.append(ddisp[-1] + dcnt[r])
+    T, D = tdisp[-1], ddisp[-1]
+    if out is not None and out[0].numel() >= T and out[2].numel() >= D + 1 and (not want_offsets or out[1].numel() >= 2 * T):
+        ids, offs, rp = out
+    else:
+        ids = torch.empty(T, dtype=torch.int32, device=dev)
+        offs = torch.empty((T, 2), dtype=torch.int32, device=dev) if want_offsets else None
+        rp = torch.empty(D + 1, dtype=torch.int64, device=dev)
+    offs_flat = offs.reshape(-1) if want_offsets else None
+    if gather_stream is not None and gather_stream is not st:
+        st.wait_stream(gather_stream)   # an exchange of an earlier call may still be using these buffers
+    # my part, written in place by the compaction kernel (row_ptr[ddisp .. ddisp + n_docs] includes the next rank's first entry)
+    _lib.check(L.b2t_encode_batch_device_finish(
+        tok.handle, ids.data_ptr() + 4 * tdisp[rank], (offs_flat.data_ptr() + 8 * tdisp[rank]) if want_offsets else None, None,
+        rp.data_ptr() + 8 * ddisp[rank], tdisp[rank], ctypes.c_void_p(st.cuda_stream)))
+    if world > 1:
+        gs = gather_stream or st
+        if gs is not st:
+            gs.wait_stream(st)
+        with torch.cuda.stream(gs):
+            ops = []
+            for peer in range(world):
+                if peer == rank:
+                    continue
+                if tcnt[rank]:
+                    ops.append(dist.P2POp(dist.isend, ids[tdisp[rank]:tdisp[rank + 1]], peer, group))
+                    if want_offsets:
+                        ops.append(dist.P2POp(dist.isend, offs_flat[2 * tdisp[rank]:2 * tdisp[rank + 1]], peer, group))
+                if dcnt[rank]:
+                    ops.append(dist.P2POp(dist.isend, rp[ddisp[rank] + 1:ddisp[rank + 1] + 1], peer, group))
+                if tcnt[peer]:
+                    ops.append(dist.P2POp(dist.irecv, ids[tdisp[peer]:tdisp[peer + 1]], peer, group))
+                    if want_offsets:
+                        ops.append(dist.P2POp(dist.irecv, offs_flat[2 * tdisp[peer]:2 * tdisp[peer + 1]], peer, group))
+                if dcnt[peer]:
+                    ops.append(dist.P2POp(dist.irecv, rp[ddisp[peer] + 1:ddisp[peer + 1] + 1], peer, group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            if rank != 0:
+                rp[0:1].zero_()
+    return ShardedResult(ids[:T], offs[:T] if want_offsets else None, rp[:D + 1], tcnt, dcnt)
