@@ -111,6 +111,39 @@ int b2t_encode_batch_device_begin(b2t_engine* e, const uint8_t* d_bytes, uint64_
 int b2t_encode_batch_device_finish(b2t_engine* e, uint32_t* d_ids, uint32_t* d_offsets, uint32_t* d_word_ids,
                                    uint64_t* d_row_ptr, uint64_t token_base, void* stream);
 
+/* Dense mode: the steps the reference runs AFTER the path for a batch of single sequences -- truncation
+ * (utils/truncation.rs:70-166, kept part of Encoding::truncate, tokenizer/encoding.rs:307-388), the special-token template
+ * `pre $A post` (processors/template.rs:646-, BertProcessing / RobertaProcessing single form) and padding
+ * (utils/padding.rs:50-81), as TokenizerImpl::post_process orders them (tokenizer/mod.rs:1265-1317) -- done on the device:
+ * the result is a dense [n_docs, L] tensor of ids (+ attention mask + row lengths) instead of the token CSR, which never
+ * leaves the device.  Overflowing parts (stride) are not part of a dense batch; offsets are not produced. */
+typedef struct {
+  uint32_t struct_size;        /* sizeof(b2t_dense_spec) */
+  uint32_t length;             /* PaddingStrategy::Fixed(length); 0 = BatchLongest (needs the batch in one device pass: < 2^31 bytes) */
+  uint32_t pad_to_multiple_of; /* PaddingParams.pad_to_multiple_of, 0 = none */
+  uint32_t max_length;         /* TruncationParams.max_length, special tokens included; 0 = no truncation */
+  uint32_t pad_id;             /* PaddingParams.pad_id */
+  int32_t truncate_left;       /* TruncationDirection::Left: keep the LAST tokens */
+  int32_t pad_left;            /* PaddingDirection::Left */
+  uint32_t n_pre, n_post;      /* special tokens of the single-sequence template before / after the sequence (<= 8 each) */
+  const uint32_t* pre_ids;
+  const uint32_t* post_ids;
+  uint32_t want_mask;          /* also return the attention mask (u8 per position); row lengths always come back */
+} b2t_dense_spec;
+
+/* HOST buffers in (as b2t_encode_batch), pinned host rows out.  A row that does not fit L (Fixed length without a
+ * sufficient truncation; the reference returns a longer row there) fails the batch with B2T_ERR_INVALID. */
+int b2t_encode_batch_dense(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs,
+                           const b2t_dense_spec* spec, b2t_result** out);
+/* Device buffers in (as b2t_encode_batch_device), device rows out (owned by the engine until the next call). */
+int b2t_encode_batch_dense_device(b2t_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint64_t* d_doc_off,
+                                  uint32_t n_docs, const b2t_dense_spec* spec, void* stream, b2t_result** out);
+/* Dense results: row d = ids[d * L .. (d + 1) * L); row_lengths[d] = tokens of row d that are not padding. */
+uint32_t b2t_result_dense_length(const b2t_result* r);        /* L */
+const uint32_t* b2t_result_dense_ids(const b2t_result* r);    /* n_docs * L */
+const uint8_t* b2t_result_attention_mask(const b2t_result* r); /* n_docs * L, or NULL */
+const uint32_t* b2t_result_row_lengths(const b2t_result* r);  /* n_docs */
+
 /* Replaces PreTokenizer::pre_tokenize (tokenizer/mod.rs:65-67) for a batch: the splits of every document as
  * (start, end) BYTE offsets into the document (offsets[2k], offsets[2k+1]); row_ptr delimits documents.  ids and
  * word_ids are absent.  Host buffers in, pinned host buffers out.  (With add_prefix_space the split that contains the
@@ -127,6 +160,7 @@ const uint32_t* b2t_result_ids(const b2t_result* r);      /* n_tokens */
 const uint32_t* b2t_result_offsets(const b2t_result* r);  /* 2 * n_tokens, or NULL */
 const uint32_t* b2t_result_word_ids(const b2t_result* r); /* n_tokens, or NULL */
 const uint64_t* b2t_result_row_ptr(const b2t_result* r);  /* n_docs + 1 */
+/* Host results return their pinned buffers to the engine's pool: free every result BEFORE b2t_engine_destroy. */
 void b2t_result_free(b2t_result* r);
 
 /* Pinned host memory for callers that want b2t_encode_batch to copy straight from their buffer. */

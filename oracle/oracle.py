@@ -179,3 +179,33 @@ class Oracle:
         out = np.zeros(2 * (len(b) + 2), dtype=np.uint32)
         k = lib().orc_pretokenize(self._h, b.ctypes.data if b.size else 0, len(b), out.ctypes.data, len(b) + 2)
         return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(k)]
+
+
+def dense_rows(ids, row_ptr, *, length, pad_to_multiple_of, max_length, pad_id, truncate_left, pad_left, pre, post):
+    """TEST INFRASTRUCTURE.  Plain restatement of what the reference does to a batch of single sequences after the model:
+    truncation to max_length - n_added_tokens (tokenizer/mod.rs:1272-1283, utils/truncation.rs:70-166: kept part only),
+    the template `pre $A post` (processors/template.rs:646-) and pad_encodings (utils/padding.rs:50-81).
+    -> (ids uint32[n, L], attention_mask uint8[n, L], lengths uint32[n]); raises if a row does not fit a fixed length."""
+    n = len(row_ptr) - 1
+    rows = []
+    for d in range(n):
+        seq = list(ids[int(row_ptr[d]):int(row_ptr[d + 1])])
+        if max_length:
+            keep = max_length - len(pre) - len(post)
+            if len(seq) > keep:
+                seq = seq[len(seq) - keep:] if truncate_left else seq[:keep]
+        rows.append(list(pre) + seq + list(post))
+    L = length if length else max((len(r) for r in rows), default=0)
+    if pad_to_multiple_of and L % pad_to_multiple_of:
+        L += pad_to_multiple_of - L % pad_to_multiple_of
+    out = np.full((n, L), pad_id, dtype=np.uint32)
+    mask = np.zeros((n, L), dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.uint32)
+    for d, r in enumerate(rows):
+        if len(r) > L:
+            raise ValueError(f"row {d} has {len(r)} tokens, dense length is {L}")
+        a = L - len(r) if pad_left else 0
+        out[d, a:a + len(r)] = r
+        mask[d, a:a + len(r)] = 1
+        lens[d] = len(r)
+    return out, mask, lens

@@ -12,6 +12,8 @@ WANT_OFFSETS, WANT_WORD_IDS, OFFSETS_BYTES = 1, 2, 4
 # every symbol include/b2t.h declares
 SYMBOLS = ["b2t_engine_create", "b2t_engine_destroy", "b2t_encode_batch", "b2t_encode_batch_device", "b2t_encode_batch_device_begin",
            "b2t_encode_batch_device_finish", "b2t_pre_tokenize_batch",
+           "b2t_encode_batch_dense", "b2t_encode_batch_dense_device", "b2t_result_dense_length", "b2t_result_dense_ids",
+           "b2t_result_attention_mask", "b2t_result_row_lengths",
            "b2t_result_n_tokens", "b2t_result_n_docs", "b2t_result_on_device", "b2t_result_ids", "b2t_result_offsets",
            "b2t_result_word_ids", "b2t_result_row_ptr", "b2t_result_free", "b2t_host_alloc", "b2t_host_free",
            "b2t_engine_set_profiling", "b2t_engine_last_kernels", "b2t_unicode_class_table", "b2t_last_error", "b2t_version"]
@@ -25,6 +27,13 @@ class Config(ctypes.Structure):
                 ("n_merges", ctypes.c_uint32), ("merge_bytes", ctypes.c_void_p), ("merge_off", ctypes.c_void_p),
                 ("unk_token", ctypes.c_char_p), ("continuing_subword_prefix", ctypes.c_char_p),
                 ("max_input_chars_per_word", ctypes.c_uint32), ("device", ctypes.c_int32)]
+
+
+class DenseSpec(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("length", ctypes.c_uint32), ("pad_to_multiple_of", ctypes.c_uint32),
+                ("max_length", ctypes.c_uint32), ("pad_id", ctypes.c_uint32), ("truncate_left", ctypes.c_int32), ("pad_left", ctypes.c_int32),
+                ("n_pre", ctypes.c_uint32), ("n_post", ctypes.c_uint32), ("pre_ids", ctypes.c_void_p), ("post_ids", ctypes.c_void_p),
+                ("want_mask", ctypes.c_uint32)]
 
 
 class B2TError(RuntimeError):
@@ -53,6 +62,11 @@ def lib():
     L.b2t_encode_batch_device_begin.argtypes = [vp, vp, u64, vp, u32, u32, vp, ctypes.POINTER(u64)]
     L.b2t_encode_batch_device_finish.argtypes = [vp, vp, vp, vp, vp, u64, vp]
     L.b2t_pre_tokenize_batch.argtypes = [vp, vp, vp, u32, ctypes.POINTER(vp)]
+    L.b2t_encode_batch_dense.argtypes = [vp, vp, vp, u32, ctypes.POINTER(DenseSpec), ctypes.POINTER(vp)]
+    L.b2t_encode_batch_dense_device.argtypes = [vp, vp, u64, vp, u32, ctypes.POINTER(DenseSpec), vp, ctypes.POINTER(vp)]
+    L.b2t_result_dense_length.argtypes = [vp]; L.b2t_result_dense_length.restype = u32
+    for f in ("b2t_result_dense_ids", "b2t_result_attention_mask", "b2t_result_row_lengths"):
+        getattr(L, f).argtypes = [vp]; getattr(L, f).restype = vp
     L.b2t_result_n_tokens.argtypes = [vp]; L.b2t_result_n_tokens.restype = u64
     L.b2t_result_n_docs.argtypes = [vp]; L.b2t_result_n_docs.restype = u32
     L.b2t_result_on_device.argtypes = [vp]; L.b2t_result_on_device.restype = i32

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/b2t.h"
+#include "dense_kernels.cuh"
 #include "host_tables.h"
 #include "long_kernels.cuh"
 #include "model_kernels.cuh"
@@ -95,6 +96,7 @@ struct Workspace {
   DevBuf page_long, long_desc, long_desc1, soft_bits, page_soft, lp_id, lp_val, lp_len, lp_plen, lp_aux, lp_out;  // long BPE pre-tokens (long_kernels.cuh)
   unsigned long long pool_cap = 0;
   DevBuf wcache;                      // per-batch word cache (model_kernels.cuh)
+  DevBuf dense_ids, dense_mask, dense_len;  // dense [n_docs, L] rows (dense_kernels.cuh)
   DevBuf pfx_bytes, pfx_doc_off, pfx_local, pfx_block, prefix_bits, pfx_total;  // add_prefix_space re-pack (prefix_kernels.cuh)
   int64_t n_eff = 0;                  // bytes of the batch the kernels actually ran on (n + inserted spaces)
   cudaStream_t stream = nullptr;
@@ -106,6 +108,7 @@ struct Workspace {
     word_ids.release(); row_ptr.release(); row_ptr_local.release(); h_ctl.release();
     tmp_ids.release(); tmp_offsets.release(); tmp_word_ids.release(); tile_count.release(); tile_first.release(); tile_lexcl.release(); tile_bsum.release();
     pfx_bytes.release(); pfx_doc_off.release(); pfx_local.release(); pfx_block.release(); prefix_bits.release(); pfx_total.release();
+    dense_ids.release(); dense_mask.release(); dense_len.release();
     wcache.release(); page_long.release(); long_desc.release(); long_desc1.release(); soft_bits.release(); page_soft.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -120,6 +123,11 @@ struct b2t_result {
   uint64_t n_tokens = 0;
   const uint32_t* ids = nullptr; const uint32_t* offsets = nullptr; const uint32_t* word_ids = nullptr; const uint64_t* row_ptr = nullptr;
   PinBuf h_ids, h_offsets, h_word_ids, h_row_ptr;  // host results own pinned memory (returned to the engine pool on free)
+  // dense mode (b2t_encode_batch_dense*): [n_docs, dense_len] rows instead of the CSR
+  uint32_t dense_len = 0;
+  const uint32_t* dense_ids = nullptr; const uint8_t* dense_mask = nullptr; const uint32_t* row_len = nullptr;
+  PinBuf h_dense_ids, h_dense_mask, h_row_len;
+  void release_host() { h_ids.release(); h_offsets.release(); h_word_ids.release(); h_row_ptr.release(); h_dense_ids.release(); h_dense_mask.release(); h_row_len.release(); }
 };
 
 constexpr int NSLOT = 3;
@@ -236,7 +244,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
   e->dev_ws.release();
   for (auto& s : e->slot) s.release();
   e->d_cls.release(); e->d_byte_to_id.release(); e->d_merge.release(); e->d_word.release(); e->d_pool.release(); e->d_edge.release(); e->d_tok2.release(); e->d_tri.release();
-  for (b2t_result* r : e->pool) { r->h_ids.release(); r->h_offsets.release(); r->h_word_ids.release(); r->h_row_ptr.release(); delete r; }
+  for (b2t_result* r : e->pool) { r->release_host(); delete r; }
   if (e->rec_ev_made) for (auto& ev : e->rec_ev) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
@@ -244,7 +252,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
 
 // ------------------------------------------------------------------------------------------------ device pipeline
 struct ctl_block {  // lives in ws.ctl
-  uint32_t reserved;
+  uint32_t max_row;   // dense mode: longest row (template included, after truncation)
   uint32_t err;
   unsigned long long total;
   LongCtl lc;
@@ -307,6 +315,33 @@ static void rec(b2t_engine* e, cudaStream_t st, const char* name) {
   e->n_rec++;
 }
 
+// Dense mode request (b2t_encode_batch_dense*): the device-side spec plus how L is chosen.
+struct DenseReq {
+  DenseSpec S;
+  bool batch_longest = false;   // padding strategy BatchLongest: L = longest row of the batch (after pad_to_multiple_of)
+  uint32_t multiple = 0;        // pad_to_multiple_of
+  bool want_mask = false;
+};
+static uint32_t dense_round(uint32_t len, uint32_t multiple) {
+  if (multiple > 0 && len % multiple) len += multiple - len % multiple;
+  return len;
+}
+// CSR of the workspace -> dense rows in ws.dense_* (asynchronous on st)
+static int launch_dense(b2t_engine* e, Workspace& ws, uint32_t n_docs, const DenseReq& dq, cudaStream_t st) {
+  int rc;
+  const size_t cells = (size_t)n_docs * dq.S.L;
+  if ((rc = ws.dense_ids.ensure(cells * 4 + 16)) || (rc = ws.dense_len.ensure((size_t)n_docs * 4 + 16)) ||
+      (dq.want_mask && (rc = ws.dense_mask.ensure(cells + 16))))
+    return rc;
+  if (n_docs && dq.S.L)
+    dense_rows_kernel<<<(unsigned)(((uint64_t)n_docs * 32 + 255) / 256), 256, 0, st>>>(
+        ws.ids.as<uint32_t>(), ws.row_ptr.as<uint64_t>(), n_docs, dq.S, ws.dense_ids.as<uint32_t>(),
+        dq.want_mask ? ws.dense_mask.as<uint8_t>() : nullptr, ws.dense_len.as<uint32_t>(), nullptr);
+  e->last_launches++;
+  CU(cudaGetLastError());
+  return B2T_OK;
+}
+
 // Runs K0..K2 for a batch resident on the device.  Does not synchronise.  model_pass=false stops after K1b.
 // pass 2 of the model pass: provisional slots -> CSR at the given destination, row_ptr = token_base + shard-local row_ptr
 static int finish_device(b2t_engine* e, Workspace& ws, uint32_t* d_ids, uint32_t* d_off, uint32_t* d_wid, uint64_t* d_rp,
@@ -326,7 +361,7 @@ static int finish_device(b2t_engine* e, Workspace& ws, uint32_t* d_ids, uint32_t
 }
 
 static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_bytes, int64_t n, const uint64_t* d_doc_off,
-                               uint32_t n_docs, uint32_t flags, cudaStream_t st, bool model_pass, bool finish = true) {
+                               uint32_t n_docs, uint32_t flags, cudaStream_t st, bool model_pass, bool finish = true, const DenseReq* dq = nullptr) {
   if (n + (int64_t)n_docs >= (1ll << 31)) return fail(B2T_ERR_TOO_LARGE, "batch of %lld bytes exceeds the per-call limit of 2^31-1; split it", (long long)n);
   int rc;
   const uint32_t* d_prefix_bits = nullptr;
@@ -448,6 +483,14 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
       if ((rc = finish_device(e, ws, ws.ids.as<uint32_t>(), ws.offsets.as<uint32_t>(), ws.word_ids.as<uint32_t>(), ws.row_ptr.as<uint64_t>(), 0ull, st))) return rc;
     }
     rec(e, st, "scan_compact");
+    if (dq && finish) {
+      // dense mode: the longest row always (the host checks it against L / derives L from it), the rows themselves now if L is fixed
+      ctl_block* ctl = ws.ctl.as<ctl_block>();
+      if (n_docs) row_len_max_kernel<<<(n_docs + 255) / 256, 256, 0, st>>>(ws.row_ptr.as<uint64_t>(), n_docs, dq->S.keep_max, dq->S.n_pre + dq->S.n_post, &ctl->max_row);
+      e->last_launches++;
+      if (!dq->batch_longest && (rc = launch_dense(e, ws, n_docs, *dq, st))) return rc;
+      rec(e, st, "dense_rows");
+    }
     CU(cudaMemcpyAsync(ws.h_ctl.p, ws.ctl.p, sizeof(ctl_block), cudaMemcpyDeviceToHost, st));
   }
   CU(cudaGetLastError());
@@ -558,6 +601,69 @@ extern "C" int b2t_encode_batch_device_finish(b2t_engine* e, uint32_t* d_ids, ui
   return finish_device(e, ws, d_ids, d_offsets, d_word_ids, d_row_ptr, token_base, st);
 }
 
+// ------------------------------------------------------------------------------------------------ dense mode
+static int make_dense_req(const b2t_dense_spec* sp, DenseReq* dq) {
+  if (!sp) return fail(B2T_ERR_INVALID, "dense spec is null");
+  if (sp->struct_size != sizeof(b2t_dense_spec)) return fail(B2T_ERR_INVALID, "b2t_dense_spec: struct_size mismatch (%u != %zu)", sp->struct_size, sizeof(b2t_dense_spec));
+  if (sp->n_pre > (uint32_t)DENSE_MAX_SPECIAL || sp->n_post > (uint32_t)DENSE_MAX_SPECIAL)
+    return fail(B2T_ERR_UNSUPPORTED, "templates with more than %d special tokens on one side are not supported", DENSE_MAX_SPECIAL);
+  if ((sp->n_pre && !sp->pre_ids) || (sp->n_post && !sp->post_ids)) return fail(B2T_ERR_INVALID, "dense spec: null special-token list");
+  const uint32_t n_special = sp->n_pre + sp->n_post;
+  // tokenizer/mod.rs:1272-1283: the sequence is truncated to max_length - n_added_tokens
+  if (sp->max_length && sp->max_length < n_special) return fail(B2T_ERR_INVALID, "max_length %u is smaller than the %u special tokens of the template", sp->max_length, n_special);
+  memset(&dq->S, 0, sizeof(dq->S));
+  dq->S.keep_max = sp->max_length ? sp->max_length - n_special : DENSE_NO_LIMIT;
+  dq->S.pad_id = sp->pad_id; dq->S.n_pre = sp->n_pre; dq->S.n_post = sp->n_post;
+  dq->S.trunc_left = sp->truncate_left ? 1 : 0; dq->S.pad_left = sp->pad_left ? 1 : 0;
+  for (uint32_t i = 0; i < sp->n_pre; ++i) dq->S.pre[i] = sp->pre_ids[i];
+  for (uint32_t i = 0; i < sp->n_post; ++i) dq->S.post[i] = sp->post_ids[i];
+  dq->batch_longest = sp->length == 0;
+  dq->multiple = sp->pad_to_multiple_of;
+  dq->S.L = dq->batch_longest ? 0u : dense_round(sp->length, dq->multiple);
+  dq->want_mask = sp->want_mask != 0;
+  return B2T_OK;
+}
+
+extern "C" int b2t_encode_batch_dense(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, const b2t_dense_spec* spec,
+                                      b2t_result** out);
+
+extern "C" int b2t_encode_batch_dense_device(b2t_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint64_t* d_doc_off, uint32_t n_docs,
+                                             const b2t_dense_spec* spec, void* stream, b2t_result** out) {
+  if (!e || !out || !d_doc_off || (!d_bytes && n_bytes)) return fail(B2T_ERR_INVALID, "b2t_encode_batch_dense_device: null argument");
+  if (((uintptr_t)d_bytes & 15u) != 0) return fail(B2T_ERR_INVALID, "b2t_encode_batch_dense_device: d_bytes must be 16-byte aligned");
+  DenseReq dq;
+  int rc;
+  if ((rc = make_dense_req(spec, &dq))) return rc;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->own_stream;
+  Workspace& ws = e->dev_ws;
+  for (int attempt = 0;; ++attempt) {
+    if ((rc = run_device_pipeline(e, ws, d_bytes, (int64_t)n_bytes, d_doc_off, n_docs, 0u, st, true, true, &dq))) return rc;
+    CU(cudaStreamSynchronize(st));
+    unsigned long long want = 0;
+    rc = check_ctl(ws, &want);
+    if (rc == B2T_OK) break;
+    if (rc != -1 || attempt >= 2) return rc == -1 ? fail(B2T_ERR_CUDA, "long pool did not converge") : rc;
+    if ((rc = ensure_long_pool(ws, want))) return rc;
+  }
+  const uint32_t max_row = ws.h_ctl.as<ctl_block>()->max_row;
+  if (dq.batch_longest) {
+    dq.S.L = dense_round(max_row, dq.multiple);
+    if ((rc = launch_dense(e, ws, n_docs, dq, st))) return rc;   // asynchronous on st, like the CSR entry point's result
+  } else if (max_row > dq.S.L) {
+    return fail(B2T_ERR_INVALID, "a row of %u tokens does not fit the dense length %u: enable truncation (the reference returns a longer row here)", max_row, dq.S.L);
+  }
+  b2t_result* r = new b2t_result();
+  r->eng = e; r->on_device = 1; r->n_docs = n_docs;
+  r->n_tokens = ws.h_ctl.as<ctl_block>()->total;
+  r->dense_len = dq.S.L;
+  r->dense_ids = ws.dense_ids.as<uint32_t>(); r->row_len = ws.dense_len.as<uint32_t>();
+  r->dense_mask = dq.want_mask ? ws.dense_mask.as<uint8_t>() : nullptr;
+  *out = r;
+  return B2T_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ host pipeline
 static b2t_result* pool_get(b2t_engine* e) {
   if (!e->pool.empty()) { b2t_result* r = e->pool.back(); e->pool.pop_back(); return r; }
@@ -579,7 +685,7 @@ __global__ void rebase_kernel(uint64_t* doc_off, uint32_t count, uint64_t base) 
 struct Chunk { uint32_t d0, d1; uint64_t b0, b1; uint64_t tok_base; };
 
 static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, uint32_t flags, bool pretok_only,
-                       b2t_result** out) {
+                       b2t_result** out, const DenseReq* dq_in = nullptr) {
   if (doc_off[0] != 0) return fail(B2T_ERR_INVALID, "doc_off[0] must be 0");
   for (uint32_t d = 0; d < n_docs; ++d)  // the kernels index the buffer with these: a decreasing offset must never reach them
     if (doc_off[d + 1] < doc_off[d]) return fail(B2T_ERR_INVALID, "doc_off must be non-decreasing (document %u)", d);
@@ -587,10 +693,17 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
   // ---- split into chunks of whole documents
   std::vector<Chunk> chunks;
   uint64_t max_chunk = 0;
+  DenseReq dq_local;
+  DenseReq* dq = nullptr;
+  if (dq_in) { dq_local = *dq_in; dq = &dq_local; flags = 0; }
+  // BatchLongest padding needs every row length before the first row can be written: the batch runs as one chunk
+  if (dq && dq->batch_longest && total_bytes + n_docs >= (1ull << 31))
+    return fail(B2T_ERR_UNSUPPORTED, "dense output padded to the longest row needs the batch in one device pass (< 2^31 bytes); pad to a fixed length instead");
+  const uint64_t chunk_bytes = (dq && dq->batch_longest) ? (1ull << 31) : (uint64_t)e->chunk_bytes;
   {
     uint32_t d = 0;
     while (d < n_docs) {
-      uint64_t limit = doc_off[d] + e->chunk_bytes;
+      uint64_t limit = doc_off[d] + chunk_bytes;
       uint32_t d1 = (uint32_t)(std::upper_bound(doc_off + d + 1, doc_off + n_docs + 1, limit) - doc_off) - 1;
       if (d1 <= d) d1 = d + 1;  // a single document larger than the chunk size
       if (doc_off[d1] - doc_off[d] >= (1ull << 31)) return fail(B2T_ERR_TOO_LARGE, "document %u is larger than 2 GiB", d);
@@ -614,7 +727,17 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
     if (want_wid && (rc2 = r->h_word_ids.ensure(need_tok * 4, true))) return rc2;
     return B2T_OK;
   };
-  if ((rc = grow(cap_tok))) { e->pool.push_back(r); return rc; }
+  r->dense_len = 0; r->dense_ids = nullptr; r->dense_mask = nullptr; r->row_len = nullptr;
+  auto dense_host = [&](uint32_t L) -> int {   // pinned rows of the whole batch
+    int rc2;
+    const size_t cells = (size_t)n_docs * L;
+    if ((rc2 = r->h_dense_ids.ensure(cells * 4 + 16, false)) || (rc2 = r->h_row_len.ensure((size_t)n_docs * 4 + 16, false)) ||
+        (dq->want_mask && (rc2 = r->h_dense_mask.ensure(cells + 16, false))))
+      return rc2;
+    return B2T_OK;
+  };
+  if (dq) { if (!dq->batch_longest && (rc = dense_host(dq->S.L))) { e->pool.push_back(r); return rc; } }
+  else if ((rc = grow(cap_tok))) { e->pool.push_back(r); return rc; }
 
   uint64_t tok_base = 0;
   const size_t nc = chunks.size();
@@ -633,11 +756,28 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
       if (rc2 != -1 || attempt >= 2) return rc2 == -1 ? fail(B2T_ERR_CUDA, "long pool did not converge") : rc2;
       // rerun this chunk with a larger pool (its input is still resident in the slot)
       if ((rc2 = ensure_long_pool(ws, want))) return rc2;
-      if ((rc2 = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)(c.b1 - c.b0), ws.doc_off.as<uint64_t>(), c.d1 - c.d0, flags, ws.stream, true))) return rc2;
+      if ((rc2 = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)(c.b1 - c.b0), ws.doc_off.as<uint64_t>(), c.d1 - c.d0, flags, ws.stream, true, true, dq))) return rc2;
       CU(cudaStreamSynchronize(ws.stream));
     }
     const uint64_t nt = ws.h_ctl.as<ctl_block>()->total;
     c.tok_base = tok_base;
+    if (dq) {
+      const uint32_t nd = c.d1 - c.d0, max_row = ws.h_ctl.as<ctl_block>()->max_row;
+      if (dq->batch_longest) {   // one chunk: L is known now
+        dq->S.L = dense_round(max_row, dq->multiple);
+        if ((rc2 = dense_host(dq->S.L)) || (rc2 = launch_dense(e, ws, nd, *dq, ws.stream))) return rc2;
+      } else if (max_row > dq->S.L) {
+        return fail(B2T_ERR_INVALID, "a row of %u tokens does not fit the dense length %u: enable truncation (the reference returns a longer row here)", max_row, dq->S.L);
+      }
+      const size_t L = dq->S.L;
+      if (nd && L) {
+        CU(cudaMemcpyAsync(r->h_dense_ids.as<uint32_t>() + (size_t)c.d0 * L, ws.dense_ids.p, (size_t)nd * L * 4, cudaMemcpyDeviceToHost, ws.stream));
+        if (dq->want_mask) CU(cudaMemcpyAsync(r->h_dense_mask.as<uint8_t>() + (size_t)c.d0 * L, ws.dense_mask.p, (size_t)nd * L, cudaMemcpyDeviceToHost, ws.stream));
+      }
+      if (nd) CU(cudaMemcpyAsync(r->h_row_len.as<uint32_t>() + c.d0, ws.dense_len.p, (size_t)nd * 4, cudaMemcpyDeviceToHost, ws.stream));
+      tok_base += nt;
+      return B2T_OK;
+    }
     if (tok_base + nt > cap_tok) {
       // earlier chunks may still be copying into the old buffers: let them land, then grow (contents are kept)
       for (auto& s : e->slot) if (s.stream) CU(cudaStreamSynchronize(s.stream));
@@ -658,6 +798,12 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
   };
   size_t drained = 0;
   rc = B2T_OK;
+#define CUL(call)                                                                                             \
+  {                                                                                                           \
+    cudaError_t _e = (call);                                                                                  \
+    if (_e != cudaSuccess) { rc = fail(B2T_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); break; } \
+  }
+  // (a CUDA failure inside the loop must reach the common cleanup below: the pooled result goes back, slot streams are drained)
   for (size_t ci = 0; ci < nc && rc == B2T_OK; ++ci) {
     Workspace& ws = e->slot[ci % NSLOT];
     if ((rc = slot_init(ws))) break;
@@ -665,26 +811,33 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
       // slot reuse: the chunk that used it must be drained and its copies must have landed
       while (rc == B2T_OK && drained + NSLOT <= ci) rc = drain(drained++);
       if (rc) break;
-      CU(cudaStreamSynchronize(ws.stream));
+      CUL(cudaStreamSynchronize(ws.stream));
     }
     Chunk& c = chunks[ci];
     const uint64_t nb = c.b1 - c.b0;
     const uint32_t nd = c.d1 - c.d0;
     if ((rc = ws.bytes.ensure(nb + 64)) || (rc = ws.doc_off.ensure(((size_t)nd + 1) * 8))) break;
-    if (nb) CU(cudaMemcpyAsync(ws.bytes.p, bytes + c.b0, nb, cudaMemcpyHostToDevice, ws.stream));
-    CU(cudaMemcpyAsync(ws.doc_off.p, doc_off + c.d0, ((size_t)nd + 1) * 8, cudaMemcpyHostToDevice, ws.stream));
+    if (nb) CUL(cudaMemcpyAsync(ws.bytes.p, bytes + c.b0, nb, cudaMemcpyHostToDevice, ws.stream));
+    CUL(cudaMemcpyAsync(ws.doc_off.p, doc_off + c.d0, ((size_t)nd + 1) * 8, cudaMemcpyHostToDevice, ws.stream));
     if (c.b0) rebase_kernel<<<(nd + 1 + 255) / 256, 256, 0, ws.stream>>>(ws.doc_off.as<uint64_t>(), nd + 1, c.b0);
-    rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)nb, ws.doc_off.as<uint64_t>(), nd, flags, ws.stream, !pretok_only);
+    rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)nb, ws.doc_off.as<uint64_t>(), nd, flags, ws.stream, !pretok_only, true, dq);
     if (rc) break;
-    CU(cudaEventRecord(ws.done, ws.stream));
+    CUL(cudaEventRecord(ws.done, ws.stream));
     // keep at most NSLOT - 1 chunks un-drained so that result copies overlap the next chunks' kernels
     while (rc == B2T_OK && drained + (NSLOT - 1) <= ci) rc = drain(drained++);
   }
+#undef CUL
   while (rc == B2T_OK && drained < nc) rc = drain(drained++);
   for (auto& s : e->slot) if (s.stream) cudaStreamSynchronize(s.stream);
   if (rc) { e->pool.push_back(r); return rc; }
 
-  if (!pretok_only) {
+  if (dq) {
+    if (n_docs == 0 && dq->batch_longest) dq->S.L = 0;
+    r->n_tokens = tok_base; r->ids = nullptr; r->offsets = nullptr; r->word_ids = nullptr; r->row_ptr = nullptr;
+    r->dense_len = dq->S.L;
+    r->dense_ids = r->h_dense_ids.as<uint32_t>(); r->row_len = r->h_row_len.as<uint32_t>();
+    r->dense_mask = dq->want_mask ? r->h_dense_mask.as<uint8_t>() : nullptr;
+  } else if (!pretok_only) {
     // chunk-relative row_ptr -> batch-relative (host fix-up: one addition per document)
     uint64_t* rp = r->h_row_ptr.as<uint64_t>();
     for (size_t ci = 1; ci < nc; ++ci) {
@@ -708,6 +861,17 @@ extern "C" int b2t_encode_batch(b2t_engine* e, const uint8_t* bytes, const uint6
   std::lock_guard<std::mutex> lk(e->mu);
   CU(cudaSetDevice(e->device));
   return host_encode(e, bytes, doc_off, n_docs, flags, false, out);
+}
+
+extern "C" int b2t_encode_batch_dense(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, const b2t_dense_spec* spec,
+                                      b2t_result** out) {
+  if (!e || !out || !doc_off || (!bytes && doc_off[n_docs])) return fail(B2T_ERR_INVALID, "b2t_encode_batch_dense: null argument");
+  DenseReq dq;
+  int rc;
+  if ((rc = make_dense_req(spec, &dq))) return rc;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  return host_encode(e, bytes, doc_off, n_docs, 0u, false, out, &dq);
 }
 
 // PreTokenizer seam: runs K0/K1 and expands the split bitmaps into (start, end) pairs.  The expansion of the bitmap
@@ -776,13 +940,17 @@ extern "C" const uint32_t* b2t_result_ids(const b2t_result* r) { return r ? r->i
 extern "C" const uint32_t* b2t_result_offsets(const b2t_result* r) { return r ? r->offsets : nullptr; }
 extern "C" const uint32_t* b2t_result_word_ids(const b2t_result* r) { return r ? r->word_ids : nullptr; }
 extern "C" const uint64_t* b2t_result_row_ptr(const b2t_result* r) { return r ? r->row_ptr : nullptr; }
+extern "C" uint32_t b2t_result_dense_length(const b2t_result* r) { return r ? r->dense_len : 0; }
+extern "C" const uint32_t* b2t_result_dense_ids(const b2t_result* r) { return r ? r->dense_ids : nullptr; }
+extern "C" const uint8_t* b2t_result_attention_mask(const b2t_result* r) { return r ? r->dense_mask : nullptr; }
+extern "C" const uint32_t* b2t_result_row_lengths(const b2t_result* r) { return r ? r->row_len : nullptr; }
 extern "C" void b2t_result_free(b2t_result* r) {
   if (!r) return;
   if (r->on_device || !r->eng) { delete r; return; }
   b2t_engine* e = r->eng;
   std::lock_guard<std::mutex> lk(e->mu);
   if (e->pool.size() < 4) e->pool.push_back(r);
-  else { cudaSetDevice(e->device); r->h_ids.release(); r->h_offsets.release(); r->h_word_ids.release(); r->h_row_ptr.release(); delete r; }
+  else { cudaSetDevice(e->device); r->release_host(); delete r; }
 }
 
 extern "C" int b2t_host_alloc(size_t bytes, void** out) {

@@ -660,6 +660,59 @@ class Tokenizer:
         be, trim = self._encode_core(data, doc_off, flags, data, extract_added_tokens)
         return self._finish(be, trim, add_special_tokens)
 
+    # ---- dense mode: template + truncation + padding on the device (include/b2t.h b2t_encode_batch_dense)
+    def dense_spec(self, add_special_tokens=True, want_mask=True):
+        """The tokenizer's truncation / padding / single-sequence template as a b2t_dense_spec (+ the arrays it points to)."""
+        tp, tr, pd = self._template, self._truncation, self._padding
+        if pd is None:
+            raise UnsupportedConfig("dense output needs padding enabled (enable_padding): rows must share one length")
+        pre = [t for t, _ in tp["pre"]] if (tp is not None and add_special_tokens) else []
+        post = [t for t, _ in tp["post"]] if (tp is not None and add_special_tokens) else []
+        sp = _lib.DenseSpec()
+        sp.struct_size = ctypes.sizeof(_lib.DenseSpec)
+        sp.length = 0 if pd["length"] is None else int(pd["length"])
+        sp.pad_to_multiple_of = int(pd["pad_to_multiple_of"] or 0)
+        sp.max_length = 0 if tr is None else int(tr["max_length"])
+        if tr is not None and sp.max_length == 0:
+            raise UnsupportedConfig("truncation to max_length 0 has no dense form")
+        sp.pad_id = pd["pad_id"]
+        sp.truncate_left = int(tr is not None and tr["direction"] == "left")
+        sp.pad_left = int(pd["direction"] == "left")
+        keep = (np.asarray(pre, dtype=np.uint32), np.asarray(post, dtype=np.uint32))
+        sp.n_pre, sp.n_post = len(pre), len(post)
+        sp.pre_ids, sp.post_ids = (keep[0].ctypes.data if pre else None), (keep[1].ctypes.data if post else None)
+        sp.want_mask = int(want_mask)
+        return sp, keep
+
+    def encode_batch_dense(self, data, doc_off=None, add_special_tokens=True, want_mask=True):
+        """Batch of single sequences -> {"input_ids": uint32[n, L], "attention_mask": uint8[n, L] | None, "lengths": uint32[n]}
+        with the tokenizer's truncation, template and padding applied on the device (what `encode_batch` + stacking the
+        Encodings' ids / attention_mask gives in the reference).  `data` is a list of str, or packed (np.uint8[N], np.uint64[n+1])."""
+        if doc_off is None:
+            bs = [d.encode("utf-8") for d in data]
+            doc_off = np.zeros(len(bs) + 1, dtype=np.uint64)
+            if bs:
+                np.cumsum([len(b) for b in bs], out=doc_off[1:])
+            data = np.frombuffer(b"".join(bs), dtype=np.uint8)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        if self._added is not None and added.split_batch(self._added, data, doc_off)[2]:
+            raise UnsupportedConfig("the batch contains added tokens: dense mode has no added-token extraction yet, use encode_batch")
+        sp, keep = self.dense_spec(add_special_tokens, want_mask)
+        n = len(doc_off) - 1
+        L = _lib.lib()
+        res = ctypes.c_void_p()
+        _lib.check(L.b2t_encode_batch_dense(self._h, data.ctypes.data if data.size else None, doc_off.ctypes.data, n, ctypes.byref(sp), ctypes.byref(res)))
+        try:
+            W = L.b2t_result_dense_length(res)
+            ids = _view(L.b2t_result_dense_ids(res), n * W, np.uint32).reshape(n, W).copy()
+            mask = _view(L.b2t_result_attention_mask(res), n * W, np.uint8).reshape(n, W).copy() if want_mask else None
+            lens = _view(L.b2t_result_row_lengths(res), n, np.uint32).copy()
+        finally:
+            L.b2t_result_free(res)
+        del keep
+        return {"input_ids": ids, "attention_mask": mask, "lengths": lens}
+
     def _trim_tables(self):
         """per token id: leading / trailing 'G-dot' characters (the byte-level image of U+0020) of its vocabulary string"""
         if self._trim is None:

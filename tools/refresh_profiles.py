@@ -83,13 +83,13 @@ def main():
     run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "tokenizers_b200", "libb2t.so")], cwd=work)
     sass = os.path.join(work, "engine.sass")
     open(sass, "w").write(run(["nvdisasm", "-g", os.path.join(work, "engine.sm_100a.cubin")]))
-    d = kernel_summary(tag, "k1", "pretok_scan_kernelILi0", sass)
+    d = kernel_summary(tag, "k1", "pretok_lean_kernelILi0", sass)
     kernel_summary(tag, "k2", "model_tile_kernelILi0", sass)
     if d:
         n_in = 256 * 2 ** 20  # bench.py --mb 256 (the generator stops a little short of it; good to three digits)
         per = d["_dram_bytes"] / n_in
         json.dump({"config": "gpt2", "dram_bytes_per_input_byte": round(per, 4),
-                   "source": f"ncu --set full, pretok_scan_kernel<0,256>, bench.py --mb 256 (gpurun_out/{tag}_k1.ncu-rep)"},
+                   "source": f"ncu --set full, pretok_lean_kernel<0>, bench.py --mb 256 (gpurun_out/{tag}_k1.ncu-rep)"},
                   open(os.path.join(PROF, "k1_traffic.json"), "w"))
 
 
