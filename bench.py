@@ -444,6 +444,19 @@ def main():
                     "e2e_ids_only": {"value": mm["n"] / (mm["e2e_ids_ms"] / mm["steps"] * 1e-3) / 1e9, "unit": "GB/s"}}
             except Exception as ex:
                 out["configs"][name] = {"error": str(ex)[:300]}
+        # the reference benches BPE with its word cache off too (benches/bpe_benchmark.rs:59-71, cache_capacity(0)): same corpus, the
+        # per-batch word cache of the page kernel switched off, so that every pre-token goes through the merge loop
+        try:
+            os.environ["B2T_WCACHE"] = "0"
+            mm = measure(ctx, "gpt2", 2, 256, 2, 3)
+            st = mm["dev_ms"] / mm["steps"]
+            out["configs"]["gpt2_word_cache_off"] = {
+                "workload": WORK["gpt2"] + f", {mm['n'] / 1e6:.0f} MB / {mm['n_docs']} docs, 2 timed steps, B2T_WCACHE=0 (no word cache: every pre-token is merged)",
+                "value": mm["n"] / (st * 1e-3) / 1e9, "unit": "GB/s", "tokens_per_s": mm["T"] / (st * 1e-3), "ms_per_step": st, "kernels_ms": mm["kern_ms"]}
+        except Exception as ex:
+            out["configs"]["gpt2_word_cache_off"] = {"error": str(ex)[:300]}
+        finally:
+            os.environ.pop("B2T_WCACHE", None)
     if not a.no_cpu and world == 1:
         try:
             cb = cpu_reference(cfg)

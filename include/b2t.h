@@ -73,14 +73,32 @@ typedef struct {
 enum {
   B2T_WANT_OFFSETS = 1u,   /* produce (start, end) per token */
   B2T_WANT_WORD_IDS = 2u,  /* produce the pre-token ordinal per token (Encoding.words, tokenizer/pre_tokenizer.rs:252-256) */
-  B2T_OFFSETS_BYTES = 4u   /* OffsetType::Byte (Rust encode_batch) instead of OffsetType::Char (encode_batch_char_offsets,
+  B2T_OFFSETS_BYTES = 4u,  /* OffsetType::Byte (Rust encode_batch) instead of OffsetType::Char (encode_batch_char_offsets,
                               what the Python binding always uses: bindings/python/src/tokenizer.rs:1332) */
+  B2T_NO_ADDED_TOKENS = 8u,   /* skip the added-token extraction of an engine that has added tokens (the caller knows the text
+                                 holds none, or has split it already) */
+  B2T_FLAG_ADDED_IDS = 16u    /* mark the tokens that come from the added vocabulary with bit 31 of their id */
 };
+
+/* AddedToken properties (tokenizer/added_vocabulary.rs:11-76) */
+enum { B2T_ADDED_SINGLE_WORD = 1u, B2T_ADDED_LSTRIP = 2u, B2T_ADDED_RSTRIP = 4u, B2T_ADDED_NORMALIZED = 8u };
 
 /* Replaces TokenizerBuilder::build for the path.  The tables are uploaded to the device once; the engine is
  * immutable afterwards and may be used from several host threads (calls serialise on an internal mutex). */
 int b2t_engine_create(const b2t_config* cfg, b2t_engine** out);
 void b2t_engine_destroy(b2t_engine* e);
+
+/* Replaces AddedVocabulary::add_tokens / refresh_added_tokens (tokenizer/added_vocabulary.rs:270-420) for the path: the
+ * tokens the encode entry points extract from the text BEFORE pre-tokenization, like extract_and_normalize without a
+ * normalizer (added_vocabulary.rs:523-564: non-normalized tokens first, then the normalized ones on the remaining pieces;
+ * leftmost-longest, single_word / lstrip / rstrip).  Token i = bytes[off[i] .. off[i+1]), ids[i] < 2^20, flags[i] = OR of
+ * B2T_ADDED_*.  The extraction runs on the device (no re-packing: span boundaries become hard boundaries of the scan, a
+ * span becomes one pre-token that carries the token's id).  Not combinable with add_prefix_space (B2T_ERR_UNSUPPORTED); a
+ * batch whose spans do not fit the device limits (a span over 256 bytes after lstrip / rstrip, more spans than one per
+ * 16 input bytes, the reference's overlapping-span corner case) fails with B2T_ERR_UNSUPPORTED -- the host can then split
+ * the text itself and pass B2T_NO_ADDED_TOKENS.  n_tokens = 0 clears the set.  Not to be called concurrently with encodes. */
+int b2t_engine_set_added_tokens(b2t_engine* e, uint32_t n_tokens, const uint8_t* bytes, const uint32_t* off,
+                                const uint32_t* ids, const uint8_t* flags);
 
 /* Replaces TokenizerImpl::encode_batch / encode_batch_char_offsets / encode_batch_fast (tokenizer/mod.rs:1337-1401)
  * for raw (not pre-tokenized) single sequences with add_special_tokens=false.  HOST buffers: `bytes` holds the

@@ -202,11 +202,59 @@ def test_gpu_added_tokens_vs_golden(idx):
     from tokenizers_b200 import Tokenizer
     g = _golden_cases()["configs"][idx]
     tok = Tokenizer.from_str(with_added_tokens(_patched(g["asset"], g["prefix_space"]), g["template"]))
+    assert tok._dev_added == (not g["prefix_space"])   # add_prefix_space: the prefix goes in front of every piece, the host splits
     docs = g["docs"]
     for special in (False, True):
         _compare(_flat(tok.encode_batch(docs, add_special_tokens=special)), g["expected"][str(special)], docs, f"gpu golden {g['asset']}")
     ids_fast = [e.ids for e in tok.encode_batch_fast(docs, add_special_tokens=True)]
     assert ids_fast == [c["ids"] for c in g["expected"]["True"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("asset,template", CONFIGS)
+def test_gpu_device_extraction_matches_host_logic(asset, template):
+    """Added-token extraction ON THE DEVICE (b2t_engine_set_added_tokens: candidates, per-document resolution, spans as hard
+    boundaries of the scan) against the host logic in front of the oracle (itself pinned to the wheel above)."""
+    from tokenizers_b200 import Tokenizer
+    from helpers import pack_docs
+    tj = with_added_tokens(_patched(asset, False), template)
+    tok, ref = Tokenizer.from_str(tj), oracle_backed_tokenizer(tj)
+    assert tok._dev_added and not ref._dev_added
+    docs = added_token_docs(99, 1500) + ["x" + " " * 40 + "<mask>" + " " * 50 + "[SEP2]" + "\t" * 30 + "y", "<a>" * 7 + "<a><b>" * 3, "tok" * 5]
+    for special in (False, True):
+        _compare(_flat(tok.encode_batch(docs, add_special_tokens=special)), _flat(ref.encode_batch(docs, add_special_tokens=special)), docs, f"device {asset}")
+    assert [e.ids for e in tok.encode_batch_fast(docs)] == [e.ids for e in ref.encode_batch_fast(docs)]
+    data, off = pack_docs(docs)
+    for kw in (dict(byte_offsets=True), dict(offsets=False, word_ids=False), dict(add_special_tokens=True)):
+        a, b = tok.encode_batch_csr(data, off, **kw), ref.encode_batch_csr(data, off, **kw)
+        for x, y in ((a.ids, b.ids), (a.offsets, b.offsets), (a.word_ids, b.word_ids), (a.row_ptr, b.row_ptr)):
+            assert (x is None and y is None) or np.array_equal(x, y), (asset, kw)
+    # beyond the device limits (a span over 256 bytes after lstrip) the shim splits on the host: same result
+    hard = ["a" + " " * 300 + "<mask> b", "<a>" * 40 + " z", "q " + "<|endoftext|>" * 12]
+    _compare(_flat(tok.encode_batch(hard)), _flat(ref.encode_batch(hard)), hard, f"fallback {asset}")
+    # many documents, many chunks
+    os.environ["B2T_CHUNK_BYTES"] = "32768"
+    try:
+        tok2 = Tokenizer.from_str(tj)
+        many = added_token_docs(7, 6000)
+        _compare(_flat(tok2.encode_batch(many)), _flat(ref.encode_batch(many)), many, f"chunks {asset}")
+    finally:
+        del os.environ["B2T_CHUNK_BYTES"]
+
+
+@pytest.mark.gpu
+def test_gpu_dense_with_added_tokens():
+    """dense mode runs the device extraction too"""
+    from tokenizers_b200 import Tokenizer
+    tj = with_added_tokens(_patched("gpt2_style", False), True)
+    tok, ref = Tokenizer.from_str(tj), oracle_backed_tokenizer(tj)
+    docs = added_token_docs(5, 400)
+    tok.enable_truncation(24); tok.enable_padding(length=24, pad_id=7)
+    ref.enable_truncation(24); ref.enable_padding(length=24, pad_id=7)
+    got = tok.encode_batch_dense(docs)
+    exp = ref.encode_batch(docs)
+    assert np.array_equal(got["input_ids"], np.array([e.ids for e in exp], dtype=np.uint32))
+    assert np.array_equal(got["attention_mask"], np.array([e.attention_mask for e in exp], dtype=np.uint8))
 
 
 @pytest.mark.gpu

@@ -7,10 +7,11 @@ LIB_PATH = os.environ.get("B2T_LIB") or os.path.join(_HERE, "libb2t.so")  # B2T_
 B2T_OK, B2T_ERR_INVALID, B2T_ERR_UNSUPPORTED, B2T_ERR_CUDA, B2T_ERR_VOCAB, B2T_ERR_TOO_LARGE = range(6)
 MODEL_BPE, MODEL_WORDPIECE = 0, 1
 PRETOK_BYTELEVEL, PRETOK_LLAMA3, PRETOK_WHITESPACE, PRETOK_BYTELEVEL_NOREGEX = 0, 1, 2, 3
-WANT_OFFSETS, WANT_WORD_IDS, OFFSETS_BYTES = 1, 2, 4
+WANT_OFFSETS, WANT_WORD_IDS, OFFSETS_BYTES, NO_ADDED_TOKENS, FLAG_ADDED_IDS = 1, 2, 4, 8, 16
+ADDED_SINGLE_WORD, ADDED_LSTRIP, ADDED_RSTRIP, ADDED_NORMALIZED = 1, 2, 4, 8
 
 # every symbol include/b2t.h declares
-SYMBOLS = ["b2t_engine_create", "b2t_engine_destroy", "b2t_encode_batch", "b2t_encode_batch_device", "b2t_encode_batch_device_begin",
+SYMBOLS = ["b2t_engine_create", "b2t_engine_destroy", "b2t_engine_set_added_tokens", "b2t_encode_batch", "b2t_encode_batch_device", "b2t_encode_batch_device_begin",
            "b2t_encode_batch_device_finish", "b2t_pre_tokenize_batch",
            "b2t_encode_batch_dense", "b2t_encode_batch_dense_device", "b2t_result_dense_length", "b2t_result_dense_ids",
            "b2t_result_attention_mask", "b2t_result_row_lengths",
@@ -57,6 +58,7 @@ def lib():
     vp, u32, u64, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
     L.b2t_engine_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(vp)]
     L.b2t_engine_destroy.argtypes = [vp]; L.b2t_engine_destroy.restype = None
+    L.b2t_engine_set_added_tokens.argtypes = [vp, u32, vp, vp, vp, vp]
     L.b2t_encode_batch.argtypes = [vp, vp, vp, u32, u32, ctypes.POINTER(vp)]
     L.b2t_encode_batch_device.argtypes = [vp, vp, u64, vp, u32, u32, vp, ctypes.POINTER(vp)]
     L.b2t_encode_batch_device_begin.argtypes = [vp, vp, u64, vp, u32, u32, vp, ctypes.POINTER(u64)]

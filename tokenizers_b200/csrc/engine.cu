@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/b2t.h"
+#include "added_kernels.cuh"
 #include "dense_kernels.cuh"
 #include "host_tables.h"
 #include "long_kernels.cuh"
@@ -97,6 +98,8 @@ struct Workspace {
   unsigned long long pool_cap = 0;
   DevBuf wcache;                      // per-batch word cache (model_kernels.cuh)
   DevBuf dense_ids, dense_mask, dense_len;  // dense [n_docs, L] rows (dense_kernels.cuh)
+  DevBuf cand0, cand1, hard_bits, inner_bits, added_bits, added_head, added_pool;
+  uint32_t added_cap = 0;  // added-token extraction (added_kernels.cuh)
   DevBuf pfx_bytes, pfx_doc_off, pfx_local, pfx_block, prefix_bits, pfx_total;  // add_prefix_space re-pack (prefix_kernels.cuh)
   int64_t n_eff = 0;                  // bytes of the batch the kernels actually ran on (n + inserted spaces)
   cudaStream_t stream = nullptr;
@@ -109,6 +112,7 @@ struct Workspace {
     tmp_ids.release(); tmp_offsets.release(); tmp_word_ids.release(); tile_count.release(); tile_first.release(); tile_lexcl.release(); tile_bsum.release();
     pfx_bytes.release(); pfx_doc_off.release(); pfx_local.release(); pfx_block.release(); prefix_bits.release(); pfx_total.release();
     dense_ids.release(); dense_mask.release(); dense_len.release();
+    cand0.release(); cand1.release(); hard_bits.release(); inner_bits.release(); added_bits.release(); added_head.release(); added_pool.release();
     wcache.release(); page_long.release(); long_desc.release(); long_desc1.release(); soft_bits.release(); page_soft.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -137,10 +141,15 @@ struct b2t_engine {
   int device = 0;
   int model = 0, pretok = 0, add_prefix_space = 0;
   int sm_count = 148;
+  int wcache_on = 1;         // B2T_WCACHE=0: no word cache, every pre-token is merged (the reference benches cache_capacity(0) too)
   int k1_tiled = 0;          // B2T_K1_TILED=1: the round-1 shared-memory-tiled scan (kept for A/B runs)
   DeviceTables dt;
   int monotone = 0;
   DevBuf d_cls, d_byte_to_id, d_merge, d_word, d_pool, d_edge, d_tok2, d_tri;
+  // added vocabulary (b2t_engine_set_added_tokens)
+  int has_added = 0;
+  AddedTables at;
+  DevBuf d_at_bytes, d_at_off, d_at_id, d_at_flags, d_at_first, d_at_pair, d_cls_rust;
   std::mutex mu;
   Workspace dev_ws;          // b2t_encode_batch_device
   Workspace slot[NSLOT];     // b2t_encode_batch chunks
@@ -201,6 +210,7 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
   e->device = dev; e->model = cfg->model; e->pretok = cfg->pretok; e->add_prefix_space = cfg->add_prefix_space;
   cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (const char* kt = getenv("B2T_K1_TILED")) e->k1_tiled = atoi(kt) != 0;
+  if (const char* wc = getenv("B2T_WCACHE")) e->wcache_on = atoi(wc) != 0;
   if (const char* cb = getenv("B2T_CHUNK_BYTES")) {  // host-path chunk size (tests use tiny chunks to exercise the pipeline)
     long long v = atoll(cb);
     if (v >= 1024 && v < (1ll << 31)) e->chunk_bytes = (size_t)v;
@@ -243,6 +253,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
   cudaDeviceSynchronize();
   e->dev_ws.release();
   for (auto& s : e->slot) s.release();
+  e->d_at_bytes.release(); e->d_at_off.release(); e->d_at_id.release(); e->d_at_flags.release(); e->d_at_first.release(); e->d_at_pair.release(); e->d_cls_rust.release();
   e->d_cls.release(); e->d_byte_to_id.release(); e->d_merge.release(); e->d_word.release(); e->d_pool.release(); e->d_edge.release(); e->d_tok2.release(); e->d_tri.release();
   for (b2t_result* r : e->pool) { r->release_host(); delete r; }
   if (e->rec_ev_made) for (auto& ev : e->rec_ev) cudaEventDestroy(ev);
@@ -256,6 +267,8 @@ struct ctl_block {  // lives in ws.ctl
   uint32_t err;
   unsigned long long total;
   LongCtl lc;
+  uint32_t added_used;   // entries of the added-token list pool handed out
+  uint32_t pad;
 };
 
 static int ensure_long_pool(Workspace& ws, unsigned long long bytes) {
@@ -273,7 +286,7 @@ static int ensure_long_pool(Workspace& ws, unsigned long long bytes) {
 #define B2T_K1_TC 256
 #endif
 template <int KIND>
-static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Workspace& ws, cudaStream_t st) {
+static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Workspace& ws, cudaStream_t st, bool added) {
   constexpr int TC = B2T_K1_TC;
   const int64_t n_chunks = n / CHUNK + 1;
   if (!e->k1_tiled) {
@@ -284,15 +297,26 @@ static void launch_pretok(b2t_engine* e, const uint8_t* d_bytes, int64_t n, Work
     kb = std::min<int64_t>(128, std::max<int64_t>(2, (kb + 1) & ~1ll));
     const int64_t n_warps = (n_kb + kb - 1) / kb;
     const int64_t grid = (n_warps + (B2T_K1S_THREADS / 32) - 1) / (B2T_K1S_THREADS / 32);
+    const AddedBits ab{ws.hard_bits.as<uint32_t>(), ws.inner_bits.as<uint32_t>(), ws.added_bits.as<uint32_t>()};
     if constexpr (KIND == PT_LLAMA3) {
-      pretok_stream_kernel<KIND><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
-                                                                           ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
-                                                                           ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb);
+      if (added)
+        pretok_stream_kernel<KIND, true><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
+                                                                                   ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
+                                                                                   ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb, ab);
+      else
+        pretok_stream_kernel<KIND><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
+                                                                             ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
+                                                                             ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb);
     } else {
       const SwapMasks masks{0x55555555u, 0x33333333u, 0x0F0F0F0Fu};
-      pretok_lean_kernel<KIND><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
-                                                                         ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
-                                                                         ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb, masks);
+      if (added)
+        pretok_lean_kernel<KIND, true><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
+                                                                                 ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
+                                                                                 ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb, masks, ab);
+      else
+        pretok_lean_kernel<KIND><<<(unsigned)grid, B2T_K1S_THREADS, 0, st>>>(d_bytes, n, ws.doc_bits.as<uint32_t>(), e->d_cls.as<uint32_t>(),
+                                                                           ws.start_bits.as<uint32_t>(), ws.drop_bits.as<uint32_t>(),
+                                                                           ws.page_sum.as<uint64_t>(), (int)n_kb, (int)kb, masks);
     }
     return;
   }
@@ -411,6 +435,18 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     if ((flags & B2T_WANT_OFFSETS) && ((rc = ws.offsets.ensure((size_t)(n + 1) * 8)) || (rc = ws.tmp_offsets.ensure((size_t)(n + 1) * 8)))) return rc;
     if ((flags & B2T_WANT_WORD_IDS) && ((rc = ws.word_ids.ensure((size_t)(n + 1) * 4)) || (rc = ws.tmp_word_ids.ensure((size_t)(n + 1) * 4)))) return rc;
   }
+  const int64_t n_chunks_all = n / CHUNK + 1;
+  if (e->has_added && !(flags & B2T_NO_ADDED_TOKENS)) {
+    if (e->add_prefix_space) return fail(B2T_ERR_UNSUPPORTED, "added-token extraction on the device does not combine with add_prefix_space (the prefix goes in front of every piece)");
+    if ((rc = ws.cand0.ensure(n_words * 4)) || (rc = ws.cand1.ensure(n_words * 4)) || (rc = ws.hard_bits.ensure(n_words * 4)) ||
+        (rc = ws.inner_bits.ensure(n_words * 4)) || (rc = ws.added_bits.ensure(n_words * 4)) ||
+        (rc = ws.added_head.ensure(n_pages * 4)) || (rc = ws.added_pool.ensure((size_t)(n / 16 + 4096) * 8)))
+      return rc;
+    ws.added_cap = (uint32_t)(n / 16 + 4096);
+    CU(cudaMemsetAsync(ws.inner_bits.p, 0, n_words * 4, st));
+    CU(cudaMemsetAsync(ws.added_bits.p, 0, n_words * 4, st));
+    CU(cudaMemsetAsync(ws.added_head.p, 0xFF, n_pages * 4, st));
+  }
   CU(cudaMemsetAsync(ws.doc_bits.p, 0, n_words * 4, st));
   CU(cudaMemsetAsync(ws.ctl.p, 0, sizeof(ctl_block), st));
   if (model_pass) CU(cudaMemsetAsync(ws.wcache.p, 0, (size_t)WCACHE_SLOTS * 64, st));
@@ -422,11 +458,22 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   rec(e, st, nullptr);
   doc_mark_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.doc_bits.as<uint32_t>(), ws.page_first_doc.as<uint32_t>());
   rec(e, st, "doc_mark"); e->last_launches++;
+  const bool added = e->has_added && !(flags & B2T_NO_ADDED_TOKENS) && n > 0 && n_docs > 0;
+  if (added) {
+    // added / special tokens (added_vocabulary.rs:430-564): candidates, then one thread per document that holds one
+    ctl_block* ctl = ws.ctl.as<ctl_block>();
+    CU(cudaMemcpyAsync(ws.hard_bits.p, ws.doc_bits.p, n_words * 4, cudaMemcpyDeviceToDevice, st));
+    added_scan_kernel<<<(unsigned)((n_chunks_all + 255) / 256), 256, 0, st>>>(d_bytes, n, e->at, ws.cand0.as<uint32_t>(), ws.cand1.as<uint32_t>());
+    AddedOut ao{ws.hard_bits.as<uint32_t>(), ws.inner_bits.as<uint32_t>(), ws.added_bits.as<uint32_t>(), ws.added_head.as<uint32_t>(),
+                ws.added_pool.as<uint2>(), &ctl->added_used, ws.added_cap, &ctl->err};
+    added_resolve_kernel<<<(n_docs + 127) / 128, 128, 0, st>>>(d_bytes, d_doc_off, n_docs, e->at, ws.cand0.as<uint32_t>(), ws.cand1.as<uint32_t>(), ao);
+    rec(e, st, "added_tokens"); e->last_launches += 2;
+  }
   switch (e->pretok) {
-    case PT_GPT2: launch_pretok<PT_GPT2>(e, d_bytes, n, ws, st); break;
-    case PT_LLAMA3: launch_pretok<PT_LLAMA3>(e, d_bytes, n, ws, st); break;
-    case PT_WHITESPACE: launch_pretok<PT_WHITESPACE>(e, d_bytes, n, ws, st); break;
-    default: launch_pretok<PT_NOREGEX>(e, d_bytes, n, ws, st); break;
+    case PT_GPT2: launch_pretok<PT_GPT2>(e, d_bytes, n, ws, st, added); break;
+    case PT_LLAMA3: launch_pretok<PT_LLAMA3>(e, d_bytes, n, ws, st, added); break;
+    case PT_WHITESPACE: launch_pretok<PT_WHITESPACE>(e, d_bytes, n, ws, st, added); break;
+    default: launch_pretok<PT_NOREGEX>(e, d_bytes, n, ws, st, added); break;
   }
   rec(e, st, "pretok_scan"); e->last_launches++;
   const int64_t n_scan_blocks = (n_pages + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -466,8 +513,10 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     P.err_flag = &ctl->err;
     P.n_tiles = n_pages;
     P.page_long = ws.page_long.as<int32_t>(); P.long_desc = ws.long_desc.as<LongDesc>(); P.long_out = ws.lp_out.as<uint4>();
-    P.wcache = ws.wcache.as<uint4>(); P.wcache_mask = WCACHE_SLOTS - 1;
+    P.wcache = ws.wcache.as<uint4>(); P.wcache_mask = WCACHE_SLOTS - 1; P.wcache_on = e->wcache_on;
     P.prefix_bits = d_prefix_bits;
+    P.added_bits = added ? ws.added_bits.as<uint32_t>() : nullptr; P.added_head = ws.added_head.as<uint32_t>(); P.added_pool = ws.added_pool.as<uint2>();
+    P.flag_added = (flags & B2T_FLAG_ADDED_IDS) ? 1u : 0u;
     P.t = e->dt;
     if (e->model == B2T_MODEL_BPE) model_tile_kernel<MODEL_BPE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
     else model_tile_kernel<MODEL_WORDPIECE><<<(unsigned)n_pages, MODEL_THREADS, 0, st>>>(P);
@@ -500,7 +549,10 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
 // 0 = ok, -1 = the long pool was too small (grow to *want and rerun), else an error status
 static int check_ctl(const Workspace& ws, unsigned long long* want) {
   const ctl_block* c = ws.h_ctl.as<ctl_block>();
-  if ((c->err | c->lc.err) & ERR_INTERNAL) return fail(B2T_ERR_CUDA, "internal error: long pre-token bookkeeping mismatch");
+  if (c->err & ERR_ADDED_UNSUPPORTED)   // (first: a refused span leaves the later kernels with half of the picture)
+    return fail(B2T_ERR_UNSUPPORTED, "added-token extraction: a span over %d bytes, more spans than one per 16 input bytes, or overlapping spans; "
+                "pass B2T_NO_ADDED_TOKENS and split on the host", ADDED_MAX_SPAN);
+  if ((c->err | c->lc.err) & ERR_INTERNAL) return fail(B2T_ERR_CUDA, "internal error: long pre-token / added-token bookkeeping mismatch");
   if (c->lc.err & ERR_POOL_OVERFLOW) { *want = c->lc.pool_used; return -1; }
   return B2T_OK;
 }
@@ -599,6 +651,64 @@ extern "C" int b2t_encode_batch_device_finish(b2t_engine* e, uint32_t* d_ids, ui
   cudaStream_t st = stream ? (cudaStream_t)stream : e->own_stream;
   ws.pending = false;
   return finish_device(e, ws, d_ids, d_offsets, d_word_ids, d_row_ptr, token_base, st);
+}
+
+// ------------------------------------------------------------------------------------------------ added vocabulary
+extern "C" int b2t_engine_set_added_tokens(b2t_engine* e, uint32_t n_tokens, const uint8_t* bytes, const uint32_t* off, const uint32_t* ids,
+                                           const uint8_t* flags) {
+  if (!e) return fail(B2T_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  e->has_added = 0;
+  if (n_tokens == 0) return B2T_OK;
+  if (!bytes || !off || !ids || !flags) return fail(B2T_ERR_INVALID, "b2t_engine_set_added_tokens: null argument");
+  if (e->add_prefix_space) return fail(B2T_ERR_UNSUPPORTED, "added-token extraction on the device does not combine with add_prefix_space");
+  if (e->k1_tiled) return fail(B2T_ERR_UNSUPPORTED, "added-token extraction needs the streaming scan kernels");
+  // two sets (normalized == false first), longest token first inside a set (find_matches: leftmost-longest)
+  std::vector<uint32_t> order[2];
+  for (uint32_t i = 0; i < n_tokens; ++i) {
+    const uint32_t len = off[i + 1] - off[i];
+    if (len == 0) continue;                                  // added_vocabulary.rs:288-291: empty tokens are ignored
+    if (ids[i] >= (1u << 20)) return fail(B2T_ERR_UNSUPPORTED, "added token id %u: ids of 2^20 and above are not supported", ids[i]);
+    order[(flags[i] & B2T_ADDED_NORMALIZED) ? 1 : 0].push_back(i);
+  }
+  std::vector<uint8_t> tb, tf;
+  std::vector<uint32_t> to{0u}, ti, first(16, 0u), pair(2 * 2048, 0u);
+  uint32_t begin[3] = {0, 0, 0};
+  for (int s2 = 0; s2 < 2; ++s2) {
+    std::stable_sort(order[s2].begin(), order[s2].end(), [&](uint32_t a, uint32_t b) { return off[a + 1] - off[a] > off[b + 1] - off[b]; });
+    begin[s2] = (uint32_t)ti.size();
+    for (uint32_t i : order[s2]) {
+      const uint8_t* p = bytes + off[i];
+      const uint32_t len = off[i + 1] - off[i];
+      tb.insert(tb.end(), p, p + len);
+      to.push_back((uint32_t)tb.size()); ti.push_back(ids[i]);
+      tf.push_back((uint8_t)(((flags[i] & B2T_ADDED_SINGLE_WORD) ? ADDED_SINGLE_WORD : 0) | ((flags[i] & B2T_ADDED_LSTRIP) ? ADDED_LSTRIP : 0) |
+                             ((flags[i] & B2T_ADDED_RSTRIP) ? ADDED_RSTRIP : 0)));
+      first[8 * s2 + (p[0] >> 5)] |= 1u << (p[0] & 31);
+      for (uint32_t b1 = 0; b1 < 256; ++b1) {
+        if (len > 1 && b1 != p[1]) continue;
+        const uint32_t two = p[0] | (b1 << 8);
+        pair[2048 * s2 + (two >> 5)] |= 1u << (two & 31);
+      }
+    }
+  }
+  begin[2] = (uint32_t)ti.size();
+  if (ti.empty()) return B2T_OK;
+  std::vector<uint8_t> cls(0x110000);
+  unicode_class_table(1, cls.data());
+  std::vector<uint32_t> packed(0x110000 / 16, 0u);
+  for (uint32_t c = 0; c < 0x110000; ++c) packed[c >> 4] |= (uint32_t)cls[c] << ((c & 15) * 2);
+  int rc;
+  if ((rc = upload(e->d_at_bytes, tb)) || (rc = upload(e->d_at_off, to)) || (rc = upload(e->d_at_id, ti)) || (rc = upload(e->d_at_flags, tf)) ||
+      (rc = upload(e->d_at_first, first)) || (rc = upload(e->d_at_pair, pair)) || (rc = upload(e->d_cls_rust, packed)))
+    return rc;
+  e->at.tok_bytes = e->d_at_bytes.as<uint8_t>(); e->at.tok_off = e->d_at_off.as<uint32_t>(); e->at.tok_id = e->d_at_id.as<uint32_t>();
+  e->at.tok_flags = e->d_at_flags.as<uint8_t>();
+  e->at.set_begin[0] = begin[0]; e->at.set_begin[1] = begin[1]; e->at.set_begin[2] = begin[2];
+  e->at.first_bits = e->d_at_first.as<uint32_t>(); e->at.pair_bits = e->d_at_pair.as<uint32_t>(); e->at.cls_rust = e->d_cls_rust.as<uint32_t>();
+  e->has_added = 1;
+  return B2T_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ dense mode
@@ -820,7 +930,7 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
     if (nb) CUL(cudaMemcpyAsync(ws.bytes.p, bytes + c.b0, nb, cudaMemcpyHostToDevice, ws.stream));
     CUL(cudaMemcpyAsync(ws.doc_off.p, doc_off + c.d0, ((size_t)nd + 1) * 8, cudaMemcpyHostToDevice, ws.stream));
     if (c.b0) rebase_kernel<<<(nd + 1 + 255) / 256, 256, 0, ws.stream>>>(ws.doc_off.as<uint64_t>(), nd + 1, c.b0);
-    rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)nb, ws.doc_off.as<uint64_t>(), nd, flags, ws.stream, !pretok_only, true, dq);
+    rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)nb, ws.doc_off.as<uint64_t>(), nd, pretok_only ? (flags | B2T_NO_ADDED_TOKENS) : flags, ws.stream, !pretok_only, true, dq);
     if (rc) break;
     CUL(cudaEventRecord(ws.done, ws.stream));
     // keep at most NSLOT - 1 chunks un-drained so that result copies overlap the next chunks' kernels
@@ -889,7 +999,7 @@ extern "C" int b2t_pre_tokenize_batch(b2t_engine* e, const uint8_t* bytes, const
   if ((rc = slot_init(ws)) || (rc = ws.bytes.ensure(n + 64)) || (rc = ws.doc_off.ensure(((size_t)n_docs + 1) * 8))) return rc;
   if (n) CU(cudaMemcpyAsync(ws.bytes.p, bytes, n, cudaMemcpyHostToDevice, ws.stream));
   CU(cudaMemcpyAsync(ws.doc_off.p, doc_off, ((size_t)n_docs + 1) * 8, cudaMemcpyHostToDevice, ws.stream));
-  if ((rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)n, ws.doc_off.as<uint64_t>(), n_docs, 0, ws.stream, false))) return rc;
+  if ((rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)n, ws.doc_off.as<uint64_t>(), n_docs, B2T_NO_ADDED_TOKENS, ws.stream, false))) return rc;  // (a PreTokenizer knows no added tokens)
   const uint64_t n_eff = (uint64_t)ws.n_eff;
   const size_t n_words = n_eff / 32 + 2;
   std::vector<uint32_t> sb(n_words), db(n_words, 0u);

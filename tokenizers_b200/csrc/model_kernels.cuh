@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "b2t_tables.h"
+#include "added_kernels.cuh"
 #include "long_kernels.cuh"
 #include "pretok_logic.cuh"
 
@@ -51,9 +52,12 @@ struct ModelParams {
   // long BPE pre-tokens resolved by the pre-pass (long_kernels.cuh)
   const int32_t* page_long; const LongDesc* long_desc; const uint4* long_out;
   // per-batch word cache (cleared at the start of every batch): pre-token bytes -> its token list
-  uint4* wcache; uint32_t wcache_mask;
+  uint4* wcache; uint32_t wcache_mask; int wcache_on;   // wcache_on = 0: every pre-token is merged (the reference's cache_capacity(0))
   // ByteLevel add_prefix_space: bit p set <=> byte p of the (re-packed) batch is an inserted prefix space (else NULL)
   const uint32_t* prefix_bits;
+  // added-token extraction (added_kernels.cuh): bit p <=> an added token's span starts at byte p, its id is in the list of
+  // the page; NULL when the batch did not go through the extraction.  flag_added: mark those tokens with bit 31 of the id.
+  const uint32_t* added_bits; const uint32_t* added_head; const uint2* added_pool; uint32_t flag_added;
   DeviceTables t;
 };
 
@@ -133,8 +137,10 @@ __device__ __forceinline__ void wc_make_key(const uint8_t* s_byte, int s, int le
                    __funnelshift_r(a3, a4, sh), __funnelshift_r(a4, a5, sh), __funnelshift_r(a5, a6, sh)};
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    const int valid = len - 4 * i;  // bytes of word i that belong to the pre-token
-    const uint32_t m = valid >= 4 ? 0xFFFFFFFFu : (valid <= 0 ? 0u : ((1u << (8 * valid)) - 1u));
+    // bytes of word i that belong to the pre-token: v = clamp(len - 4 i, 0, 4); mask = the low 8 v bits, as one clamped
+    // funnel shift (a shift count above 32 counts as 32 and yields 0; v <= 0 gives a count >= 32)
+    const int v = min(len - 4 * i, 4);
+    const uint32_t m = __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)(32 - 8 * v));
     key.k[i] = k[i] & m;
   }
   uint32_t a = key.k[0] ^ (key.k[2] * 0x9E3779B1u) ^ (key.k[4] * 0x85EBCA77u);
@@ -146,30 +152,51 @@ __device__ __forceinline__ void wc_make_key(const uint8_t* s_byte, int s, int le
   if (key.fp == 0) key.fp = 1;
 }
 
+// Memory-model note.  A slot is written once per batch (the table is zeroed, stream-ordered, before the kernel) and never
+// changes after that, readers take no lock and no fence -- an acquire load costs an L1 invalidation (CCTL.IVALL) per
+// probe on this architecture, and the merge-table probes live in L1.  Instead every 32-bit word of a written slot is
+// NON-ZERO by construction (key words and ids are stored complemented: a key word of 0xFFFFFFFF cannot occur in UTF-8,
+// ids are < 2^20; the two length words carry a marker bit), all accesses are strong (.relaxed.gpu, single-copy atomic
+// per 32-bit word), and a reader accepts a slot only if the words it uses are non-zero and the whole key matches.  A word
+// that is not yet visible reads as zero, which is a miss: the pre-token is merged, the result is the same.
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(uint4* p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+constexpr uint32_t WC_LEN_MARK = 0x80000000u;   // bit 31 of the second length word: always set in a written slot
+
 // Returns true on a hit (tokens written to s_tok).
 __device__ __forceinline__ bool wc_lookup(uint4* cache, uint32_t mask, const WordKey& key, int s, uint32_t* s_tok) {
   uint32_t slot = key.slot & mask;
 #pragma unroll 1
   for (int pr = 0; pr < WC_PROBES; ++pr, slot = (slot + 1) & mask) {
     const uint4* q = cache + (size_t)slot * 4;
-    const uint4 q0 = __ldcg(q);
+    const uint4 q0 = ld_relaxed_v4(q);
     const unsigned long long tag = ((unsigned long long)q0.y << 32) | q0.x;
     if (tag == 0ull) return false;
     if (tag != (B2T_WC_READY | key.fp)) {
       if (tag == (B2T_WC_BUSY | key.fp)) return false;  // someone is publishing this very word: just compute it
       continue;
     }
-    if (q0.z != key.k[0] || q0.w != key.k[1]) continue;
-    const uint4 q1 = __ldcg(q + 1);
-    if (q1.x != key.k[2] || q1.y != key.k[3] || q1.z != key.k[4] || q1.w != key.k[5]) continue;
-    const uint4 q2 = __ldcg(q + 2), q3 = __ldcg(q + 3);
+    if (q0.z != ~key.k[0] || q0.w != ~key.k[1]) continue;
+    const uint4 q1 = ld_relaxed_v4(q + 1);
+    if (q1.x != ~key.k[2] || q1.y != ~key.k[3] || q1.z != ~key.k[4] || q1.w != ~key.k[5]) continue;
+    const uint4 q2 = ld_relaxed_v4(q + 2), q3 = ld_relaxed_v4(q + 3);
     const int ntok = (int)(q2.x & 0xFFu);
-    const uint32_t ids[6] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+    const uint32_t cids[6] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};   // complemented ids
     const uint32_t lens[6] = {(q2.x >> 8) & 0xFFu, (q2.x >> 16) & 0xFFu, q2.x >> 24, q2.y & 0xFFu, (q2.y >> 8) & 0xFFu, (q2.y >> 16) & 0xFFu};
+    bool ok = ntok != 0 && (q2.y & WC_LEN_MARK);
+#pragma unroll
+    for (int t = 0; t < WC_MAX_TOK; ++t) ok = ok && (t >= ntok || cids[t] != 0u);
+    if (!ok) return false;   // part of the slot is not visible yet: a miss
     int pos = s;
 #pragma unroll
     for (int t = 0; t < WC_MAX_TOK; ++t)
-      if (t < ntok) { s_tok[pos] = tok_pack(ids[t], (int)lens[t]); pos += (int)lens[t]; }
+      if (t < ntok) { s_tok[pos] = tok_pack(~cids[t], (int)lens[t]); pos += (int)lens[t]; }
     return true;
   }
   return false;
@@ -195,11 +222,12 @@ __device__ __forceinline__ void wc_publish(uint4* cache, uint32_t mask, const Wo
     unsigned long long tag = *reinterpret_cast<volatile unsigned long long*>(tagp);
     if (tag == 0ull) tag = atomicCAS(tagp, 0ull, B2T_WC_BUSY | key.fp);
     if (tag == 0ull) {  // the slot is ours
-      reinterpret_cast<uint2*>(q)[1] = make_uint2(key.k[0], key.k[1]);
-      q[1] = make_uint4(key.k[2], key.k[3], key.k[4], key.k[5]);
-      q[2] = make_uint4((uint32_t)nt | (lens[0] << 8) | (lens[1] << 16) | (lens[2] << 24), lens[3] | (lens[4] << 8) | (lens[5] << 16), ids[0], ids[1]);
-      q[3] = make_uint4(ids[2], ids[3], ids[4], ids[5]);
-      __threadfence();
+      uint32_t* kw = reinterpret_cast<uint32_t*>(q);
+      asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(kw + 2), "r"(~key.k[0]), "r"(~key.k[1]) : "memory");
+      st_relaxed_v4(q + 1, make_uint4(~key.k[2], ~key.k[3], ~key.k[4], ~key.k[5]));
+      st_relaxed_v4(q + 2, make_uint4((uint32_t)nt | (lens[0] << 8) | (lens[1] << 16) | (lens[2] << 24), lens[3] | (lens[4] << 8) | (lens[5] << 16) | WC_LEN_MARK, ~ids[0], ~ids[1]));
+      st_relaxed_v4(q + 3, make_uint4(~ids[2], ~ids[3], ~ids[4], ~ids[5]));
+      __threadfence();                                  // not needed for correctness (see above); it makes the slot usable sooner
       atomicExch(tagp, B2T_WC_READY | key.fp);
       return;
     }
@@ -314,7 +342,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   static_assert(NW <= 96, "warp_prefix_words handles <= 96 words");
   __shared__ __align__(16) uint8_t s_byte[SPAN];
   __shared__ __align__(16) uint32_t s_tok[SPAN];   // tok_pack(id, length) of the token that starts at each position
-  __shared__ uint32_t s_startb[NW + 1], s_keptb[NW + 1], s_leadb[NW + 1], s_tokb[NW + 1], s_dsb[TW + 1];
+  __shared__ uint32_t s_startb[NW + 1], s_keptb[NW + 1], s_leadb[NW + 1], s_tokb[NW + 1], s_dsb[TW + 1], s_addedb[TW + 1];
   __shared__ uint16_t s_apref[NW + 1], s_spref[NW + 1], s_lpref[NW + 1], s_tpref[NW + 1];
   __shared__ int16_t s_dlast[TW + 1];
   __shared__ uint16_t s_pt[TILE + 2];
@@ -336,7 +364,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   constexpr int NWARPS = MODEL_THREADS / 32;
   if (tid == 0) {
     s_tile = (int)blockIdx.x;
-    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0; s_nmiss_hi = 0; s_anysoft = 0;
+    s_next = 0; s_nmq = 0; s_long = 0; s_long_chars = 0; s_nl = 0; s_nmiss = 0; s_nmiss_hi = 0; s_anysoft = 0; s_lcum[0] = 0;
   }
   __syncthreads();
   const int64_t t = s_tile;
@@ -366,6 +394,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
     s_startb[w] = sb | sf;   // where a unit of merging starts: splits of the pre-tokenizer + exact cuts of long ones
     s_keptb[w] = sb & ~db;   // splits of the pre-tokenizer that the reference keeps (word ids)
     if (w <= TW) s_dsb[w] = (w < TW && gw < n_chunks) ? __ldg(P.doc_bits + gw) : 0u;
+    if (w <= TW) s_addedb[w] = (P.added_bits && w < TW && gw < n_chunks) ? __ldg(P.added_bits + gw) : 0u;
   }
   __syncthreads();
   // lead bits (16 bytes per thread: continuation-byte flags by SWAR, two threads make one bitmap word) + symbol init
@@ -472,9 +501,10 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   const int Eproc = Pn ? ((MODEL == MODEL_WORDPIECE && is_long) ? (int)s_pt[Pn - 1] : Elast) : 0;
   const int Pproc = (MODEL == MODEL_WORDPIECE && is_long) ? Pn - 1 : Pn;
   if (MODEL == MODEL_BPE) {
+    int any_long = 0;
     for (int k = tid; k < Pn; k += MODEL_THREADS)
-      if ((int)s_pt[k + 1] - (int)s_pt[k] > LONG_PRETOK_MIN) { int i = atomicAdd(&s_nl, 1); if (i < MAX_LONG_PER_PAGE) s_lk[i] = (uint16_t)k; }
-    __syncthreads();
+      if ((int)s_pt[k + 1] - (int)s_pt[k] > LONG_PRETOK_MIN) { int i = atomicAdd(&s_nl, 1); if (i < MAX_LONG_PER_PAGE) s_lk[i] = (uint16_t)k; any_long = 1; }
+    if (__syncthreads_or(any_long)) {   // (almost every page: no long pre-token, one barrier instead of three)
     if (tid == 0) {
       int nl = s_nl;
       if (nl > MAX_LONG_PER_PAGE) { nl = MAX_LONG_PER_PAGE; atomicOr(P.err_flag, ERR_INTERNAL); }
@@ -497,6 +527,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
       for (int pos = ls + tid; pos < le; pos += MODEL_THREADS) s_tok[pos] = 0u;
     }
     __syncthreads();
+    }
   }
   const int n_longs = MODEL == MODEL_BPE ? s_nl : 0;
   // [s, e) is a piece of a cut pre-token (not a whole split of the pre-tokenizer): with ignore_merges the whole-word rule
@@ -515,6 +546,17 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
     return c;
   };
 
+  // the pre-token that starts at s (inside the page) is an added token's span: its id comes from the page's list
+  auto added_at = [&](int s) -> bool { return P.added_bits != nullptr && ((s_addedb[s >> 5] >> (s & 31)) & 1u); };
+  auto added_id = [&](int s) -> uint32_t {
+    for (uint32_t i = __ldg(P.added_head + t); i != ADDED_NIL;) {
+      const uint2 v = __ldg(P.added_pool + i);
+      if ((int)(v.x & (uint32_t)(PAGE - 1)) == s) return v.x >> 11;
+      i = v.y;
+    }
+    atomicOr(P.err_flag, ERR_INTERNAL);
+    return 0u;
+  };
   if (MODEL == MODEL_BPE) {
     // -------------------------------------------------------------- P3: word cache, one pre-token per thread
     // (static assignment: a lookup costs the same for every lane, so the warp stays converged)
@@ -523,11 +565,12 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
       int kind = 0;  // 0 = resolved / nothing to do, 1 = miss (<= 32 bytes), 2 = medium (33..256 bytes)
       if (k < Pproc) {
         const int s = s_pt[k], e = s_pt[k + 1], len = e - s;
-        if (len > LONG_PRETOK_MIN) kind = 0;  // resolved by the pre-pass
+        if (added_at(s)) { s_tok[s] = tok_pack(added_id(s), len); kind = 0; }   // an added token: one token, whatever the model says
+        else if (len > LONG_PRETOK_MIN) kind = 0;  // resolved by the pre-pass
         else if (len > THREAD_PATH_MAX) kind = 2;
         else {
           bool hit = false;
-          if (len <= WC_MAX_BYTES && !(P.t.ignore_merges && is_piece(s, e))) {
+          if (P.wcache_on && len <= WC_MAX_BYTES && !(P.t.ignore_merges && is_piece(s, e))) {
             WordKey key;
             wc_make_key(s_byte, s, len, key);
             hit = wc_lookup(P.wcache, P.wcache_mask, key, s, s_tok);
@@ -576,15 +619,19 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
           __syncwarp();
           // long numbers rarely repeat: publishing them only fills the table (measured: -5 % kernel time without them)
           const bool numeric = active0 && (e - s) >= 5 && (unsigned)(s_byte[s + 1] - '0') < 10u && (unsigned)(s_byte[e - 1] - '0') < 10u;
-          if (active0 && gl == 0 && e - s <= WC_MAX_BYTES && !numeric && !(P.t.ignore_merges && is_piece(s, e))) {
+          if (P.wcache_on && active0 && gl == 0 && e - s <= WC_MAX_BYTES && !numeric && !(P.t.ignore_merges && is_piece(s, e))) {
             WordKey key;
             wc_make_key(s_byte, s, e - s, key);
             wc_publish(P.wcache, P.wcache_mask, key, s, e, s_tok);
           }
         }
       };
-      // longer pre-tokens first (they take the most rounds), then the short ones with fewer lanes / positions each
+      // longer pre-tokens (17..32 bytes: rare, many rounds) by lane groups
       run_misses(IntTag<8>{}, IntTag<THREAD_PATH_MAX / 8>{}, n_longer, true);
+      // short ones (<= 16 bytes: nearly all misses) with fewer positions per lane.  (One THREAD per short miss, 32 words per
+      // warp with the pair ranks in shared memory, needs 4-5x fewer instructions per word but was measured SLOWER, with the
+      // cache on (+5 %) and off (+39 %): the page waits for its longest chain of dependent probes, and a lane group's chain
+      // is the shortest -- profiles/k2_experiments_r02.md.)
       run_misses(IntTag<P4_SHORT_G>{}, IntTag<(P4_SPLIT_BYTES + P4_SHORT_G - 1) / P4_SHORT_G>{}, n_short, false);
     }
     // -------------------------------------------------------------- P4b: one warp per longer pre-token (33..256 bytes)
@@ -609,9 +656,10 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
       bool miss = false;
       if (k < Pproc) {
         const int s = s_pt[k], e = s_pt[k + 1], len = e - s;
-        if ((s_keptb[s >> 5] >> (s & 31)) & 1u) {  // not removed whitespace
+        if (added_at(s)) s_tok[s] = tok_pack(added_id(s), len);
+        else if ((s_keptb[s >> 5] >> (s & 31)) & 1u) {  // not removed whitespace
           bool hit = false;
-          if (len <= WC_MAX_BYTES) {
+          if (P.wcache_on && len <= WC_MAX_BYTES) {
             WordKey key;
             wc_make_key(s_byte, s, len, key);
             hit = wc_lookup(P.wcache, P.wcache_mask, key, s, s_tok);
@@ -664,7 +712,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
         for (int p = s; p < e; ++p) s_tok[p] = 0u;
         s_tok[s] = tok_pack(P.t.unk_id, len);
       }
-      if (len <= WC_MAX_BYTES) {
+      if (P.wcache_on && len <= WC_MAX_BYTES) {
         WordKey key;
         wc_make_key(s_byte, s, len, key);
         wc_publish(P.wcache, P.wcache_mask, key, s, e, s_tok);
@@ -734,7 +782,7 @@ __global__ void __launch_bounds__(MODEL_THREADS, B2T_MINBLOCKS) model_tile_kerne
   };
   auto emit = [&](unsigned long long out, uint32_t id, int ts, int64_t tend_abs, int end_chars_in_page, bool end_known) {
     // ts: token start (page-relative); tend_abs: absolute end byte; end_chars_in_page: lc_incl(e-1) if end_known
-    P.ids[out] = id;
+    P.ids[out] = (P.flag_added && ts < TILE && added_at(ts)) ? (id | 0x80000000u) : id;
     const int D = doc_base(ts);
     if (want_off) {
       uint32_t o0, o1;

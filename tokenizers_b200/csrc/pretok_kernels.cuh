@@ -462,11 +462,15 @@ __device__ __forceinline__ void load_tail_words(const uint8_t* __restrict__ byte
 // (iteration j - 1): the one bit that looks forwards (finalize_gpt2), the store and the page summary.  Between the two
 // a lane keeps six words, so the kernel runs at 64 registers.  There is one copy of the code: the loop starts one
 // iteration before the warp's range (its output is discarded, only the carries are kept).
-template <int KIND>
+// ADDED: the batch went through the added-token extraction (added_kernels.cuh): the regex sees hard_bits (document starts +
+// span boundaries) where it otherwise sees doc_bits, splits inside a span are cleared (inner_bits), Whitespace never drops a
+// span's bytes (added_bits | inner_bits).  The page summaries keep counting from the DOCUMENT starts.
+struct AddedBits { const uint32_t* hard; const uint32_t* inner; const uint32_t* added; };
+template <int KIND, bool ADDED = false>
 __global__ void __launch_bounds__(B2T_K1S_THREADS, B2T_K1S_MINBLOCKS)
 pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_t* __restrict__ doc_bits,
                    const uint32_t* __restrict__ cls_tbl, uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
-                   uint64_t* __restrict__ page_sum, int n_kb, int kb_per_warp, SwapMasks masks) {
+                   uint64_t* __restrict__ page_sum, int n_kb, int kb_per_warp, SwapMasks masks, AddedBits ab = AddedBits{nullptr, nullptr, nullptr}) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -495,6 +499,7 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
   uint32_t kL = 0u, kN = 0u, kS = 0u, kSP = 0u, k_ov = 0u;
   // stage A results of iteration j - 1, waiting for stage B
   uint32_t p_start = 0u, p_drop = 0u, p_lead = 0u, p_head = 0u, p_ds = 0u, p_dsn = 0u, p_s31 = 0u;
+  uint32_t p_inner = 0u, p_doc = 0u;              // ADDED only
   uint32_t h_tot = 0u, h_aft = 0u, h_flag = 0u;   // first half of the current page
 
   uint32_t w[8];
@@ -530,9 +535,16 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
     } else { pt.N = 0u; pt.SP = 0u; }
     if (m.cont & 1u) spill_in(m, pt.L, pt.N, pt.S);
     kL = m.L; kN = m.N; kS = m.S; kSP = m.SP;
+    // ds / ds_next: where a new string starts as far as the regex is concerned (ADDED: hard_bits)
+    const uint32_t* __restrict__ rbits = ADDED ? ab.hard : doc_bits;
     uint32_t ds, ds_next;
-    if (interior) { ds = __ldg(doc_bits + c); ds_next = __ldg(doc_bits + c + 1); }
-    else { ds = (j >= 0 && c < n_chunks) ? __ldg(doc_bits + c) : 0u; ds_next = (j >= 0 && c + 1 < n_chunks) ? __ldg(doc_bits + c + 1) : 0u; }
+    if (interior) { ds = __ldg(rbits + c); ds_next = __ldg(rbits + c + 1); }
+    else { ds = (j >= 0 && c < n_chunks) ? __ldg(rbits + c) : 0u; ds_next = (j >= 0 && c + 1 < n_chunks) ? __ldg(rbits + c + 1) : 0u; }
+    uint32_t inner = 0u, keep = 0u, docw = ds;
+    if (ADDED && j >= 0 && c < n_chunks) {
+      inner = __ldg(ab.inner + c); docw = __ldg(doc_bits + c);
+      if (KIND == PT_WHITESPACE) keep = inner | __ldg(ab.added + c);
+    }
     uint32_t start, drop = 0u;
     if (KIND == PT_GPT2) {
       const FastOut o = fast_gpt2(m, pt, 1u, 1u, ds, ds_next, base, at4);
@@ -541,7 +553,7 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
       start = apply_overflow(o.start, m.lead, in);
     } else if (KIND == PT_WHITESPACE) {
       const FastOut o = fast_whitespace(m, pt, ds);
-      start = o.start; drop = o.drop;
+      start = o.start; drop = o.drop & ~keep;
     } else {
       start = ds & m.lead;
     }
@@ -555,6 +567,8 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
         const uint32_t xh = __shfl_sync(FULL, lane == 0 ? head : p_head, down);
         fin = finalize_gpt2(fin, p_lead, p_s31, xh & 15u, xh >> 4, p_dsn);
       }
+      if (ADDED) fin &= ~p_inner;      // an added token's span is one pre-token
+      const uint32_t p_docw = ADDED ? p_doc : p_ds;
       if (pc < n_chunks) {
         start_bits[pc] = fin;
         if (KIND == PT_WHITESPACE) drop_bits[pc] = p_drop;
@@ -562,7 +576,7 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
       // ---- page summary (segmented: counts restart at the last doc start of the page); one iteration is half a page
       const uint32_t kept = fin & ~p_drop;
       const uint32_t tot = (uint32_t)__popc(p_lead) | ((uint32_t)__popc(kept) << 16);
-      const unsigned dsm = __ballot_sync(FULL, p_ds != 0u);
+      const unsigned dsm = __ballot_sync(FULL, p_docw != 0u);
       const uint32_t wtot = __reduce_add_sync(FULL, tot);
       uint32_t waft = 0u;
       if (dsm) {
@@ -570,7 +584,7 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
         uint32_t mine = 0u;
         if (lane > last) mine = tot;
         else if (lane == last) {
-          const uint32_t from = ~bits_below(31 - __clz((int)p_ds));
+          const uint32_t from = ~bits_below(31 - __clz((int)p_docw));
           mine = (uint32_t)__popc(p_lead & from) | ((uint32_t)__popc(kept & from) << 16);
         }
         waft = __reduce_add_sync(FULL, mine);
@@ -586,16 +600,17 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
       }
     }
     p_start = start; p_drop = drop; p_lead = m.lead; p_head = head; p_ds = ds; p_dsn = ds_next; p_s31 = m.S >> 31;
+    if (ADDED) { p_inner = inner; p_doc = docw; }
   }
 }
 
-template <int KIND>
 // ---------------------------------------------------------------------------------------------- window form (Llama-3)
 // Same streaming structure with the 64-bit window algebra of pretok_logic.cuh (two iterations per trip).
+template <int KIND, bool ADDED = false>
 __global__ void __launch_bounds__(B2T_K1S_THREADS, B2T_K1W_MINBLOCKS)
 pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_t* __restrict__ doc_bits,
                      const uint32_t* __restrict__ cls_tbl, uint32_t* __restrict__ start_bits, uint32_t* __restrict__ drop_bits,
-                     uint64_t* __restrict__ page_sum, int n_kb, int kb_per_warp) {
+                     uint64_t* __restrict__ page_sum, int n_kb, int kb_per_warp, AddedBits ab = AddedBits{nullptr, nullptr, nullptr}) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -657,8 +672,10 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
     load(it + 3 <= it_hi ? it + 3 : -1, w);      // prefetch (the KB after the range is classified too, for its first bytes)
 
     const uint32_t c = (uint32_t)it * 32u + lane, base = c * CHUNK;
-    const uint32_t ds = c < n_chunks ? __ldg(doc_bits + c) : 0u;
-    const uint32_t ds_next = c + 1 < n_chunks ? __ldg(doc_bits + c + 1) : 0u;
+    const uint32_t* __restrict__ rbits = ADDED ? ab.hard : doc_bits;   // string starts as the regex sees them
+    const uint32_t ds = c < n_chunks ? __ldg(rbits + c) : 0u;
+    const uint32_t ds_next = c + 1 < n_chunks ? __ldg(rbits + c + 1) : 0u;
+    const uint32_t docw = ADDED ? (c < n_chunks ? __ldg(doc_bits + c) : 0u) : ds;
     uint32_t start, drop = 0u;
     {
       // window algebra of pretok_logic.cuh on [16 B of the previous chunk | mine | 16 B of the next chunk]
@@ -668,14 +685,15 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
       wd.N = win(pcur.N, cur.N, nextw(cur.N, nxt.N)); wd.S = win(pcur.S, cur.S, nextw(cur.S, nxt.S));
       wd.SP = win(pcur.SP, cur.SP, nextw(cur.SP, nxt.SP)); wd.NL = win(pcur.NL, cur.NL, nextw(cur.NL, nxt.NL));
       wd.AP = win(pcur.AP, cur.AP, nextw(cur.AP, nxt.AP));
-      const uint32_t ds_prev = (c >= 1u && c - 1u < n_chunks) ? __ldg(doc_bits + c - 1) : 0u;
+      const uint32_t ds_prev = (c >= 1u && c - 1u < n_chunks) ? __ldg(rbits + c - 1) : 0u;
       wd.DS = win(ds_prev, ds, ds_next);
       LlamaCarry cy; cy.n_count_before_window = 0; cy.zone_before_window = false; cy.tail_after_window = false;
       const ByteAtGlobal at64{bytes, n64};
       const BoundaryOut r = boundaries_llama3(wd, (int64_t)base - 16, at64, cy);
       start = r.start;
-      if (r.slow) start = exact_chunk_start<KIND>(bytes, n64, c, cls_tbl, doc_bits);
+      if (r.slow) start = exact_chunk_start<KIND>(bytes, n64, c, cls_tbl, rbits);
     }
+    if (ADDED && c < n_chunks) start &= ~__ldg(ab.inner + c);   // an added token's span is one pre-token
     if (c < n_chunks) {
       start_bits[c] = start;
       if (KIND == PT_WHITESPACE) drop_bits[c] = drop;
@@ -686,7 +704,7 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
     // ---- page summary (segmented: counts restart at the last doc start of the page); this iteration is half a page
     const uint32_t kept = start & ~drop;
     const uint32_t tot = (uint32_t)__popc(cur.lead) | ((uint32_t)__popc(kept) << 16);
-    const unsigned dsm = __ballot_sync(FULL, ds != 0u);
+    const unsigned dsm = __ballot_sync(FULL, docw != 0u);
     const uint32_t wtot = __reduce_add_sync(FULL, tot);
     uint32_t waft = 0u;
     if (dsm) {
@@ -694,7 +712,7 @@ pretok_stream_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint3
       uint32_t mine = 0u;
       if (lane > last) mine = tot;
       else if (lane == last) {
-        const uint32_t from = ~bits_below(31 - __clz((int)ds));
+        const uint32_t from = ~bits_below(31 - __clz((int)docw));
         mine = (uint32_t)__popc(cur.lead & from) | ((uint32_t)__popc(kept & from) << 16);
       }
       waft = __reduce_add_sync(FULL, mine);

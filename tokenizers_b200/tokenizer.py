@@ -7,7 +7,7 @@ Mirrors `tokenizers.Tokenizer` (bindings/python/src/tokenizer.rs:510-1461 in the
 hot path raise `UnsupportedConfig` (there is no CPU fallback).  The two host steps the reference runs around the path are
 mirrored here: added-token extraction before it (`added.py`) and the special-token template after it (`post_process`).
 """
-import ctypes, json
+import ctypes, os, json
 import numpy as np
 from . import _lib, added, pairs
 from ._lib import B2TError
@@ -434,6 +434,7 @@ class Tokenizer:
         self._decoder = cfg["decoder"]
         self._trim = None
         self._added = None
+        self._dev_added, self._added_strip = False, False
         if any(t.get("content") for t in cfg["added_tokens"]):
             self._added = added.AddedVocabulary(cfg["added_tokens"], self._rust_class_table())
 
@@ -467,6 +468,29 @@ class Tokenizer:
             raise UnsupportedConfig(L.b2t_last_error().decode())
         _lib.check(rc)
         self._h = h
+        self._register_added()
+
+    def _register_added(self):
+        """Hand the added vocabulary to the engine (b2t_engine_set_added_tokens): the extraction then runs on the device.
+        Configurations the device path refuses (add_prefix_space) keep the host extraction of added.py in front of the engine."""
+        self._dev_added = False
+        if getattr(self, "_h", None) is None:
+            return
+        L = _lib.lib()
+        toks = [] if self._added is None else list(self._added.by_content.values())
+        if not toks:
+            L.b2t_engine_set_added_tokens(self._h, 0, None, None, None, None)
+            return
+        tb, to = _pack([t.content for t in toks])
+        ti = np.asarray([t.id for t in toks], dtype=np.uint32)
+        tf = np.asarray([(_lib.ADDED_SINGLE_WORD if t.single_word else 0) | (_lib.ADDED_LSTRIP if t.lstrip else 0) |
+                         (_lib.ADDED_RSTRIP if t.rstrip else 0) | (_lib.ADDED_NORMALIZED if t.normalized else 0) for t in toks], dtype=np.uint8)
+        rc = L.b2t_engine_set_added_tokens(self._h, len(toks), tb.ctypes.data, to.ctypes.data, ti.ctypes.data, tf.ctypes.data)
+        if rc == _lib.B2T_ERR_UNSUPPORTED:
+            return
+        _lib.check(rc)
+        self._dev_added = os.environ.get("B2T_HOST_ADDED", "0") != "1"   # B2T_HOST_ADDED=1: keep the host extraction (A/B, tests)
+        self._added_strip = any(t.lstrip or t.rstrip for t in toks)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -540,6 +564,7 @@ class Tokenizer:
             added_n += 1
         self._added = added.AddedVocabulary(entries, self._rust_class_table()) if entries else None
         self._trim = None
+        self._register_added()
         return added_n
 
     def add_tokens(self, tokens):
@@ -609,14 +634,45 @@ class Tokenizer:
 
     def _encode_core(self, data, doc_off, flags, raw, extract_added_tokens):
         """added-token extraction -> engine -> stitching.  -> (BatchEncoding of the plain sequences, trim counts or None)"""
-        parts, cut, row_off, added_at = None, False, doc_off, []
-        if extract_added_tokens and self._added is not None:
-            row_off, parts, cut = added.split_batch(self._added, raw, doc_off)
-        ids, offs, wid, rp = self._engine_rows(data, row_off, flags)
-        if cut:
-            ids, offs, wid, rp, added_at = added.stitch_rows(raw, doc_off, parts, ids, offs, wid, rp, bool(flags & _lib.OFFSETS_BYTES))
-        trim = None
+        parts, cut, row_off, added_at, done = None, False, doc_off, [], False
         tp = self._template
+        if extract_added_tokens and self._added is not None and self._dev_added:
+            # the extraction runs on the device; added tokens come back marked (bit 31 of the id).  Their matched spans are
+            # read off the offsets where the host needs the text (lstrip / rstrip tokens, offset trimming)
+            want_trim = tp is not None and tp["trim"] is not None and bool(flags & _lib.WANT_OFFSETS)
+            need_text = self._added_strip or want_trim
+            fl = flags | _lib.FLAG_ADDED_IDS | (_lib.WANT_OFFSETS if need_text else 0)
+            try:
+                ids, offs, wid, rp = self._engine_rows(data, doc_off, fl)
+                done = True
+            except _lib.B2TError as ex:
+                if ex.code != _lib.B2T_ERR_UNSUPPORTED:
+                    raise                     # (spans outside the device limits: split on the host below)
+            if done:
+                marked = np.flatnonzero(ids >> 31)
+                ids &= np.uint32(0x7FFFFFFF)
+                if need_text and marked.size:
+                    docs_of = np.searchsorted(rp, marked, side="right") - 1
+                    byte_off = bool(flags & _lib.OFFSETS_BYTES)
+                    for i, d in zip(marked.tolist(), docs_of.tolist()):
+                        a0, b0 = int(doc_off[d]), int(doc_off[d + 1])
+                        o0, o1 = int(offs[i, 0]), int(offs[i, 1])
+                        if byte_off:
+                            a, b = a0 + o0, a0 + o1
+                        else:   # characters -> bytes inside the document
+                            lead_pos = np.flatnonzero((data[a0:b0] & 0xC0) != 0x80)
+                            a = a0 + (int(lead_pos[o0]) if o0 < lead_pos.size else b0 - a0)
+                            b = a0 + (int(lead_pos[o1]) if o1 < lead_pos.size else b0 - a0)
+                        added_at.append((i, a, b))
+                if not (flags & _lib.WANT_OFFSETS):
+                    offs = None
+        if not done:
+            if extract_added_tokens and self._added is not None:
+                row_off, parts, cut = added.split_batch(self._added, raw, doc_off)
+            ids, offs, wid, rp = self._engine_rows(data, row_off, flags | (_lib.NO_ADDED_TOKENS if self._added is not None else 0))
+            if cut:
+                ids, offs, wid, rp, added_at = added.stitch_rows(raw, doc_off, parts, ids, offs, wid, rp, bool(flags & _lib.OFFSETS_BYTES))
+        trim = None
         if tp is not None and tp["trim"] is not None and offs is not None:
             lead, trail = self._trim_tables()
             ld, tr = lead[ids], trail[ids]
@@ -696,8 +752,8 @@ class Tokenizer:
             data = np.frombuffer(b"".join(bs), dtype=np.uint8)
         data = np.ascontiguousarray(data, dtype=np.uint8)
         doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
-        if self._added is not None and added.split_batch(self._added, data, doc_off)[2]:
-            raise UnsupportedConfig("the batch contains added tokens: dense mode has no added-token extraction yet, use encode_batch")
+        if self._added is not None and not self._dev_added and added.split_batch(self._added, data, doc_off)[2]:
+            raise UnsupportedConfig("the batch contains added tokens and this configuration extracts them on the host: use encode_batch")
         sp, keep = self.dense_spec(add_special_tokens, want_mask)
         n = len(doc_off) - 1
         L = _lib.lib()
