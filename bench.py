@@ -191,13 +191,16 @@ class DevArr:  # zero-copy torch view of an engine-owned device buffer
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
 
 
-def measure(ctx, cfg, kind, mb, steps, warmup, sharded=False):
+def measure(ctx, cfg, kind, mb, steps, warmup, sharded=False, special=None):
     """Device-resident and end-to-end numbers of one configuration on this rank.  Returns a dict of raw measurements."""
     import torch
     from tokenizers_b200 import Tokenizer, _lib
     L, rank, world, local = ctx["L"], ctx["rank"], ctx["world"], ctx["local"]
     dist = ctx.get("dist")
     tok = Tokenizer.from_str(tokenizer_json(cfg), device=local)
+    if special:   # AddedVocabulary::add_special_tokens: the extraction then runs in front of the scan, on the device
+        tok.add_special_tokens(special)
+        assert tok._dev_added
     max_bytes = mb << 20
     n_docs_target = max_bytes // (200 if kind == 5 else 300)
     hptr = ctypes.c_void_p()
@@ -288,11 +291,65 @@ def measure(ctx, cfg, kind, mb, steps, warmup, sharded=False):
         torch.cuda.synchronize()
         e2e[key] = (time.perf_counter() - t0) * 1e3
         assert Te == T
+    # dense mode: truncation to 128 + padding to 128 on the device, [n_docs, 128] ids + row lengths come back (no CSR, no mask)
+    sp = _lib.DenseSpec()
+    sp.struct_size = ctypes.sizeof(_lib.DenseSpec); sp.length = 128; sp.max_length = 128; sp.pad_id = 0; sp.want_mask = 0
+
+    def step_dense():
+        res = ctypes.c_void_p()
+        _lib.check(L.b2t_encode_batch_dense(tok.handle, hptr, hoff_ptr, n_docs, ctypes.byref(sp), ctypes.byref(res)))
+        L.b2t_result_free(res)
+    for _ in range(warmup):
+        step_dense()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_dense()
+    torch.cuda.synchronize()
+    e2e["e2e_dense"] = (time.perf_counter() - t0) * 1e3
     L.b2t_host_free(hptr); L.b2t_host_free(hoff_ptr)
     del d_bytes, d_off, tok
     torch.cuda.empty_cache()
-    return {"n": n, "n_docs": n_docs, "T": int(T), "dev_ms": dev_ms, "shard_ms": shard_ms, "e2e_ms": e2e["e2e"], "e2e_ids_ms": e2e["e2e_ids_only"],
+    return {"n": n, "n_docs": n_docs, "T": int(T), "dev_ms": dev_ms, "shard_ms": shard_ms, "e2e_ms": e2e["e2e"], "e2e_ids_ms": e2e["e2e_ids_only"], "e2e_dense_ms": e2e["e2e_dense"],
             "kern_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()}, "launches": int(launches), "steps": steps}
+
+
+def measure_api(ctx, cfg, mb=128):
+    """The drop-in surface a user calls (tokenizers_b200.Tokenizer, the mirror of bindings/python/src/tokenizer.rs:1312-1340),
+    wall clock, inputs in ordinary (pageable) host memory, results read back: what the Python layer costs on top of the C ABI."""
+    import torch
+    from tokenizers_b200 import Tokenizer
+    tok = Tokenizer.from_str(tokenizer_json(cfg), device=ctx["local"])
+    buf = np.empty((mb << 20) + (1 << 20), dtype=np.uint8)
+    n, off = gen_corpus(KIND[cfg], SEED[cfg], 0, (mb << 20) // 300, mb << 20, buf)
+    data, off = buf[:n].copy(), np.ascontiguousarray(off, dtype=np.uint64)
+    n_docs = len(off) - 1
+
+    def timed(fn, reps=3):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
+        return best, r
+    res = {"sample": f"{n / 1e6:.0f} MB / {n_docs} docs of the bench corpus, pageable numpy input, best of 3"}
+    t, be = timed(lambda: tok.encode_batch_csr(data, off))
+    res["encode_batch_csr"] = {"GBps": n / t / 1e9, "tokens_per_s": be.n_tokens / t, "what": "ids + char offsets + word ids copied out of the pinned result"}
+    t, be = timed(lambda: tok.encode_batch_csr(data, off, zero_copy=True))
+    res["encode_batch_csr_zero_copy"] = {"GBps": n / t / 1e9, "what": "the arrays are views of the result's pinned buffers"}
+    t, be = timed(lambda: tok.encode_batch_csr(data, off, offsets=False, word_ids=False, zero_copy=True))
+    res["encode_batch_csr_ids_only_zero_copy"] = {"GBps": n / t / 1e9}
+    k = min(n_docs, 200000)
+    raw = data.tobytes()
+    docs = [raw[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(k)]
+    nb = int(off[k])
+    t, encs = timed(lambda: tok.encode_batch(docs, add_special_tokens=False), reps=2)
+    res["encode_batch_list_of_str"] = {"GBps": nb / t / 1e9, "docs_per_s": k / t, "docs": k, "what": "list[str] in, list of lazy Encoding views out (UTF-8 encode + join on the host)"}
+    t, encs = timed(lambda: tok.encode_batch_fast(docs, add_special_tokens=False), reps=2)
+    res["encode_batch_fast_list_of_str"] = {"GBps": nb / t / 1e9, "docs_per_s": k / t}
+    tok.enable_truncation(128); tok.enable_padding(length=128, pad_id=0)
+    t, dn = timed(lambda: tok.encode_batch_dense(data, off, want_mask=False))
+    res["encode_batch_dense_128"] = {"GBps": n / t / 1e9, "rows_per_s": n_docs / t, "what": "truncation to 128 + padding to 128 on the device, [n_docs, 128] ids + row lengths back"}
+    return res
 
 
 def roofline_of(m, peaks, cfg):
@@ -424,6 +481,9 @@ def main():
            "e2e_ids_only": {"value": gbps(e2e_ids_ms / a.steps), "unit": "GB/s", "ms_per_step": e2e_ids_ms / a.steps,
                             "what": "b2t_encode_batch with flags = 0 (the encode_batch_fast analogue, tokenizer/mod.rs:1382): ids + row_ptr back, 4 B per token",
                             "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(T * 4 + (n_docs + 1) * 8 + 16 * ((n >> 26) + 1))},
+           "e2e_dense_128": {"value": float(m["n"]) * world / (m["e2e_dense_ms"] / a.steps * 1e-3) / 1e9 if world == 1 else None, "unit": "GB/s", "ms_per_step": m["e2e_dense_ms"] / a.steps,
+                             "what": "b2t_encode_batch_dense, pinned host buffers: truncation to 128 tokens + padding to 128 on the device, [n_docs, 128] u32 ids + row lengths back",
+                             "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(n_docs * 128 * 4 + n_docs * 4)},
            "gpu_launches": m["launches"], "clocks": clocks}
     if world > 1:
         out["sharded_no_collective"] = {"what": "the same shards, every rank keeps only its own slice of the CSR (no exchange)", "ms_per_step": dev_step,
@@ -444,6 +504,16 @@ def main():
                     "e2e_ids_only": {"value": mm["n"] / (mm["e2e_ids_ms"] / mm["steps"] * 1e-3) / 1e9, "unit": "GB/s"}}
             except Exception as ex:
                 out["configs"][name] = {"error": str(ex)[:300]}
+        # added-token extraction on the device (added_vocabulary.rs:430-564): the same corpus with "<|endoftext|>" at the end of every document
+        try:
+            mm = measure(ctx, "gpt2", 6, 512, 3, 3, special=["<|endoftext|>"])
+            st = mm["dev_ms"] / mm["steps"]
+            out["configs"]["gpt2_special_token_in_every_doc"] = {
+                "workload": WORK["gpt2"] + f" + the special token <|endoftext|> behind every document, extracted on the device, {mm['n'] / 1e6:.0f} MB / {mm['n_docs']} docs, 3 timed steps",
+                "value": mm["n"] / (st * 1e-3) / 1e9, "unit": "GB/s", "tokens_per_s": mm["T"] / (st * 1e-3), "ms_per_step": st, "kernels_ms": mm["kern_ms"],
+                "e2e": {"value": mm["n"] / (mm["e2e_ms"] / mm["steps"] * 1e-3) / 1e9, "unit": "GB/s"}}
+        except Exception as ex:
+            out["configs"]["gpt2_special_token_in_every_doc"] = {"error": str(ex)[:300]}
         # the reference benches BPE with its word cache off too (benches/bpe_benchmark.rs:59-71, cache_capacity(0)): same corpus, the
         # per-batch word cache of the page kernel switched off, so that every pre-token goes through the merge loop
         try:
@@ -457,6 +527,11 @@ def main():
             out["configs"]["gpt2_word_cache_off"] = {"error": str(ex)[:300]}
         finally:
             os.environ.pop("B2T_WCACHE", None)
+    if world == 1 and not a.no_configs and a.kind == 0 and cfg == "gpt2":
+        try:
+            out["api"] = measure_api(ctx, cfg)
+        except Exception as ex:
+            out["api"] = {"error": str(ex)[:300]}
     if not a.no_cpu and world == 1:
         try:
             cb = cpu_reference(cfg)

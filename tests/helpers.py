@@ -105,7 +105,7 @@ def oracle_backed_tokenizer(tokenizer_json):
             self._h = None
             self._orc = Oracle(tokenizer_json)
 
-        def _engine_rows(self, data, row_off, flags):
+        def _engine_rows(self, data, row_off, flags, zero_copy=False):
             ids, offs, wid, rp = self._orc.encode_batch_csr(data, row_off, OFF_BYTE if flags & _lib.OFFSETS_BYTES else OFF_CHAR)
             return ids, (offs if flags & _lib.WANT_OFFSETS else None), (wid if flags & _lib.WANT_WORD_IDS else None), rp
 

@@ -37,6 +37,8 @@ struct AddedTables {
   const uint32_t* first_bits;   // [2][8]     bit b: some token of the set starts with byte b
   const uint32_t* pair_bits;    // [2][2048]  bit (b0 | b1 << 8): some token of the set starts with b0 b1 (one-byte tokens: every b1)
   const uint32_t* cls_rust;     // class table of the Rust regex crate (\w = CLS_L, \s = CLS_S), 2 bits per code point
+  uint32_t n_first;             // distinct first bytes over both sets if there are at most 4 of them (else 0): ...
+  uint32_t first_bcast[4];      // ... each repeated in the four bytes of a word, for a SWAR test of whole chunks
 };
 
 // ------------------------------------------------------------------------------------------------ A1: candidates
@@ -61,6 +63,16 @@ __global__ void __launch_bounds__(256) added_scan_kernel(const uint8_t* __restri
       for (int k = 0; k < 4; ++k) { const int64_t p = base + 4 * j + k; if (p < n) v |= (uint32_t)__ldg(bytes + p) << (8 * k); }
       w[j] = v;
     }
+  }
+  if (T.n_first) {
+    // special tokens start with a handful of bytes ('<', '['): a chunk that holds none of them has no candidate
+    uint32_t any = 0u;
+    for (uint32_t f = 0; f < T.n_first; ++f) {
+      const uint32_t bc = T.first_bcast[f];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const uint32_t x = w[j] ^ bc; any |= (x - 0x01010101u) & ~x & 0x80808080u; }   // a zero byte of x
+    }
+    if (!any) { cand0[c] = 0u; cand1[c] = 0u; return; }
   }
   const bool has1 = T.set_begin[2] > T.set_begin[1];
   uint32_t m0 = 0u, m1 = 0u;

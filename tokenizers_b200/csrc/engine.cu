@@ -707,6 +707,12 @@ extern "C" int b2t_engine_set_added_tokens(b2t_engine* e, uint32_t n_tokens, con
   e->at.tok_flags = e->d_at_flags.as<uint8_t>();
   e->at.set_begin[0] = begin[0]; e->at.set_begin[1] = begin[1]; e->at.set_begin[2] = begin[2];
   e->at.first_bits = e->d_at_first.as<uint32_t>(); e->at.pair_bits = e->d_at_pair.as<uint32_t>(); e->at.cls_rust = e->d_cls_rust.as<uint32_t>();
+  e->at.n_first = 0;
+  {
+    std::vector<uint32_t> fb;
+    for (uint32_t b = 0; b < 256; ++b) if (((first[b >> 5] | first[8 + (b >> 5)]) >> (b & 31)) & 1u) fb.push_back(b);
+    if (fb.size() <= 4) { e->at.n_first = (uint32_t)fb.size(); for (size_t i = 0; i < fb.size(); ++i) e->at.first_bcast[i] = fb[i] * 0x01010101u; }
+  }
   e->has_added = 1;
   return B2T_OK;
 }

@@ -6,6 +6,8 @@
 
 #include "pretok_logic.cuh"
 #include "unicode_ranges.inc"
+#include "bert_tables.inc"
+#include "norm_kernels.cuh"
 
 namespace b2t {
 
@@ -19,10 +21,85 @@ void unicode_class_table(int scheme, uint8_t* out) {
     fill(B2T_ONIG_L, B2T_ONIG_L_COUNT, CLS_L);
     fill(B2T_ONIG_N, B2T_ONIG_N_COUNT, CLS_N);
     fill(B2T_ONIG_S, B2T_ONIG_S_COUNT, CLS_S);
+  } else if (scheme == 2) {
+    // BertPreTokenizer (pre_tokenizers/bert.rs:5-19): whitespace is removed, punctuation isolated, the rest forms words
+    memset(out, CLS_L, 0x110000);
+    fill(B2T_BERT_PUNCT, B2T_BERT_PUNCT_COUNT, CLS_O);
+    fill(B2T_BERT_WS, B2T_BERT_WS_COUNT, CLS_S);
   } else {
     fill(B2T_RUST_W, B2T_RUST_W_COUNT, CLS_L);
     fill(B2T_RUST_S, B2T_RUST_S_COUNT, CLS_S);
   }
+}
+
+static void utf8_append(std::string& s, uint32_t cp);
+
+// BertNormalizer (normalizers/bert.rs:92-136) as a table: the image of every code point under the enabled steps, in the
+// reference's order clean_text -> handle_chinese_chars -> strip_accents (NFD, drop Mn) -> lowercase.  Every step maps one
+// character to a sequence of characters on its own; NFD's canonical reordering only moves characters with a non-zero
+// combining class, and all 809 of them are dropped by the reference's is_mark_nonspacing (probed: tools/gen_bert_tables.py),
+// so composing per character is exact.
+void build_bert_norm(bool clean_text, bool chinese, bool strip_accents, bool lowercase, NormHost* out) {
+  auto in_ranges = [](const uint32_t (*r)[2], uint32_t cnt, uint32_t c) {
+    uint32_t lo = 0, hi = cnt;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (r[mid][1] < c) lo = mid + 1; else hi = mid; }
+    return lo < cnt && r[lo][0] <= c;
+  };
+  std::unordered_map<uint32_t, std::vector<uint32_t>> nfd, low;
+  for (uint32_t i = 0; i < B2T_BERT_NFD_WORDS;) { const uint32_t cp = B2T_BERT_NFD[i], k = B2T_BERT_NFD[i + 1]; nfd[cp].assign(B2T_BERT_NFD + i + 2, B2T_BERT_NFD + i + 2 + k); i += 2 + k; }
+  for (uint32_t i = 0; i < B2T_BERT_LOWER_WORDS;) { const uint32_t cp = B2T_BERT_LOWER[i], k = B2T_BERT_LOWER[i + 1]; low[cp].assign(B2T_BERT_LOWER + i + 2, B2T_BERT_LOWER + i + 2 + k); i += 2 + k; }
+  out->blk.assign(0x110000 >> 7, 0);
+  out->ent.assign(128, 0u);            // block 0: identity everywhere
+  out->pool.clear();
+  out->ascii.assign(128, 0);
+  std::vector<uint32_t> seq, tmp, block(128);
+  std::string img;
+  for (uint32_t b0 = 0; b0 < 0x110000; b0 += 128) {
+    bool any = false;
+    for (uint32_t c = b0; c < b0 + 128; ++c) {
+      uint32_t e = NORM_IDENT;
+      if (c < 0xD800 || c > 0xDFFF) {
+        seq.assign(1, c);
+        if (clean_text) {
+          if (in_ranges(B2T_BERT_REMOVE, B2T_BERT_REMOVE_COUNT, c)) seq.clear();
+          else if (in_ranges(B2T_BERT_TOSPACE, B2T_BERT_TOSPACE_COUNT, c)) seq.assign(1, 0x20u);
+        }
+        if (chinese && seq.size() == 1 && in_ranges(B2T_BERT_CHINESE, B2T_BERT_CHINESE_COUNT, seq[0])) { const uint32_t x = seq[0]; seq = {0x20u, x, 0x20u}; }
+        if (strip_accents) {
+          tmp.clear();
+          for (uint32_t x : seq) {
+            if (x >= 0xAC00 && x <= 0xD7A3) {   // Hangul syllable -> L V [T]
+              const uint32_t si = x - 0xAC00;
+              tmp.push_back(0x1100 + si / 588); tmp.push_back(0x1161 + (si % 588) / 28);
+              if (si % 28) tmp.push_back(0x11A7 + si % 28);
+            } else {
+              auto it = nfd.find(x);
+              if (it == nfd.end()) tmp.push_back(x); else tmp.insert(tmp.end(), it->second.begin(), it->second.end());
+            }
+          }
+          seq.clear();
+          for (uint32_t x : tmp) if (!in_ranges(B2T_BERT_MN, B2T_BERT_MN_COUNT, x)) seq.push_back(x);
+        }
+        if (lowercase) {
+          tmp.clear();
+          for (uint32_t x : seq) { auto it = low.find(x); if (it == low.end()) tmp.push_back(x); else tmp.insert(tmp.end(), it->second.begin(), it->second.end()); }
+          seq.swap(tmp);
+        }
+        if (seq.empty()) e = NORM_REMOVE;
+        else if (!(seq.size() == 1 && seq[0] == c)) {
+          img.clear();
+          for (uint32_t x : seq) utf8_append(img, x);
+          e = NORM_STRING | ((uint32_t)img.size() << 2) | ((uint32_t)out->pool.size() << 8);
+          out->pool.insert(out->pool.end(), img.begin(), img.end());
+        }
+        if (c < 128) out->ascii[c] = seq.empty() ? 0 : (uint8_t)seq[0];   // (an ASCII character's image is one ASCII character)
+      }
+      block[c - b0] = e;
+      any = any || e != NORM_IDENT;
+    }
+    if (any) { out->blk[b0 >> 7] = (uint16_t)(out->ent.size() / 128); out->ent.insert(out->ent.end(), block.begin(), block.end()); }
+  }
+  out->pool.resize(out->pool.size() + 16, 0);
 }
 
 static void utf8_append(std::string& s, uint32_t cp) {

@@ -29,7 +29,17 @@ struct HostTables {
   bool monotone = false;
 };
 
-// Fills out[0x110000] with the class of every code point (scheme 0 = Oniguruma L/N/S, 1 = Rust regex \w,\s).
+// BertNormalizer as a per-code-point table (norm_kernels.cuh NormTables)
+struct NormHost {
+  std::vector<uint16_t> blk;
+  std::vector<uint32_t> ent;
+  std::vector<uint8_t> pool;
+  std::vector<uint8_t> ascii;
+};
+void build_bert_norm(bool clean_text, bool handle_chinese_chars, bool strip_accents, bool lowercase, NormHost* out);
+
+// Fills out[0x110000] with the class of every code point (scheme 0 = Oniguruma L/N/S, 1 = Rust regex \w,\s,
+// 2 = BertPreTokenizer: CLS_S whitespace, CLS_O punctuation, CLS_L everything else).
 void unicode_class_table(int scheme, uint8_t* out);
 
 // Returns "" on success, else an error message; *vocab_err distinguishes B2T_ERR_VOCAB from B2T_ERR_UNSUPPORTED.

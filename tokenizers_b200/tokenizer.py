@@ -169,6 +169,21 @@ def parse_tokenizer_json(js):
 NO_WORD = 0xFFFFFFFF  # word id of a token the post-processor added (the reference reports None)
 
 
+class _ResultOwner:
+    """Keeps a b2t_result (and the pinned buffers the zero-copy views point into) alive; frees it with the last view holder."""
+
+    def __init__(self, res):
+        self._res = res
+
+    def __del__(self):
+        r, self._res = self._res, None
+        if r:
+            try:
+                _lib.lib().b2t_result_free(r)
+            except Exception:
+                pass
+
+
 class BatchEncoding:
     """The whole batch as a CSR (numpy arrays copied out of the engine's pinned buffers).  `type_ids`,
     `special_tokens_mask` and `attention_mask` are None unless a special-token template / padding was applied; tokens
@@ -590,20 +605,26 @@ class Tokenizer:
         return self._h
 
     # ---- encode
-    def _engine_rows(self, data, row_off, flags):
-        """The C-ABI call: packed rows in host memory -> row CSR (ids, offsets or None, word ids or None, row_ptr)."""
+    def _engine_rows(self, data, row_off, flags, zero_copy=False):
+        """The C-ABI call: packed rows in host memory -> row CSR (ids, offsets or None, word ids or None, row_ptr).
+        zero_copy: the arrays are views of the result's pinned buffers; `self._last_owner` keeps the result alive and the
+        caller ties it to whatever holds the views."""
         n_rows = len(row_off) - 1
         L = _lib.lib()
         res = ctypes.c_void_p()
         _lib.check(L.b2t_encode_batch(self._h, data.ctypes.data if data.size else None, row_off.ctypes.data, n_rows, flags, ctypes.byref(res)))
+        owner = _ResultOwner(res) if zero_copy else None
         try:
             T = L.b2t_result_n_tokens(res)
-            ids = _view(L.b2t_result_ids(res), T, np.uint32).copy()
-            offs = _view(L.b2t_result_offsets(res), 2 * T, np.uint32).reshape(-1, 2).copy() if flags & _lib.WANT_OFFSETS else None
-            wid = _view(L.b2t_result_word_ids(res), T, np.uint32).copy() if flags & _lib.WANT_WORD_IDS else None
-            rp = _view(L.b2t_result_row_ptr(res), n_rows + 1, np.uint64).copy()
+            keep = (lambda a: a) if zero_copy else (lambda a: a.copy())
+            ids = keep(_view(L.b2t_result_ids(res), T, np.uint32))
+            offs = keep(_view(L.b2t_result_offsets(res), 2 * T, np.uint32).reshape(-1, 2)) if flags & _lib.WANT_OFFSETS else None
+            wid = keep(_view(L.b2t_result_word_ids(res), T, np.uint32)) if flags & _lib.WANT_WORD_IDS else None
+            rp = keep(_view(L.b2t_result_row_ptr(res), n_rows + 1, np.uint64))
         finally:
-            L.b2t_result_free(res)
+            if not zero_copy:
+                L.b2t_result_free(res)
+        self._last_owner = owner
         return ids, offs, wid, rp
 
     # ---- truncation / padding (bindings/python/src/tokenizer.rs:700-820)
@@ -643,7 +664,7 @@ class Tokenizer:
             need_text = self._added_strip or want_trim
             fl = flags | _lib.FLAG_ADDED_IDS | (_lib.WANT_OFFSETS if need_text else 0)
             try:
-                ids, offs, wid, rp = self._engine_rows(data, doc_off, fl)
+                ids, offs, wid, rp = self._engine_rows(data, doc_off, fl, getattr(self, "_zero_copy", False))
                 done = True
             except _lib.B2TError as ex:
                 if ex.code != _lib.B2T_ERR_UNSUPPORTED:
@@ -669,7 +690,7 @@ class Tokenizer:
         if not done:
             if extract_added_tokens and self._added is not None:
                 row_off, parts, cut = added.split_batch(self._added, raw, doc_off)
-            ids, offs, wid, rp = self._engine_rows(data, row_off, flags | (_lib.NO_ADDED_TOKENS if self._added is not None else 0))
+            ids, offs, wid, rp = self._engine_rows(data, row_off, flags | (_lib.NO_ADDED_TOKENS if self._added is not None else 0), getattr(self, "_zero_copy", False))
             if cut:
                 ids, offs, wid, rp, added_at = added.stitch_rows(raw, doc_off, parts, ids, offs, wid, rp, bool(flags & _lib.OFFSETS_BYTES))
         trim = None
@@ -698,7 +719,7 @@ class Tokenizer:
         return be
 
     def encode_batch_csr(self, data, doc_off, offsets=True, word_ids=True, byte_offsets=False, add_special_tokens=False,
-                         extract_added_tokens=True):
+                         extract_added_tokens=True, zero_copy=False):
         """Packed batch in (np.uint8[N], np.uint64[n+1]) -> BatchEncoding.  Host buffers; copies happen inside.
 
         extract_added_tokens: run the reference's added-token extraction (added_vocabulary.rs:523-564) on the host before
@@ -713,8 +734,15 @@ class Tokenizer:
         data = np.ascontiguousarray(data, dtype=np.uint8)
         doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
         flags = (_lib.WANT_OFFSETS if offsets else 0) | (_lib.WANT_WORD_IDS if word_ids else 0) | (_lib.OFFSETS_BYTES if byte_offsets else 0)
-        be, trim = self._encode_core(data, doc_off, flags, data, extract_added_tokens)
-        return self._finish(be, trim, add_special_tokens)
+        self._zero_copy = bool(zero_copy)
+        try:
+            be, trim = self._encode_core(data, doc_off, flags, data, extract_added_tokens)
+        finally:
+            self._zero_copy = False
+        out = self._finish(be, trim, add_special_tokens)
+        out._owner = getattr(self, "_last_owner", None) if zero_copy else None   # the views die with the BatchEncoding
+        self._last_owner = None
+        return out
 
     # ---- dense mode: template + truncation + padding on the device (include/b2t.h b2t_encode_batch_dense)
     def dense_spec(self, add_special_tokens=True, want_mask=True):

@@ -9,6 +9,7 @@
 //                 (80 % ASCII, 20 % multi-byte), digit runs, punctuation + contractions, mixed whitespace
 //   4  wordpiece: kind 2 lower-cased, ASCII + Latin-1 only, 0.5 % words > 100 chars, 1 % OOV-char words
 //   5  skew     : doc lengths Zipf(1.2) over [8 B, 64 KB]; 0.1 % of docs hold one 4-64 KB letter / space run
+//   6  gpt2 + special token: kind 2, every document ends with "<|endoftext|>" (the added-token extraction has work in every document)
 //
 // Build: gcc -O2 -shared -fPIC -o tools/libcorpus.so tools/corpus_gen.c -lm
 #include <math.h>
@@ -262,6 +263,7 @@ uint64_t b2t_corpus_generate(void *h, uint64_t first_doc, uint64_t n_docs, uint8
     } else {
       n = gen_doc(&c->g, &r, out + pos, target);
     }
+    if (c->g.kind == 6) { memcpy(out + pos + n, "<|endoftext|>", 13); n += 13; }
     pos += n;
     doc_off[d + 1] = pos;
   }

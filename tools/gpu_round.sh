@@ -8,7 +8,7 @@ tag=${1:-rXX}; quick=$2
 out=gpurun_out
 mkdir -p $out
 timeout 300 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; tail -2 $out/${tag}_pytest.log
-timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; cut -c1-300 $out/${tag}_bench.json
+timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; cut -c1-300 $out/${tag}_bench.json
 if [ -z "$quick" ]; then
   timeout 200 python bench.py --config llama3 --no-cpu > $out/${tag}_bench_llama3.json 2>> $out/${tag}_bench.err
   timeout 200 python bench.py --config wordpiece --no-cpu > $out/${tag}_bench_wordpiece.json 2>> $out/${tag}_bench.err
