@@ -40,8 +40,14 @@ typedef enum {
   B2T_PRETOK_BYTELEVEL = 0,         /* ByteLevel{use_regex=true}: GPT-2 pattern, byte_level.rs:43-46,119-148 */
   B2T_PRETOK_LLAMA3 = 1,            /* Sequence[Split(tiktoken pattern, Isolated), ByteLevel{use_regex=false}] */
   B2T_PRETOK_WHITESPACE = 2,        /* Whitespace: whitespace.rs:20-29 */
-  B2T_PRETOK_BYTELEVEL_NOREGEX = 3  /* ByteLevel{use_regex=false}: the whole sequence is one pre-token */
+  B2T_PRETOK_BYTELEVEL_NOREGEX = 3, /* ByteLevel{use_regex=false}: the whole sequence is one pre-token */
+  B2T_PRETOK_BERT = 4               /* BertPreTokenizer: pre_tokenizers/bert.rs:5-19 (whitespace removed, punctuation isolated) */
 } b2t_pretok_kind;
+
+/* normalizers::BertNormalizer (normalizers/bert.rs:52-136), in front of a WordPiece pipeline: b2t_config.bert_normalizer =
+ * B2T_NORM_BERT | the enabled steps (strip_accents: None resolves to lowercase, bert.rs:128).  The normalizer runs on the
+ * device; offsets refer to the ORIGINAL text through the alignments (tokenizer/normalizer.rs:317-428).  0 = no normalizer. */
+enum { B2T_NORM_BERT = 0x100, B2T_NORM_CLEAN_TEXT = 1, B2T_NORM_CHINESE_CHARS = 2, B2T_NORM_STRIP_ACCENTS = 4, B2T_NORM_LOWERCASE = 8 };
 
 /* Engine configuration = what `TokenizerBuilder` (tokenizer/mod.rs:315-437) receives for this path:
  * BPE::builder().vocab_and_merges(..).ignore_merges(..) (models/bpe/model.rs:36-210) or
@@ -67,6 +73,7 @@ typedef struct {
   const char* continuing_subword_prefix; /* NUL-terminated, e.g. "##" */
   uint32_t max_input_chars_per_word;     /* 100 in bert */
   int32_t device;                        /* CUDA device ordinal, -1 = current device */
+  int32_t bert_normalizer;               /* B2T_NORM_* flags, 0 = none */
 } b2t_config;
 
 /* encode flags */

@@ -114,6 +114,7 @@ static void emul_fast(const uint8_t* bytes, uint64_t n, const uint64_t* doc_off,
     FastOut o;
     if (KIND == PT_GPT2) o = fast_gpt2(m, PT[c], 1u, 1u, DS[c], DS[c + 1], c * 32, at4);
     else if (KIND == PT_WHITESPACE) o = fast_whitespace(m, PT[c], DS[c]);
+    else if (KIND == PT_BERT) o = fast_bert(m, PT[c], DS[c]);
     else { o.start = DS[c] & m.lead; o.drop = 0; o.fallback = 0; o.ov.bits = 0; }
     uint32_t start = apply_overflow(o.start, m.lead, ov_in), drop = o.drop;
     if (KIND == PT_GPT2) {
@@ -135,6 +136,7 @@ extern "C" int b2t_emul_pretok_fast(int kind, const uint8_t* bytes, uint64_t n, 
   if (kind == PT_GPT2) emul_fast<PT_GPT2>(bytes, n, doc_off, n_docs, cls_tbl, start_bits, drop_bits, fallbacks);
   else if (kind == PT_WHITESPACE) emul_fast<PT_WHITESPACE>(bytes, n, doc_off, n_docs, cls_tbl, start_bits, drop_bits, fallbacks);
   else if (kind == PT_NOREGEX) emul_fast<PT_NOREGEX>(bytes, n, doc_off, n_docs, cls_tbl, start_bits, drop_bits, fallbacks);
+  else if (kind == PT_BERT) emul_fast<PT_BERT>(bytes, n, doc_off, n_docs, cls_tbl, start_bits, drop_bits, fallbacks);
   else return 1;
   return 0;
 }

@@ -31,7 +31,7 @@ def _expected(o, kind, docs, off, n):
     for i, d in enumerate(docs):
         base, end = int(off[i]), int(off[i + 1])
         sp = o.pre_tokenize(d)
-        if kind == 2:
+        if kind in (2, 4):   # Whitespace / BertPreTokenizer: the gaps between the splits are removed whitespace
             pos = 0
             for a, b in sp:
                 if a > pos:

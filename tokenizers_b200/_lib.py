@@ -6,7 +6,8 @@ LIB_PATH = os.environ.get("B2T_LIB") or os.path.join(_HERE, "libb2t.so")  # B2T_
 
 B2T_OK, B2T_ERR_INVALID, B2T_ERR_UNSUPPORTED, B2T_ERR_CUDA, B2T_ERR_VOCAB, B2T_ERR_TOO_LARGE = range(6)
 MODEL_BPE, MODEL_WORDPIECE = 0, 1
-PRETOK_BYTELEVEL, PRETOK_LLAMA3, PRETOK_WHITESPACE, PRETOK_BYTELEVEL_NOREGEX = 0, 1, 2, 3
+PRETOK_BYTELEVEL, PRETOK_LLAMA3, PRETOK_WHITESPACE, PRETOK_BYTELEVEL_NOREGEX, PRETOK_BERT = 0, 1, 2, 3, 4
+NORM_BERT, NORM_CLEAN_TEXT, NORM_CHINESE_CHARS, NORM_STRIP_ACCENTS, NORM_LOWERCASE = 0x100, 1, 2, 4, 8
 WANT_OFFSETS, WANT_WORD_IDS, OFFSETS_BYTES, NO_ADDED_TOKENS, FLAG_ADDED_IDS = 1, 2, 4, 8, 16
 ADDED_SINGLE_WORD, ADDED_LSTRIP, ADDED_RSTRIP, ADDED_NORMALIZED = 1, 2, 4, 8
 
@@ -27,7 +28,7 @@ class Config(ctypes.Structure):
                 ("vocab_ids", ctypes.c_void_p),
                 ("n_merges", ctypes.c_uint32), ("merge_bytes", ctypes.c_void_p), ("merge_off", ctypes.c_void_p),
                 ("unk_token", ctypes.c_char_p), ("continuing_subword_prefix", ctypes.c_char_p),
-                ("max_input_chars_per_word", ctypes.c_uint32), ("device", ctypes.c_int32)]
+                ("max_input_chars_per_word", ctypes.c_uint32), ("device", ctypes.c_int32), ("bert_normalizer", ctypes.c_int32)]
 
 
 class DenseSpec(ctypes.Structure):

@@ -41,6 +41,11 @@ B2T_HDI uint32_t edge_hash(uint32_t node, uint32_t byte) {
   return h;
 }
 
+// BertNormalizer table entries (norm_kernels.cuh NormTables.ent): kind in bits 0-1
+enum { NORM_IDENT = 0u, NORM_REMOVE = 1u, NORM_STRING = 2u, NORM_SURVIVOR = 3u, NORM_CCC_FLAG = 4u };
+// NORM_SURVIVOR: a character with a non-zero canonical combining class that strip_accents keeps (image = itself);
+// NORM_CCC_FLAG on a NORM_REMOVE entry: a dropped character with a combining class; on a NORM_SURVIVOR entry: never usable
+
 // Everything the model kernels need, passed by value.
 struct DeviceTables {
   // BPE

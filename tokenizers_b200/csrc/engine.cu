@@ -21,6 +21,7 @@
 #include "host_tables.h"
 #include "long_kernels.cuh"
 #include "model_kernels.cuh"
+#include "norm_kernels.cuh"
 #include "prefix_kernels.cuh"
 #include "pretok_kernels.cuh"
 
@@ -98,6 +99,9 @@ struct Workspace {
   unsigned long long pool_cap = 0;
   DevBuf wcache;                      // per-batch word cache (model_kernels.cuh)
   DevBuf dense_ids, dense_mask, dense_len;  // dense [n_docs, L] rows (dense_kernels.cuh)
+  // BertNormalizer pre-pass (norm_kernels.cuh): the normalized batch and what maps its tokens back to the original
+  DevBuf nrm_doc_bits, nrm_pfd, nrm_page_out, nrm_page_chars, nrm_lexcl_o, nrm_bsum_o, nrm_lexcl_c, nrm_bsum_c, nrm_tot, nrm_bytes, nrm_src_char, nrm_doc_off, nrm_doc_char0;
+  bool norm_active = false;
   DevBuf cand0, cand1, hard_bits, inner_bits, added_bits, added_head, added_pool;
   uint32_t added_cap = 0;  // added-token extraction (added_kernels.cuh)
   DevBuf pfx_bytes, pfx_doc_off, pfx_local, pfx_block, prefix_bits, pfx_total;  // add_prefix_space re-pack (prefix_kernels.cuh)
@@ -112,6 +116,8 @@ struct Workspace {
     tmp_ids.release(); tmp_offsets.release(); tmp_word_ids.release(); tile_count.release(); tile_first.release(); tile_lexcl.release(); tile_bsum.release();
     pfx_bytes.release(); pfx_doc_off.release(); pfx_local.release(); pfx_block.release(); prefix_bits.release(); pfx_total.release();
     dense_ids.release(); dense_mask.release(); dense_len.release();
+    nrm_doc_bits.release(); nrm_pfd.release(); nrm_page_out.release(); nrm_page_chars.release(); nrm_lexcl_o.release(); nrm_bsum_o.release(); nrm_lexcl_c.release();
+    nrm_bsum_c.release(); nrm_tot.release(); nrm_bytes.release(); nrm_src_char.release(); nrm_doc_off.release(); nrm_doc_char0.release();
     cand0.release(); cand1.release(); hard_bits.release(); inner_bits.release(); added_bits.release(); added_head.release(); added_pool.release();
     wcache.release(); page_long.release(); long_desc.release(); long_desc1.release(); soft_bits.release(); page_soft.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
     if (stream) cudaStreamDestroy(stream);
@@ -146,6 +152,10 @@ struct b2t_engine {
   DeviceTables dt;
   int monotone = 0;
   DevBuf d_cls, d_byte_to_id, d_merge, d_word, d_pool, d_edge, d_tok2, d_tri;
+  // BertNormalizer (b2t_config.bert_normalizer)
+  int norm_on = 0;
+  NormTables nt;
+  DevBuf d_nt_blk, d_nt_ent, d_nt_pool, d_nt_ascii;
   // added vocabulary (b2t_engine_set_added_tokens)
   int has_added = 0;
   AddedTables at;
@@ -181,11 +191,15 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
   if (cfg->struct_size != sizeof(b2t_config)) return fail(B2T_ERR_INVALID, "b2t_engine_create: struct_size mismatch (%u != %zu)", cfg->struct_size, sizeof(b2t_config));
   *out = nullptr;
   if (cfg->model != B2T_MODEL_BPE && cfg->model != B2T_MODEL_WORDPIECE) return fail(B2T_ERR_UNSUPPORTED, "unsupported model kind %d", cfg->model);
-  if (cfg->pretok < 0 || cfg->pretok > 3) return fail(B2T_ERR_UNSUPPORTED, "unsupported pre-tokenizer kind %d", cfg->pretok);
-  if (cfg->model == B2T_MODEL_BPE && cfg->pretok == B2T_PRETOK_WHITESPACE)
+  if (cfg->pretok < 0 || cfg->pretok > 4) return fail(B2T_ERR_UNSUPPORTED, "unsupported pre-tokenizer kind %d", cfg->pretok);
+  if (cfg->model == B2T_MODEL_BPE && (cfg->pretok == B2T_PRETOK_WHITESPACE || cfg->pretok == B2T_PRETOK_BERT))
     return fail(B2T_ERR_UNSUPPORTED, "BPE is supported behind the ByteLevel pre-tokenizers only");
-  if (cfg->model == B2T_MODEL_WORDPIECE && cfg->pretok != B2T_PRETOK_WHITESPACE)
-    return fail(B2T_ERR_UNSUPPORTED, "WordPiece is supported behind the Whitespace pre-tokenizer only");
+  if (cfg->model == B2T_MODEL_WORDPIECE && cfg->pretok != B2T_PRETOK_WHITESPACE && cfg->pretok != B2T_PRETOK_BERT)
+    return fail(B2T_ERR_UNSUPPORTED, "WordPiece is supported behind the Whitespace and Bert pre-tokenizers only");
+  if ((cfg->bert_normalizer & B2T_NORM_BERT) && cfg->model != B2T_MODEL_WORDPIECE)
+    return fail(B2T_ERR_UNSUPPORTED, "BertNormalizer is supported in front of WordPiece pipelines only");
+  if (cfg->bert_normalizer & ~(B2T_NORM_BERT | B2T_NORM_CLEAN_TEXT | B2T_NORM_CHINESE_CHARS | B2T_NORM_STRIP_ACCENTS | B2T_NORM_LOWERCASE))
+    return fail(B2T_ERR_INVALID, "unknown bits in bert_normalizer");
   if (cfg->add_prefix_space && cfg->pretok != B2T_PRETOK_BYTELEVEL && cfg->pretok != B2T_PRETOK_BYTELEVEL_NOREGEX)
     return fail(B2T_ERR_UNSUPPORTED, "add_prefix_space is only meaningful for a top-level ByteLevel pre-tokenizer");
   if (!cfg->vocab_bytes || !cfg->vocab_off || !cfg->vocab_ids || cfg->n_vocab == 0) return fail(B2T_ERR_INVALID, "empty vocabulary");
@@ -210,6 +224,7 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
   e->device = dev; e->model = cfg->model; e->pretok = cfg->pretok; e->add_prefix_space = cfg->add_prefix_space;
   cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (const char* kt = getenv("B2T_K1_TILED")) e->k1_tiled = atoi(kt) != 0;
+  if (cfg->pretok == B2T_PRETOK_BERT) e->k1_tiled = 0;   // (the round-1 tiled scan knows no Bert pre-tokenizer)
   if (const char* wc = getenv("B2T_WCACHE")) e->wcache_on = atoi(wc) != 0;
   if (const char* cb = getenv("B2T_CHUNK_BYTES")) {  // host-path chunk size (tests use tiny chunks to exercise the pipeline)
     long long v = atoll(cb);
@@ -221,6 +236,17 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
       (rc = upload(e->d_tok2, ht.tok2_bits)) || (rc = upload(e->d_tri, ht.tri_bits))) {
     b2t_engine_destroy(e);
     return rc;
+  }
+  if (cfg->bert_normalizer & B2T_NORM_BERT) {
+    NormHost nh;
+    build_bert_norm((cfg->bert_normalizer & B2T_NORM_CLEAN_TEXT) != 0, (cfg->bert_normalizer & B2T_NORM_CHINESE_CHARS) != 0,
+                    (cfg->bert_normalizer & B2T_NORM_STRIP_ACCENTS) != 0, (cfg->bert_normalizer & B2T_NORM_LOWERCASE) != 0, &nh);
+    if ((rc = upload(e->d_nt_blk, nh.blk)) || (rc = upload(e->d_nt_ent, nh.ent)) || (rc = upload(e->d_nt_pool, nh.pool)) || (rc = upload(e->d_nt_ascii, nh.ascii))) {
+      b2t_engine_destroy(e);
+      return rc;
+    }
+    e->nt.blk = e->d_nt_blk.as<uint16_t>(); e->nt.ent = e->d_nt_ent.as<uint32_t>(); e->nt.pool = e->d_nt_pool.as<uint8_t>(); e->nt.ascii = e->d_nt_ascii.as<uint8_t>();
+    e->norm_on = 1;
   }
   memset(&e->dt, 0, sizeof(e->dt));
   e->dt.byte_to_id = e->d_byte_to_id.as<uint32_t>();
@@ -253,6 +279,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
   cudaDeviceSynchronize();
   e->dev_ws.release();
   for (auto& s : e->slot) s.release();
+  e->d_nt_blk.release(); e->d_nt_ent.release(); e->d_nt_pool.release(); e->d_nt_ascii.release();
   e->d_at_bytes.release(); e->d_at_off.release(); e->d_at_id.release(); e->d_at_flags.release(); e->d_at_first.release(); e->d_at_pair.release(); e->d_cls_rust.release();
   e->d_cls.release(); e->d_byte_to_id.release(); e->d_merge.release(); e->d_word.release(); e->d_pool.release(); e->d_edge.release(); e->d_tok2.release(); e->d_tri.release();
   for (b2t_result* r : e->pool) { r->release_host(); delete r; }
@@ -380,6 +407,9 @@ static int finish_device(b2t_engine* e, Workspace& ws, uint32_t* d_ids, uint32_t
   row_ptr_fix_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(ws.last_doc_off, n_docs, ws.tile_lexcl.as<unsigned long long>(),
                                                              ws.tile_bsum.as<unsigned long long>(), ws.row_ptr_local.as<uint64_t>(), d_rp, token_base);
   e->last_launches += 2;
+  if (ws.norm_active && (flags & B2T_WANT_OFFSETS) && n_docs)
+    norm_offsets_kernel<<<(unsigned)(((uint64_t)n_docs * 32 + 255) / 256), 256, 0, st>>>(d_rp, n_docs, token_base, ws.nrm_doc_off.as<uint64_t>(), ws.nrm_doc_char0.as<uint32_t>(),
+                                                                                      ws.nrm_src_char.as<uint32_t>(), reinterpret_cast<uint2*>(d_off));
   CU(cudaGetLastError());
   return B2T_OK;
 }
@@ -409,6 +439,43 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     d_bytes = ws.pfx_bytes.as<uint8_t>(); d_doc_off = ws.pfx_doc_off.as<uint64_t>(); n += (int64_t)added;
     d_prefix_bits = ws.prefix_bits.as<uint32_t>();
   }
+  ws.norm_active = false;
+  if (e->norm_on && n > 0 && n_docs > 0) {
+    // BertNormalizer as a byte-rewriting pre-pass: the kernels below see the normalized batch, the offsets are mapped back at the end
+    if (flags & B2T_OFFSETS_BYTES) return fail(B2T_ERR_UNSUPPORTED, "byte offsets are not available behind a normalizer (character offsets are)");
+    const int64_t o_words = n / 32 + 2, o_pages = n / PAGE + 1, o_blk = (o_pages + TSCAN - 1) / TSCAN;
+    if ((rc = ws.nrm_doc_bits.ensure(o_words * 4)) || (rc = ws.nrm_pfd.ensure(o_pages * 4)) || (rc = ws.nrm_page_out.ensure(o_pages * 4)) ||
+        (rc = ws.nrm_page_chars.ensure(o_pages * 4)) || (rc = ws.nrm_lexcl_o.ensure(o_pages * 8)) || (rc = ws.nrm_lexcl_c.ensure(o_pages * 8)) ||
+        (rc = ws.nrm_bsum_o.ensure((o_blk + 2) * 8)) || (rc = ws.nrm_bsum_c.ensure((o_blk + 2) * 8)) || (rc = ws.nrm_tot.ensure(32)) ||
+        (rc = ws.nrm_doc_off.ensure(((size_t)n_docs + 1) * 8)) || (rc = ws.nrm_doc_char0.ensure(((size_t)n_docs + 1) * 4)) || (rc = ws.h_ctl.ensure(sizeof(ctl_block), false)))
+      return rc;
+    CU(cudaMemsetAsync(ws.nrm_doc_bits.p, 0, o_words * 4, st));
+    CU(cudaMemsetAsync(ws.nrm_tot.p, 0, 32, st));
+    unsigned long long* tot = ws.nrm_tot.as<unsigned long long>();
+    uint32_t* nerr = reinterpret_cast<uint32_t*>(tot + 2);
+    doc_mark_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.nrm_doc_bits.as<uint32_t>(), ws.nrm_pfd.as<uint32_t>());
+    norm_count_kernel<<<(unsigned)o_pages, NORM_THREADS, 0, st>>>(d_bytes, n, e->nt, ws.nrm_page_out.as<uint32_t>(), ws.nrm_page_chars.as<uint32_t>(), nerr);
+    tile_scan_block_kernel<<<(unsigned)o_blk, TSCAN, 0, st>>>(ws.nrm_page_out.as<uint32_t>(), ws.nrm_lexcl_o.as<unsigned long long>(), ws.nrm_bsum_o.as<unsigned long long>(), o_pages);
+    tile_scan_top_kernel<<<1, TSCAN, 0, st>>>(ws.nrm_bsum_o.as<unsigned long long>(), o_blk, tot);
+    tile_scan_block_kernel<<<(unsigned)o_blk, TSCAN, 0, st>>>(ws.nrm_page_chars.as<uint32_t>(), ws.nrm_lexcl_c.as<unsigned long long>(), ws.nrm_bsum_c.as<unsigned long long>(), o_pages);
+    tile_scan_top_kernel<<<1, TSCAN, 0, st>>>(ws.nrm_bsum_c.as<unsigned long long>(), o_blk, tot + 1);
+    unsigned long long h_tot[3] = {0, 0, 0};
+    CU(cudaMemcpyAsync(h_tot, ws.nrm_tot.p, 24, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));   // one small read: the size of the normalized batch
+    if ((uint32_t)h_tot[2] & ERR_NORM_UNSUPPORTED)
+      return fail(B2T_ERR_UNSUPPORTED, "the text holds a combining character that strip_accents keeps right behind another combining character: "
+                  "their canonical order (NFD) is not restated on the device");
+    const int64_t m = (int64_t)h_tot[0];
+    if (m + (int64_t)n_docs >= (1ll << 31)) return fail(B2T_ERR_TOO_LARGE, "normalized batch of %lld bytes exceeds the per-call limit of 2^31-1; split it", (long long)m);
+    if ((rc = ws.nrm_bytes.ensure((size_t)m + 64)) || (rc = ws.nrm_src_char.ensure(((size_t)m + 1) * 4))) return rc;
+    norm_write_kernel<<<(unsigned)o_pages, NORM_THREADS, 0, st>>>(d_bytes, n, e->nt, ws.nrm_lexcl_o.as<unsigned long long>(), ws.nrm_bsum_o.as<unsigned long long>(),
+                                                               ws.nrm_lexcl_c.as<unsigned long long>(), ws.nrm_bsum_c.as<unsigned long long>(), TSCAN,
+                                                               ws.nrm_doc_bits.as<uint32_t>(), d_doc_off, n_docs, ws.nrm_bytes.as<uint8_t>(), ws.nrm_src_char.as<uint32_t>(),
+                                                               ws.nrm_doc_off.as<uint64_t>(), ws.nrm_doc_char0.as<uint32_t>(), nerr);
+    CU(cudaGetLastError());
+    d_bytes = ws.nrm_bytes.as<uint8_t>(); d_doc_off = ws.nrm_doc_off.as<uint64_t>(); n = m;
+    ws.norm_active = true;
+  }
   ws.n_eff = n;
   const int64_t n_words = n / 32 + 2, n_pages = n / PAGE + 1;
   if ((rc = ws.doc_bits.ensure(n_words * 4)) || (rc = ws.start_bits.ensure(n_words * 4)) || (rc = ws.page_sum.ensure(n_pages * 8)) ||
@@ -416,7 +483,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
       (rc = ws.block_carry.ensure((n_pages / SCAN_BLOCK + 2) * 8)) || (rc = ws.page_first_doc.ensure(n_pages * 4)) ||
       (rc = ws.ctl.ensure(sizeof(ctl_block))) || (rc = ws.h_ctl.ensure(sizeof(ctl_block), false)))
     return rc;
-  if (e->pretok == PT_WHITESPACE && (rc = ws.drop_bits.ensure(n_words * 4))) return rc;
+  if (pretok_drops_whitespace(e->pretok) && (rc = ws.drop_bits.ensure(n_words * 4))) return rc;
   const bool bpe = e->model == B2T_MODEL_BPE;
   // measured on the 1 GB corpus: 2^19 slots 19.5 ms, 2^20 17.0, 2^21 16.3, 2^22 15.8 (bpe_tile); 2^21 x 64 B = 128 MiB
   constexpr uint32_t WCACHE_SLOTS = 1u << 21;
@@ -473,6 +540,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     case PT_GPT2: launch_pretok<PT_GPT2>(e, d_bytes, n, ws, st, added); break;
     case PT_LLAMA3: launch_pretok<PT_LLAMA3>(e, d_bytes, n, ws, st, added); break;
     case PT_WHITESPACE: launch_pretok<PT_WHITESPACE>(e, d_bytes, n, ws, st, added); break;
+    case PT_BERT: launch_pretok<PT_BERT>(e, d_bytes, n, ws, st, added); break;
     default: launch_pretok<PT_NOREGEX>(e, d_bytes, n, ws, st, added); break;
   }
   rec(e, st, "pretok_scan"); e->last_launches++;
@@ -505,7 +573,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     P.page_carry = ws.page_carry.as<uint64_t>(); P.block_carry = ws.block_carry.as<uint64_t>(); P.page_first_doc = ws.page_first_doc.as<uint32_t>();
     P.doc_off = d_doc_off; P.n_docs = n_docs;
     P.flags = ((flags & B2T_WANT_OFFSETS) ? F_OFFSETS : 0u) | ((flags & B2T_WANT_WORD_IDS) ? F_WORD_IDS : 0u) |
-              ((flags & B2T_OFFSETS_BYTES) ? F_BYTE_OFFSETS : 0u);
+              (((flags & B2T_OFFSETS_BYTES) || ws.norm_active) ? F_BYTE_OFFSETS : 0u);   // behind the normalizer: bytes of the normalized document, mapped back by norm_offsets_kernel
     P.ids = ws.tmp_ids.as<uint32_t>(); P.offsets = ws.tmp_offsets.as<uint32_t>(); P.word_ids = ws.tmp_word_ids.as<uint32_t>();
     P.row_ptr = ws.row_ptr_local.as<uint64_t>();
     P.tile_count = ws.tile_count.as<uint32_t>(); P.tile_first = ws.tile_first.as<uint32_t>();
@@ -664,6 +732,7 @@ extern "C" int b2t_engine_set_added_tokens(b2t_engine* e, uint32_t n_tokens, con
   if (!bytes || !off || !ids || !flags) return fail(B2T_ERR_INVALID, "b2t_engine_set_added_tokens: null argument");
   if (e->add_prefix_space) return fail(B2T_ERR_UNSUPPORTED, "added-token extraction on the device does not combine with add_prefix_space");
   if (e->k1_tiled) return fail(B2T_ERR_UNSUPPORTED, "added-token extraction needs the streaming scan kernels");
+  if (e->norm_on) return fail(B2T_ERR_UNSUPPORTED, "added-token extraction on the device runs on the text the engine is given: with a normalizer the host splits first");
   // two sets (normalized == false first), longest token first inside a set (find_matches: leftmost-longest)
   std::vector<uint32_t> order[2];
   for (uint32_t i = 0; i < n_tokens; ++i) {
@@ -1010,7 +1079,7 @@ extern "C" int b2t_pre_tokenize_batch(b2t_engine* e, const uint8_t* bytes, const
   const size_t n_words = n_eff / 32 + 2;
   std::vector<uint32_t> sb(n_words), db(n_words, 0u);
   CU(cudaMemcpyAsync(sb.data(), ws.start_bits.p, n_words * 4, cudaMemcpyDeviceToHost, ws.stream));
-  if (e->pretok == PT_WHITESPACE) CU(cudaMemcpyAsync(db.data(), ws.drop_bits.p, n_words * 4, cudaMemcpyDeviceToHost, ws.stream));
+  if (pretok_drops_whitespace(e->pretok)) CU(cudaMemcpyAsync(db.data(), ws.drop_bits.p, n_words * 4, cudaMemcpyDeviceToHost, ws.stream));
   CU(cudaStreamSynchronize(ws.stream));
   b2t_result* r = pool_get(e);
   r->eng = e; r->on_device = 0; r->n_docs = n_docs;

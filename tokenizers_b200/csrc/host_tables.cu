@@ -7,7 +7,6 @@
 #include "pretok_logic.cuh"
 #include "unicode_ranges.inc"
 #include "bert_tables.inc"
-#include "norm_kernels.cuh"
 
 namespace b2t {
 
@@ -37,8 +36,9 @@ static void utf8_append(std::string& s, uint32_t cp);
 // BertNormalizer (normalizers/bert.rs:92-136) as a table: the image of every code point under the enabled steps, in the
 // reference's order clean_text -> handle_chinese_chars -> strip_accents (NFD, drop Mn) -> lowercase.  Every step maps one
 // character to a sequence of characters on its own; NFD's canonical reordering only moves characters with a non-zero
-// combining class, and all 809 of them are dropped by the reference's is_mark_nonspacing (probed: tools/gen_bert_tables.py),
-// so composing per character is exact.
+// combining class (809 as the reference sees them, probed: tools/gen_bert_tables.py), and strip_accents drops 726 of them,
+// so composing per character is exact.  (83 newer characters with a combining class are NOT Mn for the reference and
+// survive: NORM_SURVIVOR, see norm_kernels.cuh.)
 void build_bert_norm(bool clean_text, bool chinese, bool strip_accents, bool lowercase, NormHost* out) {
   auto in_ranges = [](const uint32_t (*r)[2], uint32_t cnt, uint32_t c) {
     uint32_t lo = 0, hi = cnt;
@@ -85,14 +85,19 @@ void build_bert_norm(bool clean_text, bool chinese, bool strip_accents, bool low
           for (uint32_t x : seq) { auto it = low.find(x); if (it == low.end()) tmp.push_back(x); else tmp.insert(tmp.end(), it->second.begin(), it->second.end()); }
           seq.swap(tmp);
         }
-        if (seq.empty()) e = NORM_REMOVE;
-        else if (!(seq.size() == 1 && seq[0] == c)) {
+        const bool reorders = strip_accents && in_ranges(B2T_BERT_CCC, B2T_BERT_CCC_COUNT, c);   // non-zero combining class
+        if (seq.empty()) e = NORM_REMOVE | (reorders ? NORM_CCC_FLAG : 0u);
+        else if (reorders) {
+          // one of the 83 characters with a combining class that strip_accents does not drop: its image is itself, but NFD
+          // may have to reorder it with a neighbouring mark -- the kernels refuse the batch if it FOLLOWS another such character
+          e = (seq.size() == 1 && seq[0] == c) ? NORM_SURVIVOR : (NORM_SURVIVOR | NORM_CCC_FLAG);
+        } else if (!(seq.size() == 1 && seq[0] == c)) {
           img.clear();
           for (uint32_t x : seq) utf8_append(img, x);
           e = NORM_STRING | ((uint32_t)img.size() << 2) | ((uint32_t)out->pool.size() << 8);
           out->pool.insert(out->pool.end(), img.begin(), img.end());
         }
-        if (c < 128) out->ascii[c] = seq.empty() ? 0 : (uint8_t)seq[0];   // (an ASCII character's image is one ASCII character)
+        if (c < 128) out->ascii[c] = seq.empty() ? 0xFF : (uint8_t)seq[0];   // (an ASCII character's image is one ASCII character; 0xFF = dropped)
       }
       block[c - b0] = e;
       any = any || e != NORM_IDENT;
@@ -132,7 +137,7 @@ std::string build_host_tables(int model, int pretok, int ignore_merges, uint32_t
   // ---- class table
   {
     std::vector<uint8_t> cls(0x110000);
-    unicode_class_table(pretok == PT_WHITESPACE ? 1 : 0, cls.data());
+    unicode_class_table(pretok == PT_BERT ? 2 : (pretok == PT_WHITESPACE ? 1 : 0), cls.data());
     out->cls_packed.assign(0x110000 / 16, 0u);
     for (uint32_t c = 0; c < 0x110000; ++c) out->cls_packed[c >> 4] |= (uint32_t)cls[c] << ((c & 15) * 2);
   }

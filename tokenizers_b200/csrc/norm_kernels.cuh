@@ -8,8 +8,10 @@
 // Every step of BertNormalizer maps ONE character to a (possibly empty) sequence of characters without looking at its
 // neighbours, so the whole normalizer is a table: code point -> UTF-8 bytes of its image (host_tables.cu composes it
 // from the probed per-character facts of bert_tables.inc for the four flags).  The one context-dependent part of NFD,
-// canonical reordering of combining marks, only permutes characters that strip_accents then drops (Mn); the handful of
-// non-Mn characters with a non-zero combining class are refused (NORM_UNSUPPORTED -> B2T_ERR_UNSUPPORTED).
+// canonical reordering of combining marks, only permutes characters that strip_accents then drops: all 809 characters with
+// a non-zero combining class but 83 count as Mn for the reference (probed, tools/gen_bert_tables.py).  One of those 83 right
+// behind another combining character is the only place where order could matter: such a batch is refused (ERR_NORM_UNSUPPORTED
+// -> B2T_ERR_UNSUPPORTED), never normalized differently.
 //
 //   N1 norm_count   per 2 KB page of the ORIGINAL batch: bytes of its image, characters it holds
 //   (exclusive scans of both, one host read of the total)
@@ -23,11 +25,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "b2t_tables.h"
 #include "pretok_logic.cuh"
 
 namespace b2t {
 
-enum { NORM_IDENT = 0u, NORM_REMOVE = 1u, NORM_STRING = 2u, NORM_UNSUPPORTED = 3u };
 enum { ERR_NORM_UNSUPPORTED = 16u };
 constexpr int NORM_THREADS = 256;
 constexpr int NORM_PER_THREAD = PAGE / NORM_THREADS;   // 8 bytes
@@ -36,7 +38,7 @@ struct NormTables {
   const uint16_t* blk;      // [0x110000 >> 7]: block of the code point
   const uint32_t* ent;      // [blocks][128]: kind (bits 0-1) | byte length (bits 2-7) | pool offset (bits 8-31)
   const uint8_t* pool;      // UTF-8 images
-  const uint8_t* ascii;     // [128]: image of an ASCII character (always one ASCII character), 0 = dropped
+  const uint8_t* ascii;     // [128]: image of an ASCII character (always one ASCII character), 0xFF = dropped
 };
 
 __device__ __forceinline__ uint32_t norm_entry(const NormTables& T, uint32_t cp) {
@@ -59,7 +61,7 @@ __device__ __forceinline__ int norm_out_len(const NormTables& T, const uint8_t* 
   const uint32_t b0 = __ldg(b + p);
   if ((b0 & 0xC0u) == 0x80u) { *is_lead = false; return 0; }
   *is_lead = true;
-  if (b0 < 0x80u) return __ldg(T.ascii + b0) ? 1 : 0;
+  if (b0 < 0x80u) return __ldg(T.ascii + b0) != 0xFFu ? 1 : 0;
   int l;
   const uint32_t cp = norm_decode(b, p, n, &l);
   const uint32_t e = norm_entry(T, cp);
@@ -67,7 +69,20 @@ __device__ __forceinline__ int norm_out_len(const NormTables& T, const uint8_t* 
     case NORM_IDENT: return l;
     case NORM_REMOVE: return 0;
     case NORM_STRING: return (int)((e >> 2) & 63u);
-    default: atomicOr(err, ERR_NORM_UNSUPPORTED); return l;
+    default: {
+      // a combining character that survives strip_accents: NFD would have to order it against the combining character in
+      // front of it, if there is one (dropped or not) -- that case is refused, everything else is the identity
+      bool bad = (e & NORM_CCC_FLAG) != 0u;
+      if (p > 0) {
+        int64_t q = p - 1;
+        while (q > 0 && (__ldg(b + q) & 0xC0u) == 0x80u && p - q < 4) --q;
+        int l2;
+        const uint32_t e2 = norm_entry(T, norm_decode(b, q, n, &l2));
+        bad = bad || (e2 & 3u) == NORM_SURVIVOR || ((e2 & 3u) == NORM_REMOVE && (e2 & NORM_CCC_FLAG));
+      }
+      if (bad) atomicOr(err, ERR_NORM_UNSUPPORTED);
+      return l;
+    }
   }
 }
 
@@ -117,15 +132,15 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_write_kernel(const uint8_t*
   const int64_t base = t * PAGE + (int64_t)threadIdx.x * NORM_PER_THREAD;
   int lens[NORM_PER_THREAD];
   bool leads[NORM_PER_THREAD];
-  int out = 0, chars = 0;
+  int n_out = 0, chars = 0;
 #pragma unroll
   for (int i = 0; i < NORM_PER_THREAD; ++i) {
     const int64_t p = base + i;
     lens[i] = 0; leads[i] = false;
-    if (p < n) { lens[i] = norm_out_len(T, bytes, p, n, &leads[i], err); out += lens[i]; chars += leads[i] ? 1 : 0; }
+    if (p < n) { lens[i] = norm_out_len(T, bytes, p, n, &leads[i], err); n_out += lens[i]; chars += leads[i] ? 1 : 0; }
   }
   int tot;
-  const int out_excl = norm_block_scan(out, s_warp, &tot);
+  const int out_excl = norm_block_scan(n_out, s_warp, &tot);
   const int chr_excl = norm_block_scan(chars, s_warp, &tot);
   unsigned long long o = out_lexcl[t] + out_bexcl[t / scan_block] + (unsigned long long)out_excl;
   unsigned long long c = chr_lexcl[t] + chr_bexcl[t / scan_block] + (unsigned long long)chr_excl;
@@ -145,7 +160,7 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_write_kernel(const uint8_t*
     const uint32_t b0 = __ldg(bytes + p);
     if (b0 < 0x80u) {
       const uint32_t img = __ldg(T.ascii + b0);
-      if (img) { out[o] = (uint8_t)img; src_char[o] = (uint32_t)c; }
+      if (img != 0xFFu) { out[o] = (uint8_t)img; src_char[o] = (uint32_t)c; }
     } else {
       int l;
       const uint32_t cp = norm_decode(bytes, p, n, &l);

@@ -143,6 +143,12 @@ B2T_HD FastCls classify_planes(const uint32_t b[8], uint32_t valid) {
   if (KIND == PT_WHITESPACE) {
     m.L = alpha | digit | (~b7 & b6 & ~b5 & b4 & b3 & b2 & b1 & b0);   // \w on ASCII: letters, digits, '_' (0x5F)
     m.N = 0u; m.AP = 0u; m.NL = 0u;
+  } else if (KIND == PT_BERT) {
+    // BertPreTokenizer on ASCII: whitespace as above, punctuation = is_ascii_punctuation, words = everything else, i.e.
+    // letters, digits, the control characters that are not whitespace, DEL
+    const uint32_t ctl = ~(b7 | b6 | b5) & ~wsctl;                      // 0x00..0x1F without 0x09..0x0D
+    m.L = alpha | digit | ctl | (~b7 & b6 & b5 & b4 & b3 & b2 & b1 & b0);
+    m.N = 0u; m.AP = 0u; m.NL = 0u;
   } else {
     m.L = alpha; m.N = digit;
     m.AP = c20 & ~b3 & b2 & b1 & b0;                         // 0x27
@@ -163,7 +169,9 @@ B2T_HD FastCls classify_planes(const uint32_t b[8], uint32_t valid) {
   }
   // ---- non-ASCII: characters whose class follows from their first bytes
   m.unc = 0u;
-  if (b7) {
+  if (KIND == PT_BERT) {
+    m.unc = b7 & b6 & valid;   // no shortcuts for BERT's classes: every non-ASCII character takes the table
+  } else if (b7) {
     const uint32_t nlead = b7 & b6 & valid;                  // non-ASCII lead bytes
     // conditions on a continuation byte (its low 6 bits), moved to the position of the byte before it; a lead byte at
     // position 31 sees zeros and stays uncertain
@@ -329,6 +337,19 @@ B2T_HD FastOut fast_gpt2(const FastCls& m, const PrevTop& p, uint32_t next_lead0
     o.ov.bits |= (uint32_t)(set >> 32) | ((uint32_t)(clr >> 32) << 8);
   }
   o.start = start & m.lead;
+  return o;
+}
+
+// pre_tokenizers/bert.rs:14-18: split on whitespace (removed), then every punctuation character on its own (Isolated).
+// L slot = word characters, S = whitespace, everything else is punctuation and never joins its neighbour.
+B2T_HD FastOut fast_bert(const FastCls& m, const PrevTop& p, uint32_t ds) {
+  FastOut o;
+  o.fallback = 0u; o.ov.bits = 0u;
+  const uint32_t pW = fsl(p.L, m.L, 1), pS = fsl(p.S, m.S, 1);
+  const uint32_t same = (m.L & pW) | (m.S & pS);
+  const uint32_t start = (~same | ds) & m.lead;
+  o.start = start;
+  o.drop = start & m.S;
   return o;
 }
 

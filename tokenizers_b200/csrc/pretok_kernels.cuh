@@ -543,7 +543,7 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
     uint32_t inner = 0u, keep = 0u, docw = ds;
     if (ADDED && j >= 0 && c < n_chunks) {
       inner = __ldg(ab.inner + c); docw = __ldg(doc_bits + c);
-      if (KIND == PT_WHITESPACE) keep = inner | __ldg(ab.added + c);
+      if (pretok_drops_whitespace(KIND)) keep = inner | __ldg(ab.added + c);
     }
     uint32_t start, drop = 0u;
     if (KIND == PT_GPT2) {
@@ -551,8 +551,8 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
       Overflow in; in.bits = __shfl_sync(FULL, lane == 31 ? k_ov : o.ov.bits, up);
       k_ov = o.ov.bits;
       start = apply_overflow(o.start, m.lead, in);
-    } else if (KIND == PT_WHITESPACE) {
-      const FastOut o = fast_whitespace(m, pt, ds);
+    } else if (KIND == PT_WHITESPACE || KIND == PT_BERT) {
+      const FastOut o = KIND == PT_BERT ? fast_bert(m, pt, ds) : fast_whitespace(m, pt, ds);
       start = o.start; drop = o.drop & ~keep;
     } else {
       start = ds & m.lead;
@@ -571,7 +571,7 @@ pretok_lean_kernel(const uint8_t* __restrict__ bytes, int64_t n64, const uint32_
       const uint32_t p_docw = ADDED ? p_doc : p_ds;
       if (pc < n_chunks) {
         start_bits[pc] = fin;
-        if (KIND == PT_WHITESPACE) drop_bits[pc] = p_drop;
+        if (pretok_drops_whitespace(KIND)) drop_bits[pc] = p_drop;
       }
       // ---- page summary (segmented: counts restart at the last doc start of the page); one iteration is half a page
       const uint32_t kept = fin & ~p_drop;

@@ -24,7 +24,8 @@
 
 namespace b2t {
 
-enum PretokKind { PT_GPT2 = 0, PT_LLAMA3 = 1, PT_WHITESPACE = 2, PT_NOREGEX = 3 };
+enum PretokKind { PT_GPT2 = 0, PT_LLAMA3 = 1, PT_WHITESPACE = 2, PT_NOREGEX = 3, PT_BERT = 4 };   // PT_BERT: pre_tokenizers/bert.rs:5-19
+B2T_HD bool pretok_drops_whitespace(int kind) { return kind == PT_WHITESPACE || kind == PT_BERT; }
 enum { CLS_O = 0, CLS_L = 1, CLS_N = 2, CLS_S = 3 };
 
 constexpr int CHUNK = 32;         // bytes per thread-chunk

@@ -117,11 +117,18 @@ def parse_padding(p):
 
 def parse_tokenizer_json(js):
     """tokenizer.json (tokenizer/serialization.rs:15-48 in the reference) -> engine configuration dict."""
-    if js.get("normalizer") is not None:
-        raise UnsupportedConfig("normalizers stay on the host and are not part of the accelerated path")
+    nz, norm = js.get("normalizer"), 0
+    if nz is not None:
+        # normalizers/bert.rs:52-136; every other normalizer stays outside the accelerated path
+        if nz.get("type") != "BertNormalizer":
+            raise UnsupportedConfig(f"normalizer {nz.get('type')} is not on the accelerated path (BertNormalizer is)")
+        lower = bool(nz.get("lowercase", True))
+        strip = lower if nz.get("strip_accents") is None else bool(nz["strip_accents"])   # bert.rs:128
+        norm = (_lib.NORM_BERT | (_lib.NORM_CLEAN_TEXT if nz.get("clean_text", True) else 0) | (_lib.NORM_CHINESE_CHARS if nz.get("handle_chinese_chars", True) else 0) |
+                (_lib.NORM_STRIP_ACCENTS if strip else 0) | (_lib.NORM_LOWERCASE if lower else 0))
     template = parse_post_processor(js.get("post_processor"))
     pt, m = js.get("pre_tokenizer"), js["model"]
-    cfg = dict(add_prefix_space=0, ignore_merges=0, unk=None, prefix="##", max_chars=100, merges=[])
+    cfg = dict(add_prefix_space=0, ignore_merges=0, unk=None, prefix="##", max_chars=100, merges=[], normalizer=norm)
     if pt is None:
         raise UnsupportedConfig("a pre_tokenizer is required")
     if pt["type"] == "ByteLevel":
@@ -129,6 +136,8 @@ def parse_tokenizer_json(js):
         cfg["add_prefix_space"] = int(pt.get("add_prefix_space", True))
     elif pt["type"] == "Whitespace":
         cfg["pretok"] = _lib.PRETOK_WHITESPACE
+    elif pt["type"] == "BertPreTokenizer":
+        cfg["pretok"] = _lib.PRETOK_BERT
     elif pt["type"] == "Sequence" and len(pt.get("pretokenizers", [])) == 2:
         a, b = pt["pretokenizers"]
         ok = (a.get("type") == "Split" and a.get("pattern", {}).get("Regex") == LLAMA3_PATTERN and a.get("behavior") == "Isolated"
@@ -157,6 +166,12 @@ def parse_tokenizer_json(js):
         raise UnsupportedConfig(f"model {m['type']} is not on the accelerated path")
     cfg["vocab"] = m["vocab"]
     cfg["added_tokens"] = list(js.get("added_tokens", []))
+    if norm and cfg["model"] != _lib.MODEL_WORDPIECE:
+        raise UnsupportedConfig("BertNormalizer is on the accelerated path in front of WordPiece only")
+    if norm and any(t.get("content") and t.get("normalized", not t.get("special", False)) for t in cfg["added_tokens"]):
+        # added_vocabulary.rs:545-560: such tokens are searched in the NORMALIZED text of every piece; only the special
+        # (non-normalized) ones, which are cut out of the raw text before the normalizer runs, are mirrored
+        raise UnsupportedConfig("added tokens with normalized=true behind a normalizer are not on the accelerated path")
     if template is not None and template["trim"] is not None and (cfg["model"] != _lib.MODEL_BPE or cfg["pretok"] == _lib.PRETOK_WHITESPACE):
         raise UnsupportedConfig("trim_offsets needs a byte-level BPE pipeline")
     cfg["template"] = template
@@ -477,6 +492,7 @@ class Tokenizer:
         c.continuing_subword_prefix = cfg["prefix"].encode("utf-8")
         c.max_input_chars_per_word = cfg["max_chars"]
         c.device = device
+        c.bert_normalizer = cfg.get("normalizer", 0)
         h = ctypes.c_void_p()
         rc = L.b2t_engine_create(ctypes.byref(c), ctypes.byref(h))
         if rc == _lib.B2T_ERR_UNSUPPORTED:
