@@ -27,13 +27,19 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import numpy as np  # noqa: E402
 
-ASSET = {"gpt2": "gpt2_style", "llama3": "llama3_style", "wordpiece": "wordpiece"}
-KIND = {"gpt2": 2, "llama3": 2, "wordpiece": 4}
-SEED = {"gpt2": 2, "llama3": 3, "wordpiece": 4}
+ASSET = {"gpt2": "gpt2_style", "llama3": "llama3_style", "wordpiece": "wordpiece", "bert": "wordpiece"}
+KIND = {"gpt2": 2, "llama3": 2, "wordpiece": 4, "bert": 2}
+SEED = {"gpt2": 2, "llama3": 3, "wordpiece": 4, "bert": 2}
 
 
 def tokenizer_json(cfg):
-    return gzip.open(os.path.join(ROOT, "assets", ASSET[cfg] + ".json.gz")).read().decode("utf-8")
+    js = gzip.open(os.path.join(ROOT, "assets", ASSET[cfg] + ".json.gz")).read().decode("utf-8")
+    if cfg == "bert":   # the bert-base-uncased pipeline: BertNormalizer (lowercase, strip accents, CJK spacing) + BertPreTokenizer + WordPiece
+        j = json.loads(js)
+        j["normalizer"] = {"type": "BertNormalizer", "clean_text": True, "handle_chinese_chars": True, "strip_accents": None, "lowercase": True}
+        j["pre_tokenizer"] = {"type": "BertPreTokenizer"}
+        js = json.dumps(j)
+    return js
 
 
 def gen_corpus(kind, seed, first_doc, n_docs, max_bytes, out):
@@ -396,7 +402,8 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = a.config
     WORK = {"gpt2": "GPT-2 ByteLevel BPE (50257 vocab trained offline by the reference trainer), synthetic UTF-8 docs avg ~480 B",
-            "llama3": "Llama-3-style BPE (tiktoken regex, 128k vocab, ignore_merges)", "wordpiece": "Whitespace + WordPiece 30522"}
+            "llama3": "Llama-3-style BPE (tiktoken regex, 128k vocab, ignore_merges)", "wordpiece": "Whitespace + WordPiece 30522",
+            "bert": "bert-base-uncased pipeline: BertNormalizer + BertPreTokenizer + WordPiece 30522, mixed-case multilingual corpus"}
     SKEW = " [length-skew corpus: Zipf doc lengths 8 B-64 KB, 0.1 % docs hold a 4-64 KB letter/space run]"
     workload = WORK[cfg] + (SKEW if a.kind == 5 else "")
 
@@ -492,7 +499,7 @@ def main():
     if world == 1 and not a.no_configs and a.kind == 0 and cfg == "gpt2":
         # the other BASELINE configs on the same line: smaller corpora, fewer steps (stated), same measurement code
         out["configs"] = {}
-        for name, c2, k2 in (("llama3", "llama3", 2), ("wordpiece", "wordpiece", 4), ("skew", "gpt2", 5)):
+        for name, c2, k2 in (("llama3", "llama3", 2), ("wordpiece", "wordpiece", 4), ("bert_uncased", "bert", 2), ("skew", "gpt2", 5)):
             try:
                 mm = measure(ctx, c2, k2, 512, 3, 3)
                 st = mm["dev_ms"] / mm["steps"]

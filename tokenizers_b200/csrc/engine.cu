@@ -451,6 +451,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
       return rc;
     CU(cudaMemsetAsync(ws.nrm_doc_bits.p, 0, o_words * 4, st));
     CU(cudaMemsetAsync(ws.nrm_tot.p, 0, 32, st));
+    rec(e, st, nullptr);
     unsigned long long* tot = ws.nrm_tot.as<unsigned long long>();
     uint32_t* nerr = reinterpret_cast<uint32_t*>(tot + 2);
     doc_mark_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.nrm_doc_bits.as<uint32_t>(), ws.nrm_pfd.as<uint32_t>());
@@ -473,6 +474,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
                                                                ws.nrm_doc_bits.as<uint32_t>(), d_doc_off, n_docs, ws.nrm_bytes.as<uint8_t>(), ws.nrm_src_char.as<uint32_t>(),
                                                                ws.nrm_doc_off.as<uint64_t>(), ws.nrm_doc_char0.as<uint32_t>(), nerr);
     CU(cudaGetLastError());
+    rec(e, st, "normalize");
     d_bytes = ws.nrm_bytes.as<uint8_t>(); d_doc_off = ws.nrm_doc_off.as<uint64_t>(); n = m;
     ws.norm_active = true;
   }
@@ -521,8 +523,8 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     CU(cudaMemsetAsync(ws.soft_bits.p, 0, n_words * 4, st));
     CU(cudaMemsetAsync(ws.page_soft.p, 0, n_pages, st));
   }
-  e->last_launches = 0;
-  rec(e, st, nullptr);
+  e->last_launches = ws.norm_active ? 7 : 0;
+  if (!ws.norm_active) rec(e, st, nullptr);
   doc_mark_kernel<<<(n_docs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, n_docs, ws.doc_bits.as<uint32_t>(), ws.page_first_doc.as<uint32_t>());
   rec(e, st, "doc_mark"); e->last_launches++;
   const bool added = e->has_added && !(flags & B2T_NO_ADDED_TOKENS) && n > 0 && n_docs > 0;
