@@ -129,7 +129,7 @@ ADDED_TOKEN_SPECS = [  # (content, single_word, lstrip, rstrip, normalized, spec
 def added_token_entries(vocab, specs):
     """ids the way the reference assigns them (added_vocabulary.rs:281-310): the model's id when the content is already
     in its vocabulary, else the next free id -- what a tokenizer.json written by the reference would contain"""
-    nxt, out = max(vocab.values()) + 1, []
+    nxt, out = len(vocab), []   # get_vocab_size of the model (the assets' vocabularies are dense, so this is also max id + 1)
     for c, sw, ls, rs, nm, sp in specs:
         if c in vocab:
             i = vocab[c]

@@ -289,6 +289,11 @@ class Encoding:
 
     @property
     def sequence_ids(self):
+        """Known differences from the reference (host-side bookkeeping outside the accelerated path, found by differential runs
+        against tokenizers 0.22.2): the reference derives this list from `sequence_ranges`, which it clears on truncation and
+        does not set for pre-tokenized input -- padded pre-tokenized encodings report 0 for their pad tokens there (None here),
+        and the tokens of the second sequence of a pair that was truncated into overflowing parts report None there (1 here).
+        ids, offsets, word_ids, type_ids, masks, tokens and overflowing are identical."""
         q = self._col(self._be.sequence_ids)
         if q is not None:
             return [None if v < 0 else v for v in q.tolist()]
@@ -569,8 +574,10 @@ class Tokenizer:
             {"id": t.id, "content": t.content, "single_word": t.single_word, "lstrip": t.lstrip, "rstrip": t.rstrip,
              "normalized": t.normalized, "special": t.special} for t in self._added.tokens.values()]
         known = {e["content"]: e for e in entries}
-        top = max([e["id"] for e in entries] + [max(self._vocab.values())])
-        nxt = top + 1
+        # added_vocabulary.rs add_tokens: a new token gets max(id of the added tokens) + 1 when that lies beyond the model's
+        # vocabulary, else the model's vocabulary size (NOT its largest id + 1: the two differ for vocabularies with gaps)
+        vocab_size, max_added = len(self._vocab), max([e["id"] for e in entries] + [-1])
+        nxt = max_added + 1 if max_added >= vocab_size else vocab_size
         added_n = 0
         for t in tokens:
             d = {"content": t} if isinstance(t, str) else {k: getattr(t, k) for k in ("content", "single_word", "lstrip", "rstrip", "normalized") if hasattr(t, k)}
