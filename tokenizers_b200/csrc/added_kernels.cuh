@@ -42,14 +42,27 @@ struct AddedTables {
 };
 
 // ------------------------------------------------------------------------------------------------ A1: candidates
+__device__ __forceinline__ void added_scan_chunk(const uint8_t* __restrict__ bytes, int64_t n, const AddedTables& T, const uint32_t* s_first,
+                                                 int64_t c, int64_t base, uint32_t& m0, uint32_t& m1);
+
+// cand_any: one bit per 32-byte chunk (bit c of the bitmap: cand0[c] | cand1[c] != 0), so that A2 can dismiss a document
+// that holds no candidate with one or two loads.
 __global__ void __launch_bounds__(256) added_scan_kernel(const uint8_t* __restrict__ bytes, int64_t n, const AddedTables T,
-                                                         uint32_t* __restrict__ cand0, uint32_t* __restrict__ cand1) {
+                                                         uint32_t* __restrict__ cand0, uint32_t* __restrict__ cand1, uint32_t* __restrict__ cand_any) {
   __shared__ uint32_t s_first[16];
   if (threadIdx.x < 16) s_first[threadIdx.x] = T.first_bits[threadIdx.x];
   __syncthreads();
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t base = c * CHUNK;
-  if (base >= n) return;
+  uint32_t m0 = 0u, m1 = 0u;
+  if (base < n) added_scan_chunk(bytes, n, T, s_first, c, base, m0, m1);
+  if (base < n) { cand0[c] = m0; cand1[c] = m1; }
+  const uint32_t any = __ballot_sync(0xFFFFFFFFu, (m0 | m1) != 0u);
+  if ((threadIdx.x & 31) == 0 && base < n) cand_any[c >> 5] = any;   // (lane 0 holds the warp's first chunk)
+}
+
+__device__ __forceinline__ void added_scan_chunk(const uint8_t* __restrict__ bytes, int64_t n, const AddedTables& T, const uint32_t* s_first,
+                                                 int64_t c, int64_t base, uint32_t& m0, uint32_t& m1) {
   uint32_t w[9];
   if (base + CHUNK + 4 <= n) {
     const uint4* q = reinterpret_cast<const uint4*>(bytes + base);
@@ -72,10 +85,9 @@ __global__ void __launch_bounds__(256) added_scan_kernel(const uint8_t* __restri
 #pragma unroll
       for (int j = 0; j < 8; ++j) { const uint32_t x = w[j] ^ bc; any |= (x - 0x01010101u) & ~x & 0x80808080u; }   // a zero byte of x
     }
-    if (!any) { cand0[c] = 0u; cand1[c] = 0u; return; }
+    if (!any) return;
   }
   const bool has1 = T.set_begin[2] > T.set_begin[1];
-  uint32_t m0 = 0u, m1 = 0u;
 #pragma unroll
   for (int i = 0; i < CHUNK; ++i) {
     const uint32_t two = __funnelshift_r(w[i >> 2], w[(i >> 2) + 1], 8 * (i & 3)) & 0xFFFFu;   // bytes i, i + 1 (0 past the end)
@@ -85,8 +97,6 @@ __global__ void __launch_bounds__(256) added_scan_kernel(const uint8_t* __restri
   }
   const int64_t lim = n - base;
   if (lim < CHUNK) { const uint32_t valid = (1u << (int)lim) - 1u; m0 &= valid; m1 &= valid; }
-  cand0[c] = m0;
-  cand1[c] = m1;
 }
 
 // ------------------------------------------------------------------------------------------------ A2: resolution
@@ -208,12 +218,12 @@ __device__ void added_find(const AddedCtx& c, int set, int64_t pa, int64_t pb) {
 
 __global__ void __launch_bounds__(128) added_resolve_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ doc_off, uint32_t n_docs,
                                                             const AddedTables T, const uint32_t* __restrict__ cand0, const uint32_t* __restrict__ cand1,
-                                                            AddedOut o) {
+                                                            const uint32_t* __restrict__ cand_any, AddedOut o) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n_docs) return;
   const int64_t a = (int64_t)doc_off[d], b = (int64_t)doc_off[d + 1];
   if (a >= b) return;
-  if (next_bit(cand0, a, b) >= b && next_bit(cand1, a, b) >= b) return;   // nearly every document
+  if (next_bit(cand_any, a / CHUNK, (b - 1) / CHUNK + 1) >= (b - 1) / CHUNK + 1) return;   // nearly every document: no chunk of it holds a candidate
   AddedCtx c;
   c.bytes = bytes; c.T = &T; c.cand[0] = cand0; c.cand[1] = cand1; c.o = o; c.doc_end = b;
   added_find(c, 0, a, b);

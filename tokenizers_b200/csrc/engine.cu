@@ -102,7 +102,7 @@ struct Workspace {
   // BertNormalizer pre-pass (norm_kernels.cuh): the normalized batch and what maps its tokens back to the original
   DevBuf nrm_doc_bits, nrm_pfd, nrm_page_out, nrm_page_chars, nrm_lexcl_o, nrm_bsum_o, nrm_lexcl_c, nrm_bsum_c, nrm_tot, nrm_bytes, nrm_src_char, nrm_doc_off, nrm_doc_char0;
   bool norm_active = false;
-  DevBuf cand0, cand1, hard_bits, inner_bits, added_bits, added_head, added_pool;
+  DevBuf cand0, cand1, cand_any, hard_bits, inner_bits, added_bits, added_head, added_pool;
   uint32_t added_cap = 0;  // added-token extraction (added_kernels.cuh)
   DevBuf pfx_bytes, pfx_doc_off, pfx_local, pfx_block, prefix_bits, pfx_total;  // add_prefix_space re-pack (prefix_kernels.cuh)
   int64_t n_eff = 0;                  // bytes of the batch the kernels actually ran on (n + inserted spaces)
@@ -118,7 +118,7 @@ struct Workspace {
     dense_ids.release(); dense_mask.release(); dense_len.release();
     nrm_doc_bits.release(); nrm_pfd.release(); nrm_page_out.release(); nrm_page_chars.release(); nrm_lexcl_o.release(); nrm_bsum_o.release(); nrm_lexcl_c.release();
     nrm_bsum_c.release(); nrm_tot.release(); nrm_bytes.release(); nrm_src_char.release(); nrm_doc_off.release(); nrm_doc_char0.release();
-    cand0.release(); cand1.release(); hard_bits.release(); inner_bits.release(); added_bits.release(); added_head.release(); added_pool.release();
+    cand0.release(); cand1.release(); cand_any.release(); hard_bits.release(); inner_bits.release(); added_bits.release(); added_head.release(); added_pool.release();
     wcache.release(); page_long.release(); long_desc.release(); long_desc1.release(); soft_bits.release(); page_soft.release(); lp_id.release(); lp_val.release(); lp_len.release(); lp_plen.release(); lp_aux.release(); lp_out.release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -241,6 +241,7 @@ extern "C" int b2t_engine_create(const b2t_config* cfg, b2t_engine** out) {
     NormHost nh;
     build_bert_norm((cfg->bert_normalizer & B2T_NORM_CLEAN_TEXT) != 0, (cfg->bert_normalizer & B2T_NORM_CHINESE_CHARS) != 0,
                     (cfg->bert_normalizer & B2T_NORM_STRIP_ACCENTS) != 0, (cfg->bert_normalizer & B2T_NORM_LOWERCASE) != 0, &nh);
+    if (!nh.ok) { b2t_engine_destroy(e); return fail(B2T_ERR_UNSUPPORTED, "BertNormalizer table: an image exceeds three bytes per input byte"); }
     if ((rc = upload(e->d_nt_blk, nh.blk)) || (rc = upload(e->d_nt_ent, nh.ent)) || (rc = upload(e->d_nt_pool, nh.pool)) || (rc = upload(e->d_nt_ascii, nh.ascii))) {
       b2t_engine_destroy(e);
       return rc;
@@ -471,7 +472,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     if ((rc = ws.nrm_bytes.ensure((size_t)m + 64)) || (rc = ws.nrm_src_char.ensure(((size_t)m + 1) * 4))) return rc;
     norm_write_kernel<<<(unsigned)o_pages, NORM_THREADS, 0, st>>>(d_bytes, n, e->nt, ws.nrm_lexcl_o.as<unsigned long long>(), ws.nrm_bsum_o.as<unsigned long long>(),
                                                                ws.nrm_lexcl_c.as<unsigned long long>(), ws.nrm_bsum_c.as<unsigned long long>(), TSCAN,
-                                                               ws.nrm_doc_bits.as<uint32_t>(), d_doc_off, n_docs, ws.nrm_bytes.as<uint8_t>(), ws.nrm_src_char.as<uint32_t>(),
+                                                               ws.nrm_pfd.as<uint32_t>(), d_doc_off, n_docs, ws.nrm_bytes.as<uint8_t>(), ws.nrm_src_char.as<uint32_t>(),
                                                                ws.nrm_doc_off.as<uint64_t>(), ws.nrm_doc_char0.as<uint32_t>(), nerr);
     CU(cudaGetLastError());
     rec(e, st, "normalize");
@@ -507,7 +508,7 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
   const int64_t n_chunks_all = n / CHUNK + 1;
   if (e->has_added && !(flags & B2T_NO_ADDED_TOKENS)) {
     if (e->add_prefix_space) return fail(B2T_ERR_UNSUPPORTED, "added-token extraction on the device does not combine with add_prefix_space (the prefix goes in front of every piece)");
-    if ((rc = ws.cand0.ensure(n_words * 4)) || (rc = ws.cand1.ensure(n_words * 4)) || (rc = ws.hard_bits.ensure(n_words * 4)) ||
+    if ((rc = ws.cand0.ensure(n_words * 4)) || (rc = ws.cand1.ensure(n_words * 4)) || (rc = ws.cand_any.ensure((n_words / 32 + 2) * 4)) || (rc = ws.hard_bits.ensure(n_words * 4)) ||
         (rc = ws.inner_bits.ensure(n_words * 4)) || (rc = ws.added_bits.ensure(n_words * 4)) ||
         (rc = ws.added_head.ensure(n_pages * 4)) || (rc = ws.added_pool.ensure((size_t)(n / 16 + 4096) * 8)))
       return rc;
@@ -532,10 +533,10 @@ static int run_device_pipeline(b2t_engine* e, Workspace& ws, const uint8_t* d_by
     // added / special tokens (added_vocabulary.rs:430-564): candidates, then one thread per document that holds one
     ctl_block* ctl = ws.ctl.as<ctl_block>();
     CU(cudaMemcpyAsync(ws.hard_bits.p, ws.doc_bits.p, n_words * 4, cudaMemcpyDeviceToDevice, st));
-    added_scan_kernel<<<(unsigned)((n_chunks_all + 255) / 256), 256, 0, st>>>(d_bytes, n, e->at, ws.cand0.as<uint32_t>(), ws.cand1.as<uint32_t>());
+    added_scan_kernel<<<(unsigned)((n_chunks_all + 255) / 256), 256, 0, st>>>(d_bytes, n, e->at, ws.cand0.as<uint32_t>(), ws.cand1.as<uint32_t>(), ws.cand_any.as<uint32_t>());
     AddedOut ao{ws.hard_bits.as<uint32_t>(), ws.inner_bits.as<uint32_t>(), ws.added_bits.as<uint32_t>(), ws.added_head.as<uint32_t>(),
                 ws.added_pool.as<uint2>(), &ctl->added_used, ws.added_cap, &ctl->err};
-    added_resolve_kernel<<<(n_docs + 127) / 128, 128, 0, st>>>(d_bytes, d_doc_off, n_docs, e->at, ws.cand0.as<uint32_t>(), ws.cand1.as<uint32_t>(), ao);
+    added_resolve_kernel<<<(n_docs + 127) / 128, 128, 0, st>>>(d_bytes, d_doc_off, n_docs, e->at, ws.cand0.as<uint32_t>(), ws.cand1.as<uint32_t>(), ws.cand_any.as<uint32_t>(), ao);
     rec(e, st, "added_tokens"); e->last_launches += 2;
   }
   switch (e->pretok) {

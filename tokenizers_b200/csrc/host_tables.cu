@@ -94,6 +94,8 @@ void build_bert_norm(bool clean_text, bool chinese, bool strip_accents, bool low
         } else if (!(seq.size() == 1 && seq[0] == c)) {
           img.clear();
           for (uint32_t x : seq) utf8_append(img, x);
+          const size_t src_len = c < 0x80 ? 1 : (c < 0x800 ? 2 : (c < 0x10000 ? 3 : 4));
+          if (img.size() > 3 * src_len || img.size() > 62) out->ok = false;   // (norm_write_kernel sizes its staging for 3x; holds for every character today)
           e = NORM_STRING | ((uint32_t)img.size() << 2) | ((uint32_t)out->pool.size() << 8);
           out->pool.insert(out->pool.end(), img.begin(), img.end());
         }

@@ -35,6 +35,7 @@ struct NormHost {
   std::vector<uint32_t> ent;
   std::vector<uint8_t> pool;
   std::vector<uint8_t> ascii;
+  bool ok = true;   // every image fits the kernels' bound of 3 bytes per input byte
 };
 void build_bert_norm(bool clean_text, bool handle_chinese_chars, bool strip_accents, bool lowercase, NormHost* out);
 

@@ -62,7 +62,8 @@ struct ModelParams {
 };
 
 __device__ __forceinline__ uint64_t merge_lookup(const DeviceTables& t, uint32_t a, uint32_t b) {
-  uint32_t h = pair_hash(a, b) & t.merge_mask;
+  const uint32_t hf = pair_hash(a, b);
+  uint32_t h = hf & t.merge_mask;
   while (true) {
     uint4 e = __ldg(t.merge_tbl + h);
     if (e.x == a && e.y == b) return ((uint64_t)e.z << 32) | e.w;

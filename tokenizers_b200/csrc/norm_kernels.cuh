@@ -56,36 +56,6 @@ __device__ __forceinline__ uint32_t norm_decode(const uint8_t* __restrict__ b, i
   return cp < 0x110000u ? cp : 0x10FFFFu;
 }
 
-// image length of the character at p (0 for continuation bytes); *is_lead tells whether p starts a character
-__device__ __forceinline__ int norm_out_len(const NormTables& T, const uint8_t* __restrict__ b, int64_t p, int64_t n, bool* is_lead, uint32_t* err) {
-  const uint32_t b0 = __ldg(b + p);
-  if ((b0 & 0xC0u) == 0x80u) { *is_lead = false; return 0; }
-  *is_lead = true;
-  if (b0 < 0x80u) return __ldg(T.ascii + b0) != 0xFFu ? 1 : 0;
-  int l;
-  const uint32_t cp = norm_decode(b, p, n, &l);
-  const uint32_t e = norm_entry(T, cp);
-  switch (e & 3u) {
-    case NORM_IDENT: return l;
-    case NORM_REMOVE: return 0;
-    case NORM_STRING: return (int)((e >> 2) & 63u);
-    default: {
-      // a combining character that survives strip_accents: NFD would have to order it against the combining character in
-      // front of it, if there is one (dropped or not) -- that case is refused, everything else is the identity
-      bool bad = (e & NORM_CCC_FLAG) != 0u;
-      if (p > 0) {
-        int64_t q = p - 1;
-        while (q > 0 && (__ldg(b + q) & 0xC0u) == 0x80u && p - q < 4) --q;
-        int l2;
-        const uint32_t e2 = norm_entry(T, norm_decode(b, q, n, &l2));
-        bad = bad || (e2 & 3u) == NORM_SURVIVOR || ((e2 & 3u) == NORM_REMOVE && (e2 & NORM_CCC_FLAG));
-      }
-      if (bad) atomicOr(err, ERR_NORM_UNSUPPORTED);
-      return l;
-    }
-  }
-}
-
 // block-wide exclusive scan of one int per thread (256 threads); returns the exclusive prefix, *total = block sum
 __device__ __forceinline__ int norm_block_scan(int v, int* s_warp, int* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -102,79 +72,190 @@ __device__ __forceinline__ int norm_block_scan(int v, int* s_warp, int* total) {
   return base + inc - v;
 }
 
-// ------------------------------------------------------------------------------------------------ N1
-__global__ void __launch_bounds__(NORM_THREADS) norm_count_kernel(const uint8_t* __restrict__ bytes, int64_t n, const NormTables T,
-                                                                  uint32_t* __restrict__ page_out, uint32_t* __restrict__ page_chars, uint32_t* __restrict__ err) {
-  __shared__ int s_warp[NORM_THREADS / 32];
-  const int64_t base = (int64_t)blockIdx.x * PAGE + (int64_t)threadIdx.x * NORM_PER_THREAD;
-  int out = 0, chars = 0;
+// What a thread learns about its 8 bytes: per byte the length of the image of the character that starts there
+// (6 bits each, 63 = "not a character start"), the table entry of the non-ASCII ones is looked up again when writing.
+constexpr uint32_t NORM_NOT_LEAD = 63u;
+constexpr int NORM_MAX_OUT = 3 * PAGE;   // an image is at most 3x its character (Hangul syllable -> three jamo)
+
+struct NormChunk {
+  uint32_t w0, w1, w2;     // the thread's 8 bytes and the 4 behind them (little endian)
+  unsigned long long lens; // 8 x 6 bits
+  uint32_t ent[NORM_PER_THREAD];   // table entry of the non-ASCII character that starts at byte i (0 otherwise)
+  int n_out, n_chars;
+};
+
+__device__ __forceinline__ uint32_t norm_bytes_at(const NormChunk& c, int i) {   // the four bytes that start at byte i (i < 8)
+  const uint32_t lo = i < 4 ? c.w0 : c.w1, hi = i < 4 ? c.w1 : c.w2;
+  return __funnelshift_r(lo, hi, 8 * (i & 3));
+}
+__device__ __forceinline__ uint32_t norm_cp_of(uint32_t v, int* len) {           // v: the character's bytes, little endian
+  const uint32_t b0 = v & 0xFFu;
+  const int l = b0 < 0xE0u ? 2 : (b0 < 0xF0u ? 3 : 4);
+  const uint32_t t24 = ((v & 0x3Fu) << 18) | ((v << 4) & 0x3F000u) | ((v >> 10) & 0xFC0u) | ((v >> 24) & 0x3Fu);
+  uint32_t cp = (t24 >> (6 * (4 - l))) & ((2u << (5 * l)) - 1u);
+  *len = l;
+  return cp < 0x110000u ? cp : 0x10FFFFu;
+}
+
+// The table look-ups of a thread's (up to 8) non-ASCII characters are issued together -- first all block numbers, then all
+// entries -- instead of one dependent pair per character: the pre-pass is bound by the latency of these loads.
+__device__ __forceinline__ void norm_load_chunk(const uint8_t* __restrict__ bytes, int64_t n, int64_t base, const NormTables& T, const uint8_t* s_ascii,
+                                                NormChunk& c, uint32_t* err) {
+  c.w0 = c.w1 = c.w2 = 0u; c.lens = 0ull; c.n_out = 0; c.n_chars = 0;
+#pragma unroll
+  for (int i = 0; i < NORM_PER_THREAD; ++i) c.ent[i] = 0u;
+  if (base >= n) { c.lens = ~0ull; return; }
+  if (base + 12 <= n) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(bytes + base));
+    c.w0 = v.x; c.w1 = v.y; c.w2 = __ldg(reinterpret_cast<const uint32_t*>(bytes + base + 8));
+  } else {
+    uint32_t w[3] = {0u, 0u, 0u};
+    for (int k = 0; k < 12 && base + k < n; ++k) w[k >> 2] |= (uint32_t)__ldg(bytes + base + k) << (8 * (k & 3));
+    c.w0 = w[0]; c.w1 = w[1]; c.w2 = w[2];
+  }
+  const int valid = n - base >= NORM_PER_THREAD ? NORM_PER_THREAD : (int)(n - base);
+  uint32_t cps[NORM_PER_THREAD], clen[NORM_PER_THREAD], blk[NORM_PER_THREAD];
+  uint32_t lead = 0u, hi = 0u;   // bit i: byte i starts a character / a non-ASCII character
 #pragma unroll
   for (int i = 0; i < NORM_PER_THREAD; ++i) {
-    const int64_t p = base + i;
-    if (p < n) { bool lead; out += norm_out_len(T, bytes, p, n, &lead, err); chars += lead ? 1 : 0; }
+    const uint32_t b0 = ((i < 4 ? c.w0 : c.w1) >> (8 * (i & 3))) & 0xFFu;
+    int l = 1;
+    cps[i] = b0;
+    if (i < valid && (b0 & 0xC0u) != 0x80u) {
+      lead |= 1u << i;
+      if (b0 >= 0x80u) { hi |= 1u << i; cps[i] = norm_cp_of(norm_bytes_at(c, i), &l); }
+    }
+    clen[i] = (uint32_t)l;
   }
+#pragma unroll
+  for (int i = 0; i < NORM_PER_THREAD; ++i) blk[i] = (hi >> i) & 1u ? (uint32_t)__ldg(T.blk + (cps[i] >> 7)) : 0u;
+#pragma unroll
+  for (int i = 0; i < NORM_PER_THREAD; ++i) if ((hi >> i) & 1u) c.ent[i] = __ldg(T.ent + blk[i] * 128u + (cps[i] & 127u));
+#pragma unroll
+  for (int i = 0; i < NORM_PER_THREAD; ++i) {
+    uint32_t len = NORM_NOT_LEAD;
+    if ((lead >> i) & 1u) {
+      ++c.n_chars;
+      if (!((hi >> i) & 1u)) len = s_ascii[cps[i]] != 0xFFu ? 1u : 0u;
+      else {
+        const uint32_t e = c.ent[i], kind = e & 3u;
+        len = kind == NORM_REMOVE ? 0u : (kind == NORM_STRING ? ((e >> 2) & 63u) : clen[i]);
+        if (kind == NORM_SURVIVOR) {
+          // a combining character that survives strip_accents: NFD would have to order it against the combining character in
+          // front of it, if there is one (dropped or not) -- that case is refused, everything else is the identity
+          bool bad = (e & NORM_CCC_FLAG) != 0u;
+          const int64_t p = base + i;
+          if (p > 0) {
+            int64_t q = p - 1;
+            while (q > 0 && (__ldg(bytes + q) & 0xC0u) == 0x80u && p - q < 4) --q;
+            int l2;
+            const uint32_t e2 = norm_entry(T, norm_decode(bytes, q, n, &l2));
+            bad = bad || (e2 & 3u) == NORM_SURVIVOR || ((e2 & 3u) == NORM_REMOVE && (e2 & NORM_CCC_FLAG));
+          }
+          if (bad) atomicOr(err, ERR_NORM_UNSUPPORTED);
+        }
+      }
+      c.n_out += (int)len;
+    }
+    c.lens |= (unsigned long long)len << (6 * i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ N1
+__global__ void __launch_bounds__(NORM_THREADS, 8) norm_count_kernel(const uint8_t* __restrict__ bytes, int64_t n, const NormTables T,
+                                                                  uint32_t* __restrict__ page_out, uint32_t* __restrict__ page_chars, uint32_t* __restrict__ err) {
+  __shared__ int s_warp[NORM_THREADS / 32];
+  __shared__ uint8_t s_ascii[128];
+  if (threadIdx.x < 128) s_ascii[threadIdx.x] = __ldg(T.ascii + threadIdx.x);
+  __syncthreads();
+  NormChunk c;
+  norm_load_chunk(bytes, n, (int64_t)blockIdx.x * PAGE + (int64_t)threadIdx.x * NORM_PER_THREAD, T, s_ascii, c, err);
   int tot_out, tot_chars;
-  norm_block_scan(out, s_warp, &tot_out);
-  norm_block_scan(chars, s_warp, &tot_chars);
+  norm_block_scan(c.n_out, s_warp, &tot_out);
+  norm_block_scan(c.n_chars, s_warp, &tot_chars);
   if (threadIdx.x == 0) { page_out[blockIdx.x] = (uint32_t)tot_out; page_chars[blockIdx.x] = (uint32_t)tot_chars; }
 }
 
 // ------------------------------------------------------------------------------------------------ N2
-// page_out_base / page_char_base: exclusive scans of N1's counts (two-level: local + block, as the token-count scan).
-__global__ void __launch_bounds__(NORM_THREADS) norm_write_kernel(const uint8_t* __restrict__ bytes, int64_t n, const NormTables T,
+// out_lexcl / out_bexcl, chr_lexcl / chr_bexcl: exclusive scans of N1's counts (two-level: local + block, as the token-count
+// scan).  The page's image is assembled in shared memory (bytes + page-relative original character index) and written out
+// with consecutive threads on consecutive addresses.
+__global__ void __launch_bounds__(NORM_THREADS, 6) norm_write_kernel(const uint8_t* __restrict__ bytes, int64_t n, const NormTables T,
                                                                   const unsigned long long* __restrict__ out_lexcl, const unsigned long long* __restrict__ out_bexcl,
                                                                   const unsigned long long* __restrict__ chr_lexcl, const unsigned long long* __restrict__ chr_bexcl, int scan_block,
-                                                                  const uint32_t* __restrict__ doc_bits, const uint64_t* __restrict__ doc_off, uint32_t n_docs,
+                                                                  const uint32_t* __restrict__ page_first_doc, const uint64_t* __restrict__ doc_off, uint32_t n_docs,
                                                                   uint8_t* __restrict__ out, uint32_t* __restrict__ src_char,
                                                                   uint64_t* __restrict__ doc_off_out, uint32_t* __restrict__ doc_char0, uint32_t* __restrict__ err) {
   __shared__ int s_warp[NORM_THREADS / 32];
+  __shared__ uint8_t s_ascii[128];
+  __shared__ uint8_t s_img[NORM_MAX_OUT];
+  __shared__ uint16_t s_src[NORM_MAX_OUT];
+  __shared__ uint16_t s_oex[NORM_THREADS], s_cex[NORM_THREADS];
+  __shared__ unsigned long long s_lens[NORM_THREADS];
+  if (threadIdx.x < 128) s_ascii[threadIdx.x] = __ldg(T.ascii + threadIdx.x);
+  __syncthreads();
   const int64_t t = blockIdx.x;
   const int64_t base = t * PAGE + (int64_t)threadIdx.x * NORM_PER_THREAD;
-  int lens[NORM_PER_THREAD];
-  bool leads[NORM_PER_THREAD];
-  int n_out = 0, chars = 0;
+  // loads that depend on nothing computed here go first (the kernel is a chain of latencies: bytes -> table -> scans -> stores)
+  const unsigned long long g_out = out_lexcl[t] + out_bexcl[t / scan_block], g_chr = chr_lexcl[t] + chr_bexcl[t / scan_block];
+  const uint64_t d_first = (uint64_t)__ldg(page_first_doc + t) + threadIdx.x;
+  const int64_t q_first = d_first <= n_docs ? (int64_t)__ldg(doc_off + d_first) : (int64_t)1 << 62;
+  NormChunk c;
+  norm_load_chunk(bytes, n, base, T, s_ascii, c, err);
+  int tot_out, tot_chars;
+  int o = norm_block_scan(c.n_out, s_warp, &tot_out);       // page-relative position in the image
+  int ch = norm_block_scan(c.n_chars, s_warp, &tot_chars);  // page-relative character index
+  // what the document pass below needs from every thread: where its 8 bytes start in the image / in characters, and the lengths
+  s_oex[threadIdx.x] = (uint16_t)o; s_cex[threadIdx.x] = (uint16_t)ch; s_lens[threadIdx.x] = c.lens;
+  // Emit byte by byte over the 8 bytes of the thread and the (up to 3) bytes behind them that finish its last character:
+  // ASCII characters and non-ASCII characters whose image is themselves -- nearly everything -- are copied through by the
+  // same few instructions in every lane; only a character with a table image (upper case, accents, CJK spacing) loops.
+  {
+    int copy = 0, chi = ch;
 #pragma unroll
-  for (int i = 0; i < NORM_PER_THREAD; ++i) {
-    const int64_t p = base + i;
-    lens[i] = 0; leads[i] = false;
-    if (p < n) { lens[i] = norm_out_len(T, bytes, p, n, &leads[i], err); n_out += lens[i]; chars += leads[i] ? 1 : 0; }
+    for (int j = 0; j < NORM_PER_THREAD + 3; ++j) {
+      const uint32_t b = ((j < 4 ? c.w0 : (j < 8 ? c.w1 : c.w2)) >> (8 * (j & 3))) & 0xFFu;
+      if (j < NORM_PER_THREAD) {
+        const uint32_t len = (uint32_t)(c.lens >> (6 * j)) & 63u;
+        if (len != NORM_NOT_LEAD) {            // a character of this thread starts here
+          const uint32_t e = c.ent[j];         // 0 for ASCII
+          const bool str = (e & 3u) == NORM_STRING;
+          chi = ch++;
+          copy = (len != 0u && !str) ? 1 : 0;
+          if (str) {
+            const uint8_t* __restrict__ src = T.pool + (e >> 8);
+            for (uint32_t k = 0; k < len; ++k) { s_img[o + k] = __ldg(src + k); s_src[o + k] = (uint16_t)chi; }
+            o += (int)len;
+          }
+        }
+      } else if ((b & 0xC0u) != 0x80u) copy = 0;   // behind the 8 bytes: only continuation bytes of the last character
+      if (copy) { s_img[o] = b < 0x80u ? s_ascii[b] : (uint8_t)b; s_src[o] = (uint16_t)chi; ++o; }
+    }
   }
-  int tot;
-  const int out_excl = norm_block_scan(n_out, s_warp, &tot);
-  const int chr_excl = norm_block_scan(chars, s_warp, &tot);
-  unsigned long long o = out_lexcl[t] + out_bexcl[t / scan_block] + (unsigned long long)out_excl;
-  unsigned long long c = chr_lexcl[t] + chr_bexcl[t / scan_block] + (unsigned long long)chr_excl;
-  // the 8 bytes of this thread lie in one word pair of the document bitmap
-  const uint32_t dsw = base < n + 1 ? __ldg(doc_bits + (base >> 5)) >> (base & 31) : 0u;
-#pragma unroll
-  for (int i = 0; i < NORM_PER_THREAD; ++i) {
-    const int64_t p = base + i;
-    if (p > n) break;
-    if ((dsw >> i) & 1u) {
-      // every document that starts at byte p (several if some are empty): doc_off is sorted, find the first by bisection
-      uint32_t lo = 0, hi = n_docs;
-      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((int64_t)__ldg(doc_off + mid) < p) lo = mid + 1; else hi = mid; }
-      for (uint32_t d = lo; d <= n_docs && (int64_t)__ldg(doc_off + d) == p; ++d) { doc_off_out[d] = o; doc_char0[d] = (uint32_t)c; }
-    }
-    if (p >= n || !leads[i]) continue;
-    const uint32_t b0 = __ldg(bytes + p);
-    if (b0 < 0x80u) {
-      const uint32_t img = __ldg(T.ascii + b0);
-      if (img != 0xFFu) { out[o] = (uint8_t)img; src_char[o] = (uint32_t)c; }
-    } else {
-      int l;
-      const uint32_t cp = norm_decode(bytes, p, n, &l);
-      const uint32_t e = norm_entry(T, cp);
-      const uint32_t kind = e & 3u;
-      if (kind == NORM_STRING) {
-        const uint8_t* __restrict__ src = T.pool + (e >> 8);
-        for (int k = 0; k < lens[i]; ++k) { out[o + k] = __ldg(src + k); src_char[o + k] = (uint32_t)c; }
-      } else if (kind != NORM_REMOVE) {
-        for (int k = 0; k < l; ++k) { out[o + k] = p + k < n ? __ldg(bytes + p + k) : 0; src_char[o + k] = (uint32_t)c; }
+  __syncthreads();
+  // the documents that start in this page (consecutive from page_first_doc[t]; the last page also owns the end sentinel):
+  // their start in the image and the index of their first original character
+  {
+    const int64_t page_lo = t * PAGE, page_hi = page_lo + PAGE;
+    for (uint64_t d = d_first; d <= n_docs; d += NORM_THREADS) {
+      const int64_t q = d == d_first ? q_first : (int64_t)__ldg(doc_off + d);
+      if (q >= page_hi) break;
+      if (q < page_lo) continue;       // (cannot happen: page_first_doc is the first document at or behind the page start)
+      const int owner = (int)(q - page_lo) / NORM_PER_THREAD, within = (int)(q - page_lo) % NORM_PER_THREAD;
+      int oo = s_oex[owner], cc = s_cex[owner];
+      const unsigned long long lens = s_lens[owner];
+      for (int i = 0; i < within; ++i) {
+        const uint32_t len = (uint32_t)(lens >> (6 * i)) & 63u;
+        if (len != NORM_NOT_LEAD) { oo += (int)len; ++cc; }
       }
+      doc_off_out[d] = g_out + (unsigned long long)oo;
+      doc_char0[d] = (uint32_t)(g_chr + (unsigned long long)cc);
     }
-    o += (unsigned long long)lens[i];
-    c += 1ull;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < tot_out; i += NORM_THREADS) {
+    out[g_out + i] = s_img[i];
+    src_char[g_out + i] = (uint32_t)(g_chr + s_src[i]);
   }
 }
 
