@@ -446,7 +446,7 @@ def main():
 
     # ---- reduce over ranks: time = max, work = sum
     if world > 1:
-        v = torch.tensor([m["dev_ms"], m["e2e_ms"], m["e2e_ids_ms"], m["shard_ms"]], dtype=torch.float64, device="cuda")
+        v = torch.tensor([m["dev_ms"], m["e2e_ms"], m["e2e_ids_ms"], m["shard_ms"], m["e2e_dense_ms"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         w = torch.tensor([float(m["n"]), float(m["T"])], dtype=torch.float64, device="cuda")
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
@@ -454,9 +454,31 @@ def main():
         allr = torch.empty(4 * world, dtype=torch.float64, device="cuda")
         dist.all_gather_into_tensor(allr, mine)
         allr = allr.reshape(world, 4).tolist()
-        dev_ms, e2e_ms, e2e_ids_ms, shard_ms = v.tolist(); tot_bytes, tot_tok = w.tolist()
+        dev_ms, e2e_ms, e2e_ids_ms, shard_ms, e2e_dense_ms = v.tolist(); tot_bytes, tot_tok = w.tolist()
+        # BASELINE configs[4]: the length-skew corpus across the ranks (Zipf doc lengths 8 B-64 KB, 0.1 % of the documents hold a
+        # 4-64 KB run), same sharded step; what the load balance looks like is in the per-rank times
+        skew = None
+        if cfg == "gpt2" and a.kind == 0 and not a.no_configs:
+            try:
+                ms = measure(ctx, "gpt2", 5, 512, 3, 3, sharded=True)
+                sv = torch.tensor([ms["shard_ms"], ms["dev_ms"]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(sv, op=dist.ReduceOp.MAX)
+                sw = torch.tensor([float(ms["n"])], dtype=torch.float64, device="cuda")
+                dist.all_reduce(sw, op=dist.ReduceOp.SUM)
+                smine = torch.tensor([ms["dev_ms"] / ms["steps"], ms["kern_ms"].get("bpe_long", 0.0) + ms["kern_ms"].get("long_find", 0.0)], dtype=torch.float64, device="cuda")
+                sall = torch.empty(2 * world, dtype=torch.float64, device="cuda")
+                dist.all_gather_into_tensor(sall, smine)
+                sall = sall.reshape(world, 2).tolist()
+                per = [x[0] for x in sall]
+                skew = {"workload": "length-skew corpus, 512 MB per GPU, 3 timed steps, the sharded step with its exchange",
+                        "value": sw.item() / (sv[0].item() / ms["steps"] * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": sv[0].item() / ms["steps"],
+                        "no_collective_GBps": sw.item() / (sv[1].item() / ms["steps"] * 1e-3) / 1e9,
+                        "per_rank_ms_per_step": [round(x, 3) for x in per], "imbalance_max_over_mean": max(per) / (sum(per) / len(per)),
+                        "per_rank_long_pretoken_kernels_ms": [round(x[1], 3) for x in sall]}
+            except Exception as ex:
+                skew = {"error": str(ex)[:300]}
     else:
-        dev_ms, e2e_ms, e2e_ids_ms, shard_ms = m["dev_ms"], m["e2e_ms"], m["e2e_ids_ms"], None
+        dev_ms, e2e_ms, e2e_ids_ms, shard_ms, e2e_dense_ms = m["dev_ms"], m["e2e_ms"], m["e2e_ids_ms"], None, m["e2e_dense_ms"]
         tot_bytes, tot_tok = float(m["n"]), float(m["T"])
         allr = [[m["dev_ms"] / a.steps, sum(m["kern_ms"].values()), m["e2e_ms"] / a.steps, float(numa if numa is not None else -1)]]
     if rank != 0:
@@ -488,7 +510,7 @@ def main():
            "e2e_ids_only": {"value": gbps(e2e_ids_ms / a.steps), "unit": "GB/s", "ms_per_step": e2e_ids_ms / a.steps,
                             "what": "b2t_encode_batch with flags = 0 (the encode_batch_fast analogue, tokenizer/mod.rs:1382): ids + row_ptr back, 4 B per token",
                             "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(T * 4 + (n_docs + 1) * 8 + 16 * ((n >> 26) + 1))},
-           "e2e_dense_128": {"value": float(m["n"]) * world / (m["e2e_dense_ms"] / a.steps * 1e-3) / 1e9 if world == 1 else None, "unit": "GB/s", "ms_per_step": m["e2e_dense_ms"] / a.steps,
+           "e2e_dense_128": {"value": gbps(e2e_dense_ms / a.steps), "unit": "GB/s", "ms_per_step": e2e_dense_ms / a.steps,
                              "what": "b2t_encode_batch_dense, pinned host buffers: truncation to 128 tokens + padding to 128 on the device, [n_docs, 128] u32 ids + row lengths back",
                              "h2d_bytes_per_step": int(n + (n_docs + 1) * 8), "d2h_bytes_per_step": int(n_docs * 128 * 4 + n_docs * 4)},
            "gpu_launches": m["launches"], "clocks": clocks}
@@ -496,6 +518,8 @@ def main():
         out["sharded_no_collective"] = {"what": "the same shards, every rank keeps only its own slice of the CSR (no exchange)", "ms_per_step": dev_step,
                                         "value": gbps(dev_step), "unit": "GB/s"}
         out["exchange"] = {"what": "bytes of other ranks' CSR each rank receives per step", "bytes": int((tot_tok - T) * 12 + (world - 1) * (n_docs + 1) * 8)}
+        if skew is not None:
+            out["configs"] = {"skew_sharded": skew}
     if world == 1 and not a.no_configs and a.kind == 0 and cfg == "gpt2":
         # the other BASELINE configs on the same line: smaller corpora, fewer steps (stated), same measurement code
         out["configs"] = {}

@@ -937,10 +937,12 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
     CU(cudaEventSynchronize(ws.done));
     if (pretok_only) return B2T_OK;
     int rc2;
+    bool reran = false;
     for (int attempt = 0;; ++attempt) {
       unsigned long long want = 0;
       rc2 = check_ctl(ws, &want);
       if (rc2 == B2T_OK) break;
+      reran = true;
       if (rc2 != -1 || attempt >= 2) return rc2 == -1 ? fail(B2T_ERR_CUDA, "long pool did not converge") : rc2;
       // rerun this chunk with a larger pool (its input is still resident in the slot)
       if ((rc2 = ensure_long_pool(ws, want))) return rc2;
@@ -957,12 +959,14 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
       } else if (max_row > dq->S.L) {
         return fail(B2T_ERR_INVALID, "a row of %u tokens does not fit the dense length %u: enable truncation (the reference returns a longer row here)", max_row, dq->S.L);
       }
-      const size_t L = dq->S.L;
-      if (nd && L) {
-        CU(cudaMemcpyAsync(r->h_dense_ids.as<uint32_t>() + (size_t)c.d0 * L, ws.dense_ids.p, (size_t)nd * L * 4, cudaMemcpyDeviceToHost, ws.stream));
-        if (dq->want_mask) CU(cudaMemcpyAsync(r->h_dense_mask.as<uint8_t>() + (size_t)c.d0 * L, ws.dense_mask.p, (size_t)nd * L, cudaMemcpyDeviceToHost, ws.stream));
+      if (dq->batch_longest || reran) {   // (a fixed length: the rows were queued for the copy right behind the kernels, see below)
+        const size_t L = dq->S.L;
+        if (nd && L) {
+          CU(cudaMemcpyAsync(r->h_dense_ids.as<uint32_t>() + (size_t)c.d0 * L, ws.dense_ids.p, (size_t)nd * L * 4, cudaMemcpyDeviceToHost, ws.stream));
+          if (dq->want_mask) CU(cudaMemcpyAsync(r->h_dense_mask.as<uint8_t>() + (size_t)c.d0 * L, ws.dense_mask.p, (size_t)nd * L, cudaMemcpyDeviceToHost, ws.stream));
+        }
+        if (nd) CU(cudaMemcpyAsync(r->h_row_len.as<uint32_t>() + c.d0, ws.dense_len.p, (size_t)nd * 4, cudaMemcpyDeviceToHost, ws.stream));
       }
-      if (nd) CU(cudaMemcpyAsync(r->h_row_len.as<uint32_t>() + c.d0, ws.dense_len.p, (size_t)nd * 4, cudaMemcpyDeviceToHost, ws.stream));
       tok_base += nt;
       return B2T_OK;
     }
@@ -1010,6 +1014,16 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
     if (c.b0) rebase_kernel<<<(nd + 1 + 255) / 256, 256, 0, ws.stream>>>(ws.doc_off.as<uint64_t>(), nd + 1, c.b0);
     rc = run_device_pipeline(e, ws, ws.bytes.as<uint8_t>(), (int64_t)nb, ws.doc_off.as<uint64_t>(), nd, pretok_only ? (flags | B2T_NO_ADDED_TOKENS) : flags, ws.stream, !pretok_only, true, dq);
     if (rc) break;
+    if (dq && !dq->batch_longest && nd) {
+      // dense rows of a fixed length: their place in the result does not depend on anything the host has to read first, so
+      // the copy back is queued right behind the kernels (the CSR modes need the chunk's token count for that)
+      const size_t L = dq->S.L;
+      if (L) {
+        CUL(cudaMemcpyAsync(r->h_dense_ids.as<uint32_t>() + (size_t)c.d0 * L, ws.dense_ids.p, (size_t)nd * L * 4, cudaMemcpyDeviceToHost, ws.stream));
+        if (dq->want_mask) CUL(cudaMemcpyAsync(r->h_dense_mask.as<uint8_t>() + (size_t)c.d0 * L, ws.dense_mask.p, (size_t)nd * L, cudaMemcpyDeviceToHost, ws.stream));
+      }
+      CUL(cudaMemcpyAsync(r->h_row_len.as<uint32_t>() + c.d0, ws.dense_len.p, (size_t)nd * 4, cudaMemcpyDeviceToHost, ws.stream));
+    }
     CUL(cudaEventRecord(ws.done, ws.stream));
     // keep at most NSLOT - 1 chunks un-drained so that result copies overlap the next chunks' kernels
     while (rc == B2T_OK && drained + (NSLOT - 1) <= ci) rc = drain(drained++);
