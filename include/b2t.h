@@ -91,7 +91,10 @@ enum {
 enum { B2T_ADDED_SINGLE_WORD = 1u, B2T_ADDED_LSTRIP = 2u, B2T_ADDED_RSTRIP = 4u, B2T_ADDED_NORMALIZED = 8u };
 
 /* Replaces TokenizerBuilder::build for the path.  The tables are uploaded to the device once; the engine is
- * immutable afterwards and may be used from several host threads (calls serialise on an internal mutex). */
+ * immutable afterwards and may be used from several host threads: every host-buffer call (b2t_encode_batch,
+ * b2t_encode_batch_dense, b2t_pre_tokenize_batch) runs on device workspaces and streams of its own (up to four calls in
+ * flight, further ones wait), so their copies and kernels overlap; the device-resident entry points share one workspace
+ * (their result lives in it) and serialise.  With profiling on (b2t_engine_set_profiling) calls are meant to be made one at a time. */
 int b2t_engine_create(const b2t_config* cfg, b2t_engine** out);
 void b2t_engine_destroy(b2t_engine* e);
 

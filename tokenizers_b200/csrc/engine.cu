@@ -11,6 +11,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -140,7 +142,10 @@ struct b2t_result {
   void release_host() { h_ids.release(); h_offsets.release(); h_word_ids.release(); h_row_ptr.release(); h_dense_ids.release(); h_dense_mask.release(); h_row_len.release(); }
 };
 
-constexpr int NSLOT = 3;
+#ifndef B2T_NSLOT
+#define B2T_NSLOT 3
+#endif
+constexpr int NSLOT = B2T_NSLOT;   // chunk workspaces of one host-path call: NSLOT - 1 chunks are in flight while the next is issued
 constexpr int MAX_KERNEL_RECORDS = 16;
 
 struct b2t_engine {
@@ -160,9 +165,17 @@ struct b2t_engine {
   int has_added = 0;
   AddedTables at;
   DevBuf d_at_bytes, d_at_off, d_at_id, d_at_flags, d_at_first, d_at_pair, d_cls_rust;
-  std::mutex mu;
+  // Concurrency: the tables are immutable, every host-path call (b2t_encode_batch, _dense, b2t_pre_tokenize_batch) runs on a
+  // slot set of its own -- NSLOT workspaces with their streams -- so calls from several host threads overlap their copies
+  // and kernels; `mu` only guards the pools (and the whole call while per-kernel profiling is on: the event records are one
+  // per engine).  The device-resident entry points keep one workspace (their result lives in it) and serialise on `mu`.
+  std::mutex mu;        // pools of results and slot sets (held briefly)
+  std::mutex dev_mu;    // the device-resident entry points, whole call
+  std::mutex prof_mu;   // host-path calls while profiling is on, whole call
+  std::condition_variable set_free;
   Workspace dev_ws;          // b2t_encode_batch_device
-  Workspace slot[NSLOT];     // b2t_encode_batch chunks
+  struct SlotSet { Workspace slot[NSLOT]; bool busy = false; };
+  std::vector<SlotSet*> sets;   // at most MAX_SLOT_SETS, created on demand
   cudaStream_t own_stream = nullptr;
   size_t chunk_bytes = 64u << 20;
   // pinned result pool
@@ -173,8 +186,9 @@ struct b2t_engine {
   const char* rec_name[MAX_KERNEL_RECORDS];
   cudaEvent_t rec_ev[MAX_KERNEL_RECORDS + 1];
   bool rec_ev_made = false;
-  int last_launches = 0;
+  std::atomic<int> last_launches{0};
 };
+constexpr size_t MAX_SLOT_SETS = 4;
 
 // ------------------------------------------------------------------------------------------------ create / destroy
 template <class T>
@@ -279,7 +293,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   e->dev_ws.release();
-  for (auto& s : e->slot) s.release();
+  for (auto* ss : e->sets) { for (auto& s : ss->slot) s.release(); delete ss; }
   e->d_nt_blk.release(); e->d_nt_ent.release(); e->d_nt_pool.release(); e->d_nt_ascii.release();
   e->d_at_bytes.release(); e->d_at_off.release(); e->d_at_id.release(); e->d_at_flags.release(); e->d_at_first.release(); e->d_at_pair.release(); e->d_cls_rust.release();
   e->d_cls.release(); e->d_byte_to_id.release(); e->d_merge.release(); e->d_word.release(); e->d_pool.release(); e->d_edge.release(); e->d_tok2.release(); e->d_tri.release();
@@ -637,7 +651,7 @@ static int ensure_events(b2t_engine* e) {
 
 extern "C" int b2t_engine_set_profiling(b2t_engine* e, int on) {
   if (!e) return fail(B2T_ERR_INVALID, "null engine");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::mutex> lk(e->dev_mu);
   CU(cudaSetDevice(e->device));
   if (on) { int rc = ensure_events(e); if (rc) return rc; }
   e->profiling = on ? 1 : 0;
@@ -661,7 +675,7 @@ extern "C" int b2t_encode_batch_device(b2t_engine* e, const uint8_t* d_bytes, ui
                                        uint32_t n_docs, uint32_t flags, void* stream, b2t_result** out) {
   if (!e || !out || !d_doc_off || (!d_bytes && n_bytes)) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device: null argument");
   if (((uintptr_t)d_bytes & 15u) != 0) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device: d_bytes must be 16-byte aligned");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::mutex> lk(e->dev_mu);
   CU(cudaSetDevice(e->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->own_stream;
   Workspace& ws = e->dev_ws;
@@ -690,7 +704,7 @@ extern "C" int b2t_encode_batch_device_begin(b2t_engine* e, const uint8_t* d_byt
                                              uint32_t n_docs, uint32_t flags, void* stream, uint64_t* n_tokens) {
   if (!e || !n_tokens || !d_doc_off || (!d_bytes && n_bytes)) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device_begin: null argument");
   if (((uintptr_t)d_bytes & 15u) != 0) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device_begin: d_bytes must be 16-byte aligned");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::mutex> lk(e->dev_mu);
   CU(cudaSetDevice(e->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->own_stream;
   Workspace& ws = e->dev_ws;
@@ -713,7 +727,7 @@ extern "C" int b2t_encode_batch_device_begin(b2t_engine* e, const uint8_t* d_byt
 extern "C" int b2t_encode_batch_device_finish(b2t_engine* e, uint32_t* d_ids, uint32_t* d_offsets, uint32_t* d_word_ids,
                                               uint64_t* d_row_ptr, uint64_t token_base, void* stream) {
   if (!e || !d_ids || !d_row_ptr) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device_finish: null argument");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::mutex> lk(e->dev_mu);
   Workspace& ws = e->dev_ws;
   if (!ws.pending) return fail(B2T_ERR_INVALID, "b2t_encode_batch_device_finish without a matching begin");
   if ((ws.last_flags & B2T_WANT_OFFSETS) && !d_offsets) return fail(B2T_ERR_INVALID, "offsets were requested at begin: d_offsets is null");
@@ -728,7 +742,7 @@ extern "C" int b2t_encode_batch_device_finish(b2t_engine* e, uint32_t* d_ids, ui
 extern "C" int b2t_engine_set_added_tokens(b2t_engine* e, uint32_t n_tokens, const uint8_t* bytes, const uint32_t* off, const uint32_t* ids,
                                            const uint8_t* flags) {
   if (!e) return fail(B2T_ERR_INVALID, "null engine");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::mutex> lk(e->dev_mu);
   CU(cudaSetDevice(e->device));
   e->has_added = 0;
   if (n_tokens == 0) return B2T_OK;
@@ -822,7 +836,7 @@ extern "C" int b2t_encode_batch_dense_device(b2t_engine* e, const uint8_t* d_byt
   DenseReq dq;
   int rc;
   if ((rc = make_dense_req(spec, &dq))) return rc;
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::mutex> lk(e->dev_mu);
   CU(cudaSetDevice(e->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->own_stream;
   Workspace& ws = e->dev_ws;
@@ -854,9 +868,34 @@ extern "C" int b2t_encode_batch_dense_device(b2t_engine* e, const uint8_t* d_byt
 
 // ------------------------------------------------------------------------------------------------ host pipeline
 static b2t_result* pool_get(b2t_engine* e) {
+  std::lock_guard<std::mutex> lk(e->mu);
   if (!e->pool.empty()) { b2t_result* r = e->pool.back(); e->pool.pop_back(); return r; }
   return new b2t_result();
 }
+
+static void pool_put(b2t_engine* e, b2t_result* r) {
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->pool.push_back(r);
+}
+
+// A slot set for one host-path call; blocks while MAX_SLOT_SETS calls are in flight.
+struct SetLease {
+  b2t_engine* e; b2t_engine::SlotSet* ss;
+  explicit SetLease(b2t_engine* e_) : e(e_), ss(nullptr) {
+    std::unique_lock<std::mutex> lk(e->mu);
+    while (true) {
+      for (auto* c : e->sets) if (!c->busy) { ss = c; break; }
+      if (ss) break;
+      if (e->sets.size() < MAX_SLOT_SETS) { ss = new b2t_engine::SlotSet(); e->sets.push_back(ss); break; }
+      e->set_free.wait(lk);
+    }
+    ss->busy = true;
+  }
+  ~SetLease() {
+    { std::lock_guard<std::mutex> lk(e->mu); ss->busy = false; }
+    e->set_free.notify_one();
+  }
+};
 
 static int slot_init(Workspace& ws) {
   if (!ws.stream) CU(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
@@ -872,7 +911,7 @@ __global__ void rebase_kernel(uint64_t* doc_off, uint32_t count, uint64_t base) 
 
 struct Chunk { uint32_t d0, d1; uint64_t b0, b1; uint64_t tok_base; };
 
-static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, uint32_t flags, bool pretok_only,
+static int host_encode(b2t_engine* e, b2t_engine::SlotSet& ss, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, uint32_t flags, bool pretok_only,
                        b2t_result** out, const DenseReq* dq_in = nullptr) {
   if (doc_off[0] != 0) return fail(B2T_ERR_INVALID, "doc_off[0] must be 0");
   for (uint32_t d = 0; d < n_docs; ++d)  // the kernels index the buffer with these: a decreasing offset must never reach them
@@ -907,7 +946,7 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
   const bool want_off = (flags & B2T_WANT_OFFSETS) || pretok_only, want_wid = (flags & B2T_WANT_WORD_IDS) && !pretok_only;
   // initial capacity guess: 0.30 tokens per byte, grown on demand (pinned pool => steady state allocates nothing)
   uint64_t cap_tok = std::max<uint64_t>(total_bytes * 3 / 10 + 1024, 4096);
-  if ((rc = r->h_row_ptr.ensure(((size_t)n_docs + 1) * 8, false))) { e->pool.push_back(r); return rc; }
+  if ((rc = r->h_row_ptr.ensure(((size_t)n_docs + 1) * 8, false))) { pool_put(e, r); return rc; }
   auto grow = [&](uint64_t need_tok) -> int {
     int rc2;
     if (!pretok_only && (rc2 = r->h_ids.ensure(need_tok * 4, true))) return rc2;
@@ -924,8 +963,8 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
       return rc2;
     return B2T_OK;
   };
-  if (dq) { if (!dq->batch_longest && (rc = dense_host(dq->S.L))) { e->pool.push_back(r); return rc; } }
-  else if ((rc = grow(cap_tok))) { e->pool.push_back(r); return rc; }
+  if (dq) { if (!dq->batch_longest && (rc = dense_host(dq->S.L))) { pool_put(e, r); return rc; } }
+  else if ((rc = grow(cap_tok))) { pool_put(e, r); return rc; }
 
   uint64_t tok_base = 0;
   const size_t nc = chunks.size();
@@ -933,7 +972,7 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
   // drain(i) waits for chunk i's kernels and queues the D2H of its results on the same slot stream.
   auto drain = [&](size_t ci) -> int {
     Chunk& c = chunks[ci];
-    Workspace& ws = e->slot[ci % NSLOT];
+    Workspace& ws = ss.slot[ci % NSLOT];
     CU(cudaEventSynchronize(ws.done));
     if (pretok_only) return B2T_OK;
     int rc2;
@@ -972,7 +1011,7 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
     }
     if (tok_base + nt > cap_tok) {
       // earlier chunks may still be copying into the old buffers: let them land, then grow (contents are kept)
-      for (auto& s : e->slot) if (s.stream) CU(cudaStreamSynchronize(s.stream));
+      for (auto& s : ss.slot) if (s.stream) CU(cudaStreamSynchronize(s.stream));
       cap_tok = (tok_base + nt) * 2;
       if ((rc2 = grow(cap_tok))) return rc2;
     }
@@ -997,7 +1036,7 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
   }
   // (a CUDA failure inside the loop must reach the common cleanup below: the pooled result goes back, slot streams are drained)
   for (size_t ci = 0; ci < nc && rc == B2T_OK; ++ci) {
-    Workspace& ws = e->slot[ci % NSLOT];
+    Workspace& ws = ss.slot[ci % NSLOT];
     if ((rc = slot_init(ws))) break;
     if (ci >= NSLOT) {
       // slot reuse: the chunk that used it must be drained and its copies must have landed
@@ -1030,8 +1069,8 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
   }
 #undef CUL
   while (rc == B2T_OK && drained < nc) rc = drain(drained++);
-  for (auto& s : e->slot) if (s.stream) cudaStreamSynchronize(s.stream);
-  if (rc) { e->pool.push_back(r); return rc; }
+  for (auto& s : ss.slot) if (s.stream) cudaStreamSynchronize(s.stream);
+  if (rc) { pool_put(e, r); return rc; }
 
   if (dq) {
     if (n_docs == 0 && dq->batch_longest) dq->S.L = 0;
@@ -1060,9 +1099,11 @@ static int host_encode(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_
 extern "C" int b2t_encode_batch(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, uint32_t flags,
                                 b2t_result** out) {
   if (!e || !out || !doc_off || (!bytes && doc_off[n_docs])) return fail(B2T_ERR_INVALID, "b2t_encode_batch: null argument");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::unique_lock<std::mutex> prof(e->prof_mu, std::defer_lock);
+  SetLease lease(e);
+  if (e->profiling) prof.lock();   // (the per-kernel event records are one per engine)
   CU(cudaSetDevice(e->device));
-  return host_encode(e, bytes, doc_off, n_docs, flags, false, out);
+  return host_encode(e, *lease.ss, bytes, doc_off, n_docs, flags, false, out);
 }
 
 extern "C" int b2t_encode_batch_dense(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, const b2t_dense_spec* spec,
@@ -1071,22 +1112,26 @@ extern "C" int b2t_encode_batch_dense(b2t_engine* e, const uint8_t* bytes, const
   DenseReq dq;
   int rc;
   if ((rc = make_dense_req(spec, &dq))) return rc;
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::unique_lock<std::mutex> prof(e->prof_mu, std::defer_lock);
+  SetLease lease(e);
+  if (e->profiling) prof.lock();
   CU(cudaSetDevice(e->device));
-  return host_encode(e, bytes, doc_off, n_docs, 0u, false, out, &dq);
+  return host_encode(e, *lease.ss, bytes, doc_off, n_docs, 0u, false, out, &dq);
 }
 
 // PreTokenizer seam: runs K0/K1 and expands the split bitmaps into (start, end) pairs.  The expansion of the bitmap
 // into the pair list is output formatting and happens on the host (this is an inspection API, not the hot path).
 extern "C" int b2t_pre_tokenize_batch(b2t_engine* e, const uint8_t* bytes, const uint64_t* doc_off, uint32_t n_docs, b2t_result** out) {
   if (!e || !out || !doc_off || (!bytes && doc_off[n_docs])) return fail(B2T_ERR_INVALID, "b2t_pre_tokenize_batch: null argument");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::unique_lock<std::mutex> prof(e->prof_mu, std::defer_lock);
+  SetLease lease(e);
+  if (e->profiling) prof.lock();
   CU(cudaSetDevice(e->device));
   if (doc_off[0] != 0) return fail(B2T_ERR_INVALID, "doc_off[0] must be 0");
   for (uint32_t d = 0; d < n_docs; ++d)  // the kernels index the buffer with these: a decreasing offset must never reach them
     if (doc_off[d + 1] < doc_off[d]) return fail(B2T_ERR_INVALID, "doc_off must be non-decreasing (document %u)", d);
   const uint64_t n = doc_off[n_docs];
-  Workspace& ws = e->slot[0];
+  Workspace& ws = lease.ss->slot[0];
   int rc;
   if ((rc = slot_init(ws)) || (rc = ws.bytes.ensure(n + 64)) || (rc = ws.doc_off.ensure(((size_t)n_docs + 1) * 8))) return rc;
   if (n) CU(cudaMemcpyAsync(ws.bytes.p, bytes, n, cudaMemcpyHostToDevice, ws.stream));
@@ -1103,7 +1148,7 @@ extern "C" int b2t_pre_tokenize_batch(b2t_engine* e, const uint8_t* bytes, const
   auto bit = [](const std::vector<uint32_t>& v, uint64_t p) { return (v[p >> 5] >> (p & 31)) & 1u; };
   uint64_t count = 0;
   for (uint64_t p = 0; p < n_eff; ++p) count += bit(sb, p) && !bit(db, p);
-  if ((rc = r->h_offsets.ensure((count + 1) * 8, false)) || (rc = r->h_row_ptr.ensure(((size_t)n_docs + 1) * 8, false))) { e->pool.push_back(r); return rc; }
+  if ((rc = r->h_offsets.ensure((count + 1) * 8, false)) || (rc = r->h_row_ptr.ensure(((size_t)n_docs + 1) * 8, false))) { pool_put(e, r); return rc; }
   uint32_t* off = r->h_offsets.as<uint32_t>();
   uint64_t* rp = r->h_row_ptr.as<uint64_t>();
   uint64_t k = 0, shift = 0;
