@@ -202,8 +202,15 @@ int b2t_engine_last_kernels(const b2t_engine* e, const char** names, float* ms, 
 
 /* Unicode class tables the scan kernels use, one byte per code point (0x110000 entries):
  * scheme 0 (Oniguruma: ByteLevel / Split): 1 = \p{L}, 2 = \p{N}, 3 = \s, 0 = other;
- * scheme 1 (Rust regex: Whitespace):       1 = \w, 3 = \s, 0 = other.  Host only, no device needed. */
+ * scheme 1 (Rust regex: Whitespace):       1 = \w, 3 = \s, 0 = other;
+ * scheme 2 (BertPreTokenizer):              1 = word character, 3 = whitespace (removed), 0 = punctuation (isolated).
+ * Host only, no device needed. */
 int b2t_unicode_class_table(int scheme, uint8_t* out);
+
+/* The BertNormalizer table the device kernels use, for inspection (host only, no device needed): the UTF-8 image of every
+ * code point under `flags` (B2T_NORM_* steps), images back to back in `pool` (capacity `cap`, 5 MB is enough), code point c =
+ * pool[off[c] .. off[c+1]) with off holding 0x110001 entries; an empty image = the character is dropped. */
+int b2t_bert_normalizer_images(int32_t flags, uint8_t* pool, size_t cap, uint32_t* off);
 
 /* Thread-local message of the last failing call. */
 const char* b2t_last_error(void);

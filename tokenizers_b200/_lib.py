@@ -18,7 +18,7 @@ SYMBOLS = ["b2t_engine_create", "b2t_engine_destroy", "b2t_engine_set_added_toke
            "b2t_result_attention_mask", "b2t_result_row_lengths",
            "b2t_result_n_tokens", "b2t_result_n_docs", "b2t_result_on_device", "b2t_result_ids", "b2t_result_offsets",
            "b2t_result_word_ids", "b2t_result_row_ptr", "b2t_result_free", "b2t_host_alloc", "b2t_host_free",
-           "b2t_engine_set_profiling", "b2t_engine_last_kernels", "b2t_unicode_class_table", "b2t_last_error", "b2t_version"]
+           "b2t_engine_set_profiling", "b2t_engine_last_kernels", "b2t_unicode_class_table", "b2t_bert_normalizer_images", "b2t_last_error", "b2t_version"]
 
 
 class Config(ctypes.Structure):
@@ -81,6 +81,7 @@ def lib():
     L.b2t_engine_set_profiling.argtypes = [vp, i32]
     L.b2t_engine_last_kernels.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), i32]
     L.b2t_unicode_class_table.argtypes = [i32, vp]
+    L.b2t_bert_normalizer_images.argtypes = [i32, vp, ctypes.c_size_t, vp]
     L.b2t_last_error.restype = ctypes.c_char_p
     L.b2t_version.restype = ctypes.c_char_p
     _lib = L

@@ -52,8 +52,33 @@ extern "C" int b2t_debug_k1(uint32_t* out, size_t words) {
   return (int)cudaMemcpyFromSymbol(out, b2t::g_k1_dbg, words * 4);
 }
 #endif
+extern "C" int b2t_bert_normalizer_images(int32_t flags, uint8_t* pool, size_t cap, uint32_t* off) {
+  if (!pool || !off) return fail(B2T_ERR_INVALID, "b2t_bert_normalizer_images: null argument");
+  NormHost nh;
+  build_bert_norm((flags & B2T_NORM_CLEAN_TEXT) != 0, (flags & B2T_NORM_CHINESE_CHARS) != 0, (flags & B2T_NORM_STRIP_ACCENTS) != 0, (flags & B2T_NORM_LOWERCASE) != 0, &nh);
+  size_t pos = 0;
+  for (uint32_t c = 0; c < 0x110000; ++c) {
+    off[c] = (uint32_t)pos;
+    const uint32_t e = nh.ent[(size_t)nh.blk[c >> 7] * 128 + (c & 127)], kind = e & 3u;
+    if (kind == NORM_REMOVE || (c >= 0xD800 && c <= 0xDFFF)) continue;
+    uint8_t tmp[4]; const uint8_t* src = tmp; size_t len;
+    if (kind == NORM_STRING) { src = nh.pool.data() + (e >> 8); len = (e >> 2) & 63u; }
+    else {   // the character itself
+      if (c < 0x80) { tmp[0] = (uint8_t)c; len = 1; }
+      else if (c < 0x800) { tmp[0] = 0xC0 | (c >> 6); tmp[1] = 0x80 | (c & 63); len = 2; }
+      else if (c < 0x10000) { tmp[0] = 0xE0 | (c >> 12); tmp[1] = 0x80 | ((c >> 6) & 63); tmp[2] = 0x80 | (c & 63); len = 3; }
+      else { tmp[0] = 0xF0 | (c >> 18); tmp[1] = 0x80 | ((c >> 12) & 63); tmp[2] = 0x80 | ((c >> 6) & 63); tmp[3] = 0x80 | (c & 63); len = 4; }
+    }
+    if (pos + len > cap) return fail(B2T_ERR_TOO_LARGE, "b2t_bert_normalizer_images: pool too small");
+    memcpy(pool + pos, src, len);
+    pos += len;
+  }
+  off[0x110000] = (uint32_t)pos;
+  return B2T_OK;
+}
+
 extern "C" int b2t_unicode_class_table(int scheme, uint8_t* out) {
-  if (!out || (scheme != 0 && scheme != 1)) return fail(B2T_ERR_INVALID, "b2t_unicode_class_table: bad arguments");
+  if (!out || (scheme != 0 && scheme != 1 && scheme != 2)) return fail(B2T_ERR_INVALID, "b2t_unicode_class_table: bad arguments");
   unicode_class_table(scheme, out);
   return B2T_OK;
 }
