@@ -1,5 +1,7 @@
-// engine.cu -- the C ABI of include/b2t.h: engine construction, the device pipeline (K0 doc_mark -> K1 pretok_scan ->
-// K1b page_scan -> K2 model_tile) and the chunked host<->device pipeline of b2t_encode_batch.
+// engine.cu -- the C ABI of include/b2t.h: engine construction, the device pipeline ([N1-N2 BertNormalizer pre-pass ->]
+// K0 doc_mark -> [A1-A2 added-token extraction ->] K1 pretok_scan -> K1b page_scan -> [K1c / K2L long pre-tokens ->]
+// K2 model_tile -> K2b scan + compaction [-> N3 offsets back to the original text] [-> dense rows]) and the chunked
+// host<->device pipeline of b2t_encode_batch / b2t_encode_batch_dense.
 //
 // This is the batch-level seam of the reference (tokenizer/mod.rs:1337-1401 encode_batch*): one call = one batch,
 // results in input order, any failure fails the whole batch.  There is NO CPU implementation behind these entry
