@@ -39,3 +39,25 @@ def test_scan_kernel_registers_and_instruction_budget():
     body = sass.split("Function : _ZN3b2t18pretok_scan_kernelILi0ELi256E", 1)[1].split("Function : ", 1)[0]
     n = len(re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s", body, flags=re.M))
     assert 1000 < n <= 4300, f"{n} static instructions (round 1: 4096)"
+
+
+def test_streaming_scan_and_prepass_kernels():
+    """Round 2: the streaming scan (the kernel the roofline figure is about) must stay at 8 blocks of 128 threads per SM without
+    local memory and must not grow -- it runs at the ALU-pipe roofline of its instruction count (profiles/k1_experiments_r02.md);
+    the added-token variants and the Bert variant share the budget; the normalizer pre-pass keeps 6 blocks of 256 threads."""
+    res = _res()
+    lean = {k: v for k, v in res.items() if "pretok_lean_kernel" in k}
+    assert len(lean) >= 8, sorted(lean)          # GPT-2, Whitespace, no-regex, Bert, each with and without added-token bitmaps
+    for k, (reg, stack, shared) in lean.items():
+        assert reg <= 64 and stack == 0 and shared <= 1024, (k, reg, stack, shared)
+    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    body = sass.split("Function : _ZN3b2t18pretok_lean_kernelILi0ELb0E", 1)[1].split("Function : ", 1)[0]
+    n = len(re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s", body, flags=re.M))
+    assert 500 < n <= 1000, f"{n} static instructions in the GPT-2 streaming scan (r02d: 944)"
+    assert len(re.findall(r"\bLOP3\b", body)) <= 290, "boolean operations of the scan (r02d: 274 static, 255 executed per KB)"
+    reg, stack, shared = next(v for k, v in res.items() if "norm_write_kernel" in k)
+    assert reg <= 40 and shared * 6 <= 233472, "6 blocks x 256 threads per SM"
+    reg, stack, shared = next(v for k, v in res.items() if "norm_count_kernel" in k)
+    assert reg <= 32
+    for name in ("added_scan_kernel", "added_resolve_kernel", "dense_rows_kernel", "norm_offsets_kernel"):
+        assert any(name in k for k in res), name
