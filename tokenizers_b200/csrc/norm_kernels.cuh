@@ -75,7 +75,9 @@ __device__ __forceinline__ int norm_block_scan(int v, int* s_warp, int* total) {
 // What a thread learns about its 8 bytes: per byte the length of the image of the character that starts there
 // (6 bits each, 63 = "not a character start"), the table entry of the non-ASCII ones is looked up again when writing.
 constexpr uint32_t NORM_NOT_LEAD = 63u;
-constexpr int NORM_MAX_OUT = 3 * PAGE;   // an image is at most 3x its character (Hangul syllable -> three jamo)
+// An image is at most 3x its character (Hangul syllable -> three jamo; host_tables.cu checks every entry), and a page emits
+// the whole image of its last character even if up to 3 of that character's bytes lie in the next page.
+constexpr int NORM_MAX_OUT = 3 * (PAGE + 3) + 7;
 
 struct NormChunk {
   uint32_t w0, w1, w2;     // the thread's 8 bytes and the 4 behind them (little endian)
