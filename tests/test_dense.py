@@ -73,6 +73,23 @@ def test_oracle_dense_matches_wheel(name):
         assert np.array_equal(got[2], exp[1].sum(axis=1))
 
 
+def _golden():
+    import gzip
+    return json.loads(gzip.open(os.path.join(helpers.GOLDEN, "golden_dense.json.gz")).read().decode("utf-8"))
+
+
+@pytest.mark.parametrize("name", list(TEMPLATES))
+def test_oracle_dense_matches_golden(name):
+    """the same restatement against committed vectors of the wheel (no wheel needed)"""
+    g = _golden()
+    js = tokenizer_json(name)
+    ids, _, _, rp = orc.Oracle(js).encode_batch(g["docs"])
+    for k, (tr, pd) in enumerate(SETTINGS):
+        c = g["cases"][f"{name}/{k}"]
+        got = orc.dense_rows(ids, rp, **spec_of(js, tr, pd))
+        assert list(got[0].shape) == c["shape"] and got[0].reshape(-1).tolist() == c["ids"] and got[2].tolist() == c["lengths"], (name, k)
+
+
 def _apply(tok, tr, pd):
     tok.no_truncation(); tok.no_padding()
     if tr:
@@ -97,6 +114,12 @@ def test_gpu_dense_matches_oracle_and_wheel(name):
         if tk is not None:
             w = wheel_dense(js, docs, tr, pd)
             assert np.array_equal(got["input_ids"], w[0]) and np.array_equal(got["attention_mask"], w[1]), (name, tr, pd, "wheel")
+    g = _golden()   # and the committed vectors of the wheel
+    for k, (tr, pd) in enumerate(SETTINGS):
+        _apply(tok, tr, pd)
+        got = tok.encode_batch_dense(g["docs"])
+        c = g["cases"][f"{name}/{k}"]
+        assert list(got["input_ids"].shape) == c["shape"] and got["input_ids"].reshape(-1).tolist() == c["ids"] and got["lengths"].tolist() == c["lengths"], (name, k, "golden")
     # without special tokens
     _apply(tok, *SETTINGS[0])
     got = tok.encode_batch_dense(docs, add_special_tokens=False, want_mask=False)
